@@ -1,0 +1,110 @@
+"""ctypes binding of libegm_b200.so -- the only door to the CUDA kernels.
+
+Prototypes are parsed from include/egm_b200.h, so the header is the single source of
+truth for the C ABI (tests check that every declared symbol is exported).  There is no
+CPU fallback: a missing library or a non-sm_100 device raises immediately.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from typing import Dict, List, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+HEADER = os.path.join(_ROOT, "include", "egm_b200.h")
+LIB_PATH = os.path.join(_HERE, "libegm_b200.so")
+
+F32, BF16 = 0, 1
+DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16}
+
+_CT = {"int": ctypes.c_int, "long long": ctypes.c_longlong, "float": ctypes.c_float, "double": ctypes.c_double}
+
+
+def parse_header(path: str = HEADER) -> Dict[str, Tuple[object, List[object]]]:
+    """{symbol: (restype, [argtypes])} for every function declared in the header."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    src = re.sub(r"^\s*#.*$", " ", src, flags=re.M)
+    protos = {}
+    for m in re.finditer(r"(const\s+char\s*\*|long\s+long|int)\s+(egm_\w+)\s*\(([^)]*)\)\s*;", src):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        restype = ctypes.c_char_p if "char" in ret else _CT[" ".join(ret.split())]
+        argtypes = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                if "*" in a:
+                    argtypes.append(ctypes.c_void_p)
+                else:
+                    base = " ".join(a.split()[:-1]).replace("const ", "").replace("unsigned ", "")
+                    argtypes.append(_CT[base])
+        protos[name] = (restype, argtypes)
+    return protos
+
+
+class _Lib:
+    def __init__(self):
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(egm-unet_b200/csrc/build.sh). There is no CPU / PyTorch fallback.")
+        self.cdll = ctypes.CDLL(LIB_PATH)
+        self.protos = parse_header()
+        self.fn = {}
+        for name, (restype, argtypes) in self.protos.items():
+            f = getattr(self.cdll, name)          # AttributeError if the .so lacks a declared symbol
+            f.restype, f.argtypes = restype, argtypes
+            self.fn[name] = f
+        v = self.fn["egm_abi_version"]()
+        if v != 1:
+            raise RuntimeError(f"libegm_b200 ABI version {v} != 1")
+        self.device_checked = False
+
+    def last_error(self) -> str:
+        return (self.fn["egm_last_error"]() or b"").decode()
+
+
+_lib = None
+
+
+def lib() -> _Lib:
+    global _lib
+    if _lib is None:
+        _lib = _Lib()
+    return _lib
+
+
+def _conv_arg(a):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        return a.data_ptr()
+    return a
+
+
+def call(name: str, *args):
+    """Call an int-returning entry point on the current CUDA stream; raise RuntimeError on failure."""
+    L = lib()
+    if not L.device_checked:
+        if not torch.cuda.is_available():
+            raise RuntimeError("egm_b200: no CUDA device; this package has no CPU path")
+        if L.fn["egm_device_check"]() != 0:
+            raise RuntimeError("egm_b200: " + L.last_error())
+        L.device_checked = True
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = L.fn["egm_" + name](*[_conv_arg(a) for a in args], stream)
+    if rc != 0:
+        raise RuntimeError(f"egm_{name} failed ({rc}): {L.last_error()}")
+    LAUNCH_COUNTER[0] += 1
+
+
+def query(name: str, *args):
+    """Call a host-only helper (no stream argument, returns its value)."""
+    return lib().fn["egm_" + name](*args)
+
+
+# number of C-ABI compute calls issued (bench.py reports launches per step from this)
+LAUNCH_COUNTER = [0]

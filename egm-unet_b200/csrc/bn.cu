@@ -1,0 +1,263 @@
+// BatchNorm2d (training statistics / apply / backward) fused with the activation that follows it.
+// Reference semantics: nn.BatchNorm2d as used by DoubleConv (src/EGM-UNet.py:44-55), BasicConv
+// (:958-975, momentum 0.01) and EdgeAwareFeatureEnhancer (:872-886); see SURVEY.md App. A.
+// All kernels are HBM-bound: one pass per tensor, 16-byte vector accesses, per-channel fp64 atomics.
+#include "common.cuh"
+
+// act: 0 none, 1 relu, 2 sigmoid.   mode: 0 plain, 1 edge gate (y = s*aux + aux), 2 residual (y = relu(alpha*aux + bn))
+struct BnArgs {
+  const float* scale; const float* shift; const float* mean; const float* rstd; const float* coef;
+  int act, mode; float alpha;
+};
+
+// ---------------------------------------------------------------- per-channel reduction skeleton
+// blockDim.x = CV * rpi (CV = C/V channel vectors, rpi rows per iteration). Each thread owns one
+// channel vector; partials are combined through shared memory, then one fp64 atomic per channel.
+template <int V, int K, typename F>
+__device__ __forceinline__ void chan_reduce(F f, long long M, int C, double* __restrict__ out, float* smem) {
+  const int CV = C / V;
+  const int rpi = blockDim.x / CV;
+  const int cv = threadIdx.x % CV, r = threadIdx.x / CV;
+  float acc[K][V];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[k][j] = 0.f;
+  if (r < rpi)
+    for (long long m = (long long)blockIdx.x * rpi + r; m < M; m += (long long)gridDim.x * rpi) f(m, cv * V, acc);
+  // smem layout [rpi][K][C]
+  if (r < rpi) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int j = 0; j < V; ++j) smem[((size_t)r * K + k) * C + cv * V + j] = acc[k][j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) {
+    float s = 0.f;
+    for (int rr = 0; rr < rpi; ++rr) s += smem[(size_t)rr * K * C + i];
+    atomicAdd(out + i, (double)s);
+  }
+}
+static inline int reduce_threads(int C, int V) { int CV = C / V; int rpi = 256 / CV; if (rpi < 1) rpi = 1; return CV * rpi; }
+static inline int reduce_blocks(long long M, int threads, int C, int V) {
+  int rpi = threads / (C / V);
+  long long b = (M + (long long)rpi * 8 - 1) / ((long long)rpi * 8);
+  long long cap = (long long)egm_num_sms() * 4;
+  if (b > cap) b = cap; if (b < 1) b = 1; return (int)b;
+}
+
+// ---------------------------------------------------------------- forward statistics
+template <typename T, int V>
+struct StatsF {
+  const T* x; long long cs, co;
+  __device__ void operator()(long long m, int c, float (&acc)[2][V]) const {
+    FVec<V> a = ldv<V>(x + m * cs + co + c);
+#pragma unroll
+    for (int j = 0; j < V; ++j) { acc[0][j] += a.v[j]; acc[1][j] += a.v[j] * a.v[j]; }
+  }
+};
+template <typename T, int V>
+__global__ void k_bn_stats(StatsF<T, V> f, long long M, int C, double* out) {
+  extern __shared__ float smem[];
+  chan_reduce<V, 2>(f, M, C, out, smem);
+}
+extern "C" int egm_bn_stats(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, void* stream) {
+  EGM_REQUIRE(C >= 1 && C <= 2048, EGM_E_SHAPE, "bn_stats: C=%d unsupported", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+  if (M == 0) return EGM_OK;
+  int v = egm_pick_vec(C, cstride, coff);
+  int threads = reduce_threads(C, v); size_t sm = (size_t)(threads / (C / v)) * 2 * C * sizeof(float);
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_stats<T, V><<<reduce_blocks(M, threads, C, v), threads, sm, st>>>(
+      StatsF<T, V>{(const T*)x, cstride, coff}, M, C, sums))));
+  EGM_LAUNCH_CHECK("bn_stats"); return EGM_OK;
+}
+
+// sums [2][C] -> scale/shift/mean/rstd (+ running-stat update).  training=0: use the running stats.
+__global__ void k_bn_finalize(const double* __restrict__ sums, double M, const float* __restrict__ gamma, const float* __restrict__ beta,
+                              float* running_mean, float* running_var, long long* nbt, float momentum, float eps, int training, int C,
+                              float* scale, float* shift, float* mean_o, float* rstd_o) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && nbt) *nbt += 1;
+  if (c >= C) return;
+  double mean, var;
+  if (training) {
+    mean = sums[c] / M; var = sums[C + c] / M - mean * mean; if (var < 0) var = 0;
+    if (running_mean) {
+      double unb = M > 1 ? var * M / (M - 1) : var;
+      running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+      running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+    }
+  } else { mean = running_mean[c]; var = running_var[c]; }
+  double rstd = 1.0 / sqrt(var + (double)eps);
+  float sc = (float)(gamma[c] * rstd);
+  scale[c] = sc; shift[c] = (float)(beta[c] - mean * gamma[c] * rstd);
+  if (mean_o) mean_o[c] = (float)mean;
+  if (rstd_o) rstd_o[c] = (float)rstd;
+}
+extern "C" int egm_bn_finalize(const double* sums, long long M, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                               long long* num_batches_tracked, float momentum, float eps, int training, int C,
+                               float* scale, float* shift, float* mean, float* rstd, void* stream) {
+  k_bn_finalize<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, (double)M, gamma, beta, running_mean, running_var, num_batches_tracked,
+                                                                momentum, eps, training, C, scale, shift, mean, rstd);
+  EGM_LAUNCH_CHECK("bn_finalize"); return EGM_OK;
+}
+
+// ---------------------------------------------------------------- apply (+activation / gate / residual)
+template <typename T, int V>
+__global__ void k_bn_act_fwd(const T* __restrict__ z, long long zcs, long long zco, BnArgs a, const T* __restrict__ aux, T* __restrict__ y,
+                             long long ycs, long long yco, long long M, int CV) {
+  long long total = M * CV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long m = i / CV; int c = (int)(i - m * CV) * V;
+    FVec<V> zv = ldv<V>(z + m * zcs + zco + c), sc = ldv<V>(a.scale + c), sh = ldv<V>(a.shift + c), xv, o;
+    if (a.mode != 0) xv = ldv<V>(aux + m * (long long)(CV * V) + c);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float t = fmaf(zv.v[j], sc.v[j], sh.v[j]);
+      if (a.mode == 0) o.v[j] = a.act == 1 ? fmaxf(t, 0.f) : (a.act == 2 ? sigmoidf_(t) : t);
+      else if (a.mode == 1) { float s = sigmoidf_(t); o.v[j] = fmaf(s, xv.v[j], xv.v[j]); }
+      else o.v[j] = fmaxf(fmaf(a.alpha, xv.v[j], t), 0.f);
+    }
+    stv<V>(y + m * ycs + yco + c, o);
+  }
+}
+extern "C" int egm_bn_act_fwd(const void* z, long long z_cstride, long long z_coff, const float* scale, const float* shift, int act, int mode,
+                              const void* aux, float alpha, void* y, long long y_cstride, long long y_coff, int dtype, long long M, int C, void* stream) {
+  if (M * C == 0) return EGM_OK;
+  EGM_REQUIRE(mode == 0 || aux, EGM_E_BADARG, "bn_act_fwd: mode %d needs aux", mode);
+  int v = egm_pick_vec(C, z_cstride, z_coff), v2 = egm_pick_vec(C, y_cstride, y_coff); if (v2 < v) v = v2;
+  BnArgs a{scale, shift, nullptr, nullptr, nullptr, act, mode, alpha};
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_act_fwd<T, V><<<egm_grid_for(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const T*)z, z_cstride, z_coff, a, (const T*)aux, (T*)y, y_cstride, y_coff, M, C / V))));
+  EGM_LAUNCH_CHECK("bn_act_fwd"); return EGM_OK;
+}
+
+// ---------------------------------------------------------------- backward
+// g = dL/d(bn output) given dy = dL/d(block output); also the gradient routed to aux.
+__device__ __forceinline__ void bn_local_grad(const BnArgs& a, float dy, float z, float sc, float sh, float aux, float& g, float& daux) {
+  float t = fmaf(z, sc, sh);
+  daux = 0.f;
+  if (a.mode == 0) {
+    if (a.act == 1) g = t > 0.f ? dy : 0.f;
+    else if (a.act == 2) { float s = sigmoidf_(t); g = dy * s * (1.f - s); }
+    else g = dy;
+  } else if (a.mode == 1) {
+    float s = sigmoidf_(t); g = dy * aux * s * (1.f - s); daux = dy * (1.f + s);
+  } else {
+    float m = fmaf(a.alpha, aux, t) > 0.f ? dy : 0.f; g = m; daux = a.alpha * m;
+  }
+}
+template <typename T, int V>
+struct BwdRedF {
+  const T* dy; long long dcs, dco; const T* z; const T* aux; BnArgs a; int C;
+  __device__ void operator()(long long m, int c, float (&acc)[2][V]) const {
+    FVec<V> d = ldv<V>(dy + m * dcs + dco + c), zv = ldv<V>(z + m * (long long)C + c), sc = ldv<V>(a.scale + c), sh = ldv<V>(a.shift + c),
+            mu = ldv<V>(a.mean + c), rs = ldv<V>(a.rstd + c), xv;
+    if (a.mode != 0) xv = ldv<V>(aux + m * (long long)C + c);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float g, da; bn_local_grad(a, d.v[j], zv.v[j], sc.v[j], sh.v[j], a.mode ? xv.v[j] : 0.f, g, da);
+      acc[0][j] += g; acc[1][j] += g * (zv.v[j] - mu.v[j]) * rs.v[j];
+    }
+  }
+};
+template <typename T, int V>
+__global__ void k_bn_bwd_reduce(BwdRedF<T, V> f, long long M, int C, double* out) {
+  extern __shared__ float smem[];
+  chan_reduce<V, 2>(f, M, C, out, smem);
+}
+extern "C" int egm_bn_act_bwd_reduce(const void* dy, long long dy_cstride, long long dy_coff, const void* z, const float* scale, const float* shift,
+                                     const float* mean, const float* rstd, int act, int mode, const void* aux, float alpha, int dtype, long long M, int C,
+                                     double* sums, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+  if (M == 0) return EGM_OK;
+  int v = egm_pick_vec(C, dy_cstride, dy_coff);
+  int threads = reduce_threads(C, v); size_t sm = (size_t)(threads / (C / v)) * 2 * C * sizeof(float);
+  BnArgs a{scale, shift, mean, rstd, nullptr, act, mode, alpha};
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_bwd_reduce<T, V><<<reduce_blocks(M, threads, C, v), threads, sm, st>>>(
+      BwdRedF<T, V>{(const T*)dy, dy_cstride, dy_coff, (const T*)z, (const T*)aux, a, C}, M, C, sums))));
+  EGM_LAUNCH_CHECK("bn_act_bwd_reduce"); return EGM_OK;
+}
+
+// sums -> coef[0][c] = gamma*rstd, coef[1][c] = sum(g)/M, coef[2][c] = sum(g*xhat)/M ; dgamma, dbeta
+__global__ void k_bn_bwd_finalize(const double* __restrict__ sums, double M, const float* __restrict__ gamma, const float* __restrict__ rstd, int C,
+                                  float* coef, float* dgamma, float* dbeta, int training) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double sg = sums[c], sgx = sums[C + c];
+  coef[c] = gamma[c] * rstd[c];
+  coef[C + c] = training ? (float)(sg / M) : 0.f;
+  coef[2 * C + c] = training ? (float)(sgx / M) : 0.f;
+  if (dgamma) dgamma[c] = (float)sgx;
+  if (dbeta) dbeta[c] = (float)sg;
+}
+extern "C" int egm_bn_bwd_finalize(const double* sums, long long M, const float* gamma, const float* rstd, int C, float* coef, float* dgamma,
+                                   float* dbeta, int training, void* stream) {
+  k_bn_bwd_finalize<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, (double)M, gamma, rstd, C, coef, dgamma, dbeta, training);
+  EGM_LAUNCH_CHECK("bn_bwd_finalize"); return EGM_OK;
+}
+
+template <typename T, int V>
+__global__ void k_bn_bwd_apply(const T* __restrict__ dy, long long dcs, long long dco, const T* __restrict__ z, const T* __restrict__ aux, BnArgs a,
+                               T* __restrict__ dz, T* __restrict__ daux, int daux_acc, long long M, int CV) {
+  const int C = CV * V;
+  long long total = M * CV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long m = i / CV; int c = (int)(i - m * CV) * V;
+    FVec<V> d = ldv<V>(dy + m * dcs + dco + c), zv = ldv<V>(z + m * (long long)C + c), sc = ldv<V>(a.scale + c), sh = ldv<V>(a.shift + c),
+            mu = ldv<V>(a.mean + c), rs = ldv<V>(a.rstd + c), k0 = ldv<V>(a.coef + c), k1 = ldv<V>(a.coef + C + c), k2 = ldv<V>(a.coef + 2 * C + c), xv, o, oa;
+    if (a.mode != 0) xv = ldv<V>(aux + m * (long long)C + c);
+    if (a.mode != 0 && daux && daux_acc) oa = ldv<V>(daux + m * (long long)C + c);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float g, da; bn_local_grad(a, d.v[j], zv.v[j], sc.v[j], sh.v[j], a.mode ? xv.v[j] : 0.f, g, da);
+      float xh = (zv.v[j] - mu.v[j]) * rs.v[j];
+      o.v[j] = k0.v[j] * (g - k1.v[j] - xh * k2.v[j]);
+      if (a.mode != 0) oa.v[j] = (daux_acc ? oa.v[j] : 0.f) + da;
+    }
+    stv<V>(dz + m * (long long)C + c, o);
+    if (a.mode != 0 && daux) stv<V>(daux + m * (long long)C + c, oa);
+  }
+}
+extern "C" int egm_bn_act_bwd_apply(const void* dy, long long dy_cstride, long long dy_coff, const void* z, const float* scale, const float* shift,
+                                    const float* mean, const float* rstd, const float* coef, int act, int mode, const void* aux, float alpha,
+                                    void* dz, void* daux, int daux_accumulate, int dtype, long long M, int C, void* stream) {
+  if (M * C == 0) return EGM_OK;
+  int v = egm_pick_vec(C, dy_cstride, dy_coff);
+  BnArgs a{scale, shift, mean, rstd, coef, act, mode, alpha};
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_bwd_apply<T, V><<<egm_grid_for(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const T*)dy, dy_cstride, dy_coff, (const T*)z, (const T*)aux, a, (T*)dz, (T*)daux, daux_accumulate, M, C / V))));
+  EGM_LAUNCH_CHECK("bn_act_bwd_apply"); return EGM_OK;
+}
+
+// ---------------------------------------------------------------- per-channel sum of a tensor (conv bias gradient)
+template <typename T, int V>
+struct SumF {
+  const T* x; long long cs, co;
+  __device__ void operator()(long long m, int c, float (&acc)[1][V]) const {
+    FVec<V> a = ldv<V>(x + m * cs + co + c);
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[0][j] += a.v[j];
+  }
+};
+template <typename T, int V>
+__global__ void k_chan_sum(SumF<T, V> f, long long M, int C, double* out) {
+  extern __shared__ float smem[];
+  chan_reduce<V, 1>(f, M, C, out, smem);
+}
+__global__ void k_d2f(const double* s, float* d, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) d[i] = (float)s[i]; }
+extern "C" int egm_channel_sum(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* scratch, float* out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(scratch, 0, sizeof(double) * C, st);
+  if (M > 0) {
+    int v = egm_pick_vec(C, cstride, coff);
+    int threads = reduce_threads(C, v); size_t sm = (size_t)(threads / (C / v)) * C * sizeof(float);
+    EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_chan_sum<T, V><<<reduce_blocks(M, threads, C, v), threads, sm, st>>>(
+        SumF<T, V>{(const T*)x, cstride, coff}, M, C, scratch))));
+  }
+  k_d2f<<<cdiv(C, 128), 128, 0, st>>>(scratch, out, C);
+  EGM_LAUNCH_CHECK("channel_sum"); return EGM_OK;
+}

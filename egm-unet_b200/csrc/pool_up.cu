@@ -1,0 +1,158 @@
+// Down-/up-sampling kernels of the encoder-decoder skeleton (HBM-bound, vectorised NHWC):
+//   MaxPool2d(2, stride 2)                 src/EGM-UNet.py:905-912, src/unet.py:21-26
+//   Upsample(x2, bilinear, align_corners) + F.pad + cat([skip, up])   src/EGM-UNet.py:927-949
+// The up-sample kernel writes straight into the concatenated tensor the following conv reads.
+#include "common.cuh"
+
+// ------------------------------------------------------------------ max pool 2x2 s2
+template <typename T, int V>
+__global__ void k_maxpool2_fwd(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int CV) {
+  const int Ho = H / 2, Wo = W / 2, C = CV * V;
+  long long total = (long long)N * Ho * Wo * CV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV); long long p = i / CV; int wo = (int)(p % Wo); long long q = p / Wo; int ho = (int)(q % Ho); int n = (int)(q / Ho);
+    const T* b = x + (((long long)n * H + 2 * ho) * W + 2 * wo) * C + cv * V;
+    FVec<V> a = ldv<V>(b), c1 = ldv<V>(b + C), c2 = ldv<V>(b + (long long)W * C), c3 = ldv<V>(b + (long long)W * C + C), o;
+#pragma unroll
+    for (int j = 0; j < V; ++j) o.v[j] = fmaxf(fmaxf(a.v[j], c1.v[j]), fmaxf(c2.v[j], c3.v[j]));
+    stv<V>(y + p * C + cv * V, o);
+  }
+}
+// gradient goes to the FIRST maximum in (h, w) scan order (ATen tie rule)
+template <typename T, int V>
+__global__ void k_maxpool2_bwd(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W, int CV, int accumulate) {
+  const int Ho = H / 2, Wo = W / 2, C = CV * V;
+  long long total = (long long)N * Ho * Wo * CV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV); long long p = i / CV; int wo = (int)(p % Wo); long long q = p / Wo; int ho = (int)(q % Ho); int n = (int)(q / Ho);
+    long long base = (((long long)n * H + 2 * ho) * W + 2 * wo) * C + cv * V;
+    long long off[4] = {0, C, (long long)W * C, (long long)W * C + C};
+    FVec<V> v[4], g = ldv<V>(dy + p * C + cv * V);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v[t] = ldv<V>(x + base + off[t]);
+    int arg[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float m = v[0].v[j]; int a = 0;
+#pragma unroll
+      for (int t = 1; t < 4; ++t) if (v[t].v[j] > m) { m = v[t].v[j]; a = t; }
+      arg[j] = a;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      FVec<V> o;
+      if (accumulate) o = ldv<V>(dx + base + off[t]);
+#pragma unroll
+      for (int j = 0; j < V; ++j) o.v[j] = (accumulate ? o.v[j] : 0.f) + (arg[j] == t ? g.v[j] : 0.f);
+      stv<V>(dx + base + off[t], o);
+    }
+  }
+}
+extern "C" int egm_maxpool2x2_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream) {
+  long long total = (long long)N * (H / 2) * (W / 2) * C;
+  if (total == 0) return EGM_OK;
+  int v = egm_pick_vec(C);
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_maxpool2_fwd<T, V><<<egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, N, H, W, C / V))));
+  EGM_LAUNCH_CHECK("maxpool2x2_fwd"); return EGM_OK;
+}
+extern "C" int egm_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int accumulate, int dtype, int N, int H, int W, int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t es = dtype == EGM_F32 ? 4 : 2;
+  if (!accumulate && ((H & 1) || (W & 1))) cudaMemsetAsync(dx, 0, (size_t)N * H * W * C * es, st);   // dropped trailing row/col gets no gradient
+  long long total = (long long)N * (H / 2) * (W / 2) * C;
+  if (total == 0) return EGM_OK;
+  int v = egm_pick_vec(C);
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_maxpool2_bwd<T, V><<<egm_grid_for(total / V, 256), 256, 0, st>>>((const T*)x, (const T*)dy, (T*)dx, N, H, W, C / V, accumulate))));
+  EGM_LAUNCH_CHECK("maxpool2x2_bwd"); return EGM_OK;
+}
+
+// ------------------------------------------------------------------ bilinear x2 (align_corners=True) + pad + concat
+struct UpGeom { int N, Hl, Wl, H, W, Cs, Cu, padt, padl; float sh, sw; };
+
+__device__ __forceinline__ void up_src(int o, int in, float scale, int& i0, int& ip, float& l0, float& l1) {
+  float src = scale * (float)o;               // ATen area_pixel_compute_source_index, align_corners=True
+  i0 = (int)src; ip = (i0 < in - 1) ? 1 : 0; l1 = src - (float)i0; l0 = 1.f - l1;
+}
+template <typename T, int V>
+__global__ void k_upcat_fwd(const T* __restrict__ skip, const T* __restrict__ low, T* __restrict__ out, UpGeom g) {
+  const int C = g.Cs + g.Cu, CV = C / V;
+  long long total = (long long)g.N * g.H * g.W * CV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % CV) * V; long long p = i / CV; int w = (int)(p % g.W); long long q = p / g.W; int h = (int)(q % g.H); int n = (int)(q / g.H);
+    FVec<V> o;
+    if (c < g.Cs) o = ldv<V>(skip + p * g.Cs + c);
+    else {
+      int cu = c - g.Cs, uh = h - g.padt, uw = w - g.padl;
+      if (uh < 0 || uh >= 2 * g.Hl || uw < 0 || uw >= 2 * g.Wl) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) o.v[j] = 0.f;
+      } else {
+        int h0, hp, w0, wp; float a0, a1, b0, b1;
+        up_src(uh, g.Hl, g.sh, h0, hp, a0, a1); up_src(uw, g.Wl, g.sw, w0, wp, b0, b1);
+        const T* r0 = low + (((long long)n * g.Hl + h0) * g.Wl + w0) * g.Cu + cu;
+        const T* r1 = r0 + (long long)hp * g.Wl * g.Cu;
+        FVec<V> v00 = ldv<V>(r0), v01 = ldv<V>(r0 + (long long)wp * g.Cu), v10 = ldv<V>(r1), v11 = ldv<V>(r1 + (long long)wp * g.Cu);
+#pragma unroll
+        for (int j = 0; j < V; ++j) o.v[j] = a0 * (b0 * v00.v[j] + b1 * v01.v[j]) + a1 * (b0 * v10.v[j] + b1 * v11.v[j]);
+      }
+    }
+    stv<V>(out + p * C + c, o);
+  }
+}
+// gather form of the transpose: each low-res pixel sums the (<= 6x6) high-res pixels that read it
+template <typename T, int V>
+__global__ void k_upcat_bwd_low(const T* __restrict__ dcat, T* __restrict__ dlow, UpGeom g) {
+  const int C = g.Cs + g.Cu, CV = g.Cu / V;
+  long long total = (long long)g.N * g.Hl * g.Wl * CV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int cu = (int)(i % CV) * V; long long p = i / CV; int wl = (int)(p % g.Wl); long long q = p / g.Wl; int hl = (int)(q % g.Hl); int n = (int)(q / g.Hl);
+    float wh[6], ww[6];
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+      int uh = 2 * hl - 2 + t, uw = 2 * wl - 2 + t; wh[t] = 0.f; ww[t] = 0.f;
+      if (uh >= 0 && uh < 2 * g.Hl) { int i0, ip; float l0, l1; up_src(uh, g.Hl, g.sh, i0, ip, l0, l1); if (i0 == hl) wh[t] += l0; if (i0 + ip == hl) wh[t] += l1; }
+      if (uw >= 0 && uw < 2 * g.Wl) { int i0, ip; float l0, l1; up_src(uw, g.Wl, g.sw, i0, ip, l0, l1); if (i0 == wl) ww[t] += l0; if (i0 + ip == wl) ww[t] += l1; }
+    }
+    FVec<V> acc;
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc.v[j] = 0.f;
+    for (int a = 0; a < 6; ++a) {
+      if (wh[a] == 0.f) continue;
+      int h = 2 * hl - 2 + a + g.padt; if (h < 0 || h >= g.H) continue;
+      for (int b = 0; b < 6; ++b) {
+        if (ww[b] == 0.f) continue;
+        int w = 2 * wl - 2 + b + g.padl; if (w < 0 || w >= g.W) continue;
+        FVec<V> d = ldv<V>(dcat + (((long long)n * g.H + h) * g.W + w) * C + g.Cs + cu);
+        float f = wh[a] * ww[b];
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc.v[j] = fmaf(f, d.v[j], acc.v[j]);
+      }
+    }
+    stv<V>(dlow + p * g.Cu + cu, acc);
+  }
+}
+static int up_geom(UpGeom& g, int N, int Hl, int Wl, int H, int W, int Cs, int Cu) {
+  int dy = H - 2 * Hl, dx = W - 2 * Wl;
+  EGM_REQUIRE(dy >= 0 && dx >= 0, EGM_E_SHAPE, "upsample_concat: skip %dx%d smaller than 2x low %dx%d", H, W, Hl, Wl);
+  g = UpGeom{N, Hl, Wl, H, W, Cs, Cu, dy / 2, dx / 2,
+             2 * Hl > 1 ? (float)(Hl - 1) / (float)(2 * Hl - 1) : 0.f, 2 * Wl > 1 ? (float)(Wl - 1) / (float)(2 * Wl - 1) : 0.f};
+  return EGM_OK;
+}
+// out[N,H,W,Cs+Cu] = cat([skip[N,H,W,Cs], pad(upsample2x(low[N,Hl,Wl,Cu]))])
+extern "C" int egm_upsample_concat_fwd(const void* skip, const void* low, void* out, int dtype, int N, int Hl, int Wl, int H, int W, int Cs, int Cu, void* stream) {
+  UpGeom g; int e = up_geom(g, N, Hl, Wl, H, W, Cs, Cu); if (e) return e;
+  long long total = (long long)N * H * W * (Cs + Cu);
+  if (total == 0) return EGM_OK;
+  int v = egm_pick_vec(Cs); int v2 = egm_pick_vec(Cu); if (v2 < v) v = v2;
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_upcat_fwd<T, V><<<egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream>>>((const T*)skip, (const T*)low, (T*)out, g))));
+  EGM_LAUNCH_CHECK("upsample_concat_fwd"); return EGM_OK;
+}
+// dlow[N,Hl,Wl,Cu] = transpose of the bilinear part applied to dcat[..., Cs:]; the skip part is a plain slice (egm_copy_slice).
+extern "C" int egm_upsample_concat_bwd_low(const void* dcat, void* dlow, int dtype, int N, int Hl, int Wl, int H, int W, int Cs, int Cu, void* stream) {
+  UpGeom g; int e = up_geom(g, N, Hl, Wl, H, W, Cs, Cu); if (e) return e;
+  long long total = (long long)N * Hl * Wl * Cu;
+  if (total == 0) return EGM_OK;
+  int v = egm_pick_vec(Cu, Cs + Cu, Cs);
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_upcat_bwd_low<T, V><<<egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dcat, (T*)dlow, g))));
+  EGM_LAUNCH_CHECK("upsample_concat_bwd_low"); return EGM_OK;
+}

@@ -1,0 +1,385 @@
+"""Tape engine: runs the EGM-UNet graph as a sequence of libegm_b200 kernels.
+
+No torch operator runs on the compute path -- torch supplies device memory (caching
+allocator), streams and parameter containers only.  Activations are NHWC tensors of the
+run dtype (bf16 in production, fp32 in check mode).  Every op appends a backward closure
+to the tape; `Tape.backward()` replays them in reverse, writing parameter gradients
+straight into the fp32 gradient slots handed out by `Ctx.grad_slot`.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import abi
+from .abi import call
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+MODE_PLAIN, MODE_EDGE_GATE, MODE_RESIDUAL = 0, 1, 2
+
+
+class Var:
+    """A dense NHWC activation [N,H,W,C] and (during backward) its gradient."""
+    __slots__ = ("t", "grad", "needs_grad")
+
+    def __init__(self, t: torch.Tensor, needs_grad: bool = True):
+        self.t = t
+        self.grad: Optional[torch.Tensor] = None
+        self.needs_grad = needs_grad
+
+    @property
+    def shape(self):
+        return self.t.shape
+
+    @property
+    def C(self) -> int:
+        return self.t.shape[3]
+
+    @property
+    def M(self) -> int:
+        s = self.t.shape
+        return s[0] * s[1] * s[2]
+
+    def grad_target(self, partial: bool = False):
+        """(tensor, accumulate_flag) to write this Var's gradient into.  partial=True: the writer
+        only touches a channel slice, so a fresh buffer is zero-filled."""
+        if self.grad is None:
+            self.grad = torch.empty_like(self.t)
+            if partial:
+                call("memset_zero", self.grad, self.grad.numel() * self.grad.element_size())
+                return self.grad, 1
+            return self.grad, 0
+        return self.grad, 1
+
+    def accum(self, g: torch.Tensor):
+        if self.grad is None:
+            self.grad = g
+        else:
+            call("axpby", self.grad, g, abi.DTYPE_CODE[g.dtype], g.numel(), 1.0, 1.0)
+
+
+class Ctx:
+    """One forward(/backward) execution."""
+
+    def __init__(self, dtype: torch.dtype, device, training: bool, record: bool, grad_slot: Optional[Callable] = None,
+                 use_tc: bool = True):
+        self.dtype = dtype
+        self.code = abi.DTYPE_CODE[dtype]
+        self.device = device
+        self.training = training          # BN uses batch statistics and updates running stats
+        self.record = record              # build the tape
+        self.tape: List[Callable] = []
+        self._grad_slot = grad_slot
+        self.use_tc = use_tc and dtype == torch.bfloat16
+        self.f32 = dict(dtype=torch.float32, device=device)
+
+    # ---- allocation helpers
+    def empty(self, *shape, dtype=None):
+        return torch.empty(shape, dtype=dtype or self.dtype, device=self.device)
+
+    def zeros_f32(self, n):
+        t = torch.empty(n, **self.f32)
+        call("memset_zero", t, n * 4)
+        return t
+
+    def f64(self, n):
+        return torch.empty(n, dtype=torch.float64, device=self.device)
+
+    def grad_slot(self, p: torch.Tensor) -> torch.Tensor:
+        """fp32 tensor (same shape as p) that receives dL/dp."""
+        return self._grad_slot(p)
+
+    def push(self, fn: Callable):
+        if self.record:
+            self.tape.append(fn)
+
+    def backward(self):
+        while self.tape:
+            self.tape.pop()()
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """parameter tensor -> raw fp32 data (detached)."""
+    return None if t is None else t.detach()
+
+
+# =========================================================================== layout
+def from_nchw(ctx: Ctx, x: torch.Tensor) -> Var:
+    n, c, h, w = x.shape
+    y = ctx.empty(n, h, w, c)
+    call("nchw_to_nhwc", x.contiguous(), y, ctx.code, n, c, h, w)
+    return Var(y, needs_grad=False)
+
+
+def to_nchw(ctx: Ctx, x: Var) -> torch.Tensor:
+    n, h, w, c = x.shape
+    y = torch.empty(n, c, h, w, **ctx.f32)
+    call("nhwc_to_nchw", x.t, y, ctx.code, n, c, h, w)
+    return y
+
+
+def seed_grad_from_nchw(ctx: Ctx, x: Var, g_nchw: torch.Tensor):
+    n, h, w, c = x.shape
+    g = ctx.empty(n, h, w, c)
+    call("nchw_to_nhwc", g_nchw.contiguous(), g, ctx.code, n, c, h, w)
+    x.accum(g)
+
+
+# =========================================================================== convolution
+class PackedConv:
+    """Per-forward packed weights of one nn.Conv2d (+ optional weight override for folded / merged kernels)."""
+
+    def __init__(self, ctx: Ctx, weight: torch.Tensor, groups: int, dilation: int, tc_ok: bool):
+        co, cig, kh, kw = weight.shape
+        self.co, self.cig, self.kh, self.kw, self.groups, self.dil = co, cig, kh, kw, groups, dilation
+        self.cin = cig * groups
+        self.tc = bool(tc_ok and ctx.use_tc and abi.query("conv2d_tc_supported", self.cin, co, kh, kw, dilation, groups))
+        n = weight.numel()
+        if self.tc:
+            self.wf = torch.empty(n, dtype=torch.bfloat16, device=ctx.device)
+            self.wd = torch.empty(n, dtype=torch.bfloat16, device=ctx.device) if ctx.record else None
+            call("pack_conv_weight_tc", weight, self.wf, self.wd, co, self.cin, kh, kw)
+        else:
+            self.wf = torch.empty(n, **ctx.f32)
+            self.wd = torch.empty(n, **ctx.f32) if ctx.record else None
+            call("pack_conv_weight", weight, self.wf, self.wd, co, cig, kh, kw, groups)
+
+
+def _conv_run(ctx, pk: PackedConv, x_t, x_cs, x_co, w, bias, y_t, y_cs, y_co, acc, n, h, wd_, cin, cout):
+    if pk.tc and x_cs == cin and x_co == 0 and y_cs == cout and y_co == 0 and not acc:
+        call("conv2d_tc", x_t, w, bias, y_t, n, h, wd_, cin, cout, pk.kh, pk.kw, pk.dil)
+    else:
+        assert not pk.tc, "tensor-core conv needs dense operands"
+        call("conv2d_direct", x_t, x_cs, x_co, w, bias, y_t, y_cs, y_co, acc, ctx.code, n, h, wd_, cin, cout, pk.kh, pk.kw, pk.dil, pk.groups)
+
+
+def conv2d(ctx: Ctx, x: Var, weight: torch.Tensor, bias: Optional[torch.Tensor], *, groups: int = 1, dilation: int = 1,
+           x_coff: int = 0, x_cin: Optional[int] = None, wgrad_sink: Optional[Callable] = None,
+           bgrad_sink: Optional[Callable] = None, tc_ok: bool = True) -> Var:
+    """y = conv2d(x[..., x_coff:x_coff+Cin], weight) + bias  (stride 1, "same" padding).  `weight` is the reference
+    [Cout, Cin/groups, kh, kw] fp32 parameter (or a derived tensor; then `wgrad_sink(dw)` receives its gradient)."""
+    n, h, w, ctot = x.shape
+    wparam, bparam = weight, bias          # gradient slots are keyed by the nn.Parameter objects
+    weight, bias = _p(weight), _p(bias)
+    co, cig, kh, kw = weight.shape
+    cin = cig * groups
+    assert (x_cin or ctot - x_coff) == cin, (x.shape, weight.shape, x_coff)
+    sliced = not (x_coff == 0 and cin == ctot)
+    pk = PackedConv(ctx, weight, groups, dilation, tc_ok and not sliced)
+    y = ctx.empty(n, h, w, co)
+    _conv_run(ctx, pk, x.t, ctot, x_coff, pk.wf, bias, y, co, 0, 0, n, h, w, cin, co)
+    out = Var(y)
+    if ctx.record:
+        def bwd():
+            dy = out.grad
+            out.grad = None
+            if dy is None:
+                return
+            # weight gradient
+            dwp = torch.empty(weight.numel(), **ctx.f32)
+            if pk.tc:
+                call("conv2d_wgrad_tc", x.t, dy, dwp, n, h, w, cin, co, kh, kw, dilation)
+            else:
+                call("conv2d_wgrad_direct", x.t, ctot, x_coff, dy, co, 0, dwp, ctx.code, n, h, w, cin, co, kh, kw, dilation, groups)
+            if wgrad_sink is not None:
+                dw = torch.empty_like(weight)
+                call("unpack_conv_wgrad", dwp, dw, co, cig, kh, kw, 0.0)
+                wgrad_sink(dw)
+            else:
+                call("unpack_conv_wgrad", dwp, ctx.grad_slot(wparam), co, cig, kh, kw, 0.0)
+            if bias is not None:
+                gb = torch.empty(co, **ctx.f32) if bgrad_sink is not None else ctx.grad_slot(bparam)
+                call("channel_sum", dy, ctx.code, n * h * w, co, co, 0, ctx.f64(co), gb)
+                if bgrad_sink is not None:
+                    bgrad_sink(gb)
+            if x.needs_grad:
+                gx, acc = x.grad_target(partial=sliced)
+                if pk.tc and not acc:
+                    call("conv2d_tc", dy, pk.wd, None, gx, n, h, w, co, cin, kh, kw, dilation)
+                elif pk.tc:
+                    tmp = torch.empty_like(x.t)
+                    call("conv2d_tc", dy, pk.wd, None, tmp, n, h, w, co, cin, kh, kw, dilation)
+                    call("axpby", gx, tmp, ctx.code, tmp.numel(), 1.0, 1.0)
+                else:
+                    call("conv2d_direct", dy, co, 0, pk.wd, None, gx, ctot, x_coff, acc, ctx.code, n, h, w, co, cin, kh, kw, dilation, groups)
+        ctx.push(bwd)
+    return out
+
+
+def conv_module(ctx: Ctx, x: Var, m: nn.Conv2d, **kw) -> Var:
+    d = m.dilation[0]
+    assert m.stride == (1, 1) and m.padding[0] == d * (m.kernel_size[0] - 1) // 2, "only stride-1 'same' convolutions"
+    return conv2d(ctx, x, m.weight, m.bias, groups=m.groups, dilation=d, **kw)
+
+
+# =========================================================================== batch norm (+ activation)
+def bn_act(ctx: Ctx, z: Var, bn: nn.BatchNorm2d, act: int, mode: int = MODE_PLAIN, aux: Optional[Var] = None, alpha: float = 0.0,
+           out: Optional[Var] = None, out_coff: int = 0) -> Var:
+    """y = act(BN(z)) (mode PLAIN) | sigmoid(BN(z))*aux + aux (EDGE_GATE) | relu(alpha*aux + BN(z)) (RESIDUAL).
+    With `out`, y is written into out[..., out_coff:out_coff+C] (a concat buffer) and `out` is returned."""
+    n, h, w, c = z.shape
+    M = n * h * w
+    gamma, beta = _p(bn.weight), _p(bn.bias)
+    scale, shift, mean, rstd = (torch.empty(c, **ctx.f32) for _ in range(4))
+    training = ctx.training or bn.running_mean is None
+    sums = ctx.f64(2 * c)
+    if training:
+        call("bn_stats", z.t, ctx.code, M, c, c, 0, sums)
+    mom = 0.1 if bn.momentum is None else bn.momentum
+    call("bn_finalize", sums, M, gamma, beta, bn.running_mean, bn.running_var, bn.num_batches_tracked if training else None,
+         float(mom), float(bn.eps), int(training), c, scale, shift, mean, rstd)
+    if out is None:
+        y = Var(ctx.empty(n, h, w, c))
+        ycs, yco = c, 0
+    else:
+        y, ycs, yco = out, out.C, out_coff
+    call("bn_act_fwd", z.t, c, 0, scale, shift, act, mode, aux.t if aux is not None else None, float(alpha), y.t, ycs, yco, ctx.code, M, c)
+    if ctx.record:
+        def bwd():
+            dy = y.grad
+            if dy is None:
+                return
+            if out is None:
+                y.grad = None
+            s2 = ctx.f64(2 * c)
+            auxt = aux.t if aux is not None else None
+            call("bn_act_bwd_reduce", dy, ycs, yco, z.t, scale, shift, mean, rstd, act, mode, auxt, float(alpha), ctx.code, M, c, s2)
+            coef = torch.empty(3 * c, **ctx.f32)
+            call("bn_bwd_finalize", s2, M, gamma, rstd, c, coef, ctx.grad_slot(bn.weight), ctx.grad_slot(bn.bias), int(training))
+            dz, _ = z.grad_target()
+            daux, dacc = (None, 0)
+            if aux is not None and aux.needs_grad:
+                daux, dacc = aux.grad_target()
+            call("bn_act_bwd_apply", dy, ycs, yco, z.t, scale, shift, mean, rstd, coef, act, mode, auxt, float(alpha), dz, daux, dacc,
+                 ctx.code, M, c)
+        ctx.push(bwd)
+    return y
+
+
+# =========================================================================== pooling / upsampling
+def maxpool2(ctx: Ctx, x: Var) -> Var:
+    n, h, w, c = x.shape
+    y = Var(ctx.empty(n, h // 2, w // 2, c))
+    call("maxpool2x2_fwd", x.t, y.t, ctx.code, n, h, w, c)
+    if ctx.record:
+        def bwd():
+            dy, y.grad = y.grad, None
+            if dy is None or not x.needs_grad:
+                return
+            gx, acc = x.grad_target()
+            call("maxpool2x2_bwd", x.t, dy, gx, acc, ctx.code, n, h, w, c)
+        ctx.push(bwd)
+    return y
+
+
+def upsample_concat(ctx: Ctx, low: Var, skip: Var) -> Var:
+    """cat([skip, pad(bilinear_x2(low))], channel)  -- Up.forward of the reference up to the DoubleConv."""
+    n, hl, wl, cu = low.shape
+    _, h, w, cs = skip.shape
+    out = Var(ctx.empty(n, h, w, cs + cu))
+    call("upsample_concat_fwd", skip.t, low.t, out.t, ctx.code, n, hl, wl, h, w, cs, cu)
+    if ctx.record:
+        def bwd():
+            d, out.grad = out.grad, None
+            if d is None:
+                return
+            gs, acc = skip.grad_target()
+            call("copy_slice", d, gs, ctx.code, n * h * w, cs, cs + cu, 0, cs, 0, acc)
+            gl = ctx.empty(n, hl, wl, cu)
+            call("upsample_concat_bwd_low", d, gl, ctx.code, n, hl, wl, h, w, cs, cu)
+            low.accum(gl)
+        ctx.push(bwd)
+    return out
+
+
+def copy_into(ctx: Ctx, src: Var, dst: Var, dst_coff: int, src_coff: int = 0, c: Optional[int] = None):
+    """dst[..., dst_coff:dst_coff+c] = src[..., src_coff:src_coff+c]; gradient flows back from dst.grad."""
+    c = c or src.C
+    M = src.M
+    call("copy_slice", src.t, dst.t, ctx.code, M, c, src.C, src_coff, dst.C, dst_coff, 0)
+    if ctx.record and src.needs_grad:
+        def bwd():
+            if dst.grad is None:
+                return
+            g, acc = src.grad_target(partial=(c != src.C))
+            call("copy_slice", dst.grad, g, ctx.code, M, c, dst.C, dst_coff, src.C, src_coff, acc)
+        ctx.push(bwd)
+
+
+def slice_channels(ctx: Ctx, src: Var, coff: int, c: int) -> Var:
+    n, h, w, _ = src.shape
+    out = Var(ctx.empty(n, h, w, c))
+    call("copy_slice", src.t, out.t, ctx.code, src.M, c, src.C, coff, c, 0, 0)
+    if ctx.record:
+        def bwd():
+            d, out.grad = out.grad, None
+            if d is None:
+                return
+            g, acc = src.grad_target(partial=True)
+            call("copy_slice", d, g, ctx.code, src.M, c, c, 0, src.C, coff, acc)
+        ctx.push(bwd)
+    return out
+
+
+def release_grad(ctx: Ctx, v: Var):
+    """Drop v.grad once every producer slice has consumed it (concat buffers)."""
+    if ctx.record:
+        def bwd():
+            v.grad = None
+        ctx.push(bwd)
+
+
+# =========================================================================== EdgeAwareFeatureEnhancer
+def edge_enhancer(ctx: Ctx, x: Var, m) -> Var:
+    """src/EGM-UNet.py:872-886: y = sigmoid(BN(conv1x1(x - avgpool3(x)))) * x + x."""
+    n, h, w, c = x.shape
+    e = Var(ctx.empty(n, h, w, c))
+    call("highpass3", x.t, e.t, 0, ctx.code, n, h, w, c)
+    if ctx.record:
+        def bwd():
+            d, e.grad = e.grad, None
+            if d is None:
+                return
+            gx, acc = x.grad_target()
+            call("highpass3", d, gx, acc, ctx.code, n, h, w, c)
+        ctx.push(bwd)
+    z = conv_module(ctx, e, m.weight_generator[0])
+    return bn_act(ctx, z, m.weight_generator[1], ACT_SIGMOID, MODE_EDGE_GATE, aux=x)
+
+
+# =========================================================================== MCALayer
+def mca_layer(ctx: Ctx, x: Var, m) -> Var:
+    """src/EGM-UNet.py:686-791 (see csrc/mca.cu)."""
+    n, h, w, c = x.shape
+    L = abi.query("mca_vec_len", n, h, w, c)
+    sums = ctx.f64(2 * L)
+    call("mca_stats", x.t, ctx.code, n, h, w, c, sums)
+    gates, avg, std = (torch.empty(L, **ctx.f32) for _ in range(3))
+    gh, gw, gc = m.h_cw, m.w_hc, m.c_hw
+    P = [_p(gh.weight), _p(gh.conv.weight), gh.conv.weight.shape[-1], _p(gw.weight), _p(gw.conv.weight), gw.conv.weight.shape[-1],
+         _p(gc.weight), _p(gc.conv.weight), gc.conv.weight.shape[-1]]
+    call("mca_gates", sums, n, h, w, c, *P, gates, avg, std)
+    y = Var(ctx.empty(n, h, w, c))
+    idx = torch.empty(n * h * w * c, dtype=torch.uint8, device=ctx.device) if ctx.record else None
+    call("mca_apply", x.t, gates, y.t, idx, ctx.code, n, h, w, c)
+    if ctx.record:
+        def bwd():
+            dy, y.grad = y.grad, None
+            if dy is None:
+                return
+            du, scratch = ctx.empty(n, h, w, c), ctx.empty(n, h, w, c)
+            call("mca_bwd_du", x.t, gates, dy, idx, scratch, du, ctx.code, n, h, w, c)
+            dG = ctx.f64(L)
+            call("mca_prod_sums", du, x.t, ctx.code, n, h, w, c, dG)
+            ca, cb = torch.empty(L, **ctx.f32), torch.empty(L, **ctx.f32)
+            call("mca_gates_bwd", dG, n, h, w, c, gates, avg, std, *P, ca, cb,
+                 ctx.grad_slot(gh.weight), ctx.grad_slot(gh.conv.weight), ctx.grad_slot(gw.weight), ctx.grad_slot(gw.conv.weight),
+                 ctx.grad_slot(gc.weight), ctx.grad_slot(gc.conv.weight))
+            call("mca_bwd_dx", du, x.t, gates, ca, cb, scratch, ctx.code, n, h, w, c)
+            x.accum(scratch)
+        ctx.push(bwd)
+    return y
+
+

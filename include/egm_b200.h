@@ -1,0 +1,131 @@
+/* libegm_b200 -- C ABI of the B200-native EGM-UNet hot path (sm_100a only).
+ *
+ * The reference (feiyeha/EGM-Unet) is pure PyTorch and has no FFI of its own: every GPU
+ * kernel it runs is an ATen / cuDNN / cuBLAS / cuFFT library kernel chosen by
+ * torch.nn.  Each entry point below names the reference call site(s)
+ * whose library kernels it replaces.  All functions:
+ *   - take plain device pointers + sizes (no torch types), NHWC activations of `dtype`
+ *     (EGM_F32 = fp32 check mode, EGM_BF16 = production), fp32 parameters/statistics;
+ *   - launch asynchronously on `stream` (a cudaStream_t), never allocate or free device
+ *     memory, never synchronise -- they are CUDA-graph capturable;
+ *   - return EGM_OK or a negative EGM_E_* code; egm_last_error() (thread-local) has the text.
+ * Channel-strided views: where a tensor has `*_cstride/*_coff` arguments, element (m, c)
+ * lives at ptr[m * cstride + coff + c] (used to read/write slices of concatenated tensors).
+ */
+#ifndef EGM_B200_H
+#define EGM_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EGM_ABI_VERSION 1
+enum { EGM_F32 = 0, EGM_BF16 = 1 };
+enum { EGM_OK = 0, EGM_E_BADARG = -1, EGM_E_SHAPE = -2, EGM_E_ALIGN = -3, EGM_E_ARCH = -4, EGM_E_LAUNCH = -5 };
+
+/* ---- library ---- */
+int egm_abi_version(void);
+const char* egm_last_error(void);
+int egm_device_check(void);                       /* fails unless the current device is CC 10.x */
+
+/* ---- layout / glue (replaces ATen copy_/cat/split/add kernels around src/EGM-UNet.py:1527-1541) ---- */
+int egm_nchw_to_nhwc(const float* x, void* y, int dtype, int N, int C, int H, int W, void* stream);
+int egm_nhwc_to_nchw(const void* x, float* y, int dtype, int N, int C, int H, int W, void* stream);
+int egm_copy_slice(const void* src, void* dst, int dtype, long long M, int C, long long s_cstride, long long s_coff,
+                   long long d_cstride, long long d_coff, int accumulate, void* stream);
+int egm_axpby(void* dst, const void* src, int dtype, long long n, float alpha, float beta, void* stream);
+int egm_memset_zero(void* p, long long bytes, void* stream);
+int egm_cast_from_f32(const float* src, void* dst, int dtype, long long n, void* stream);
+int egm_cast_to_f32(const void* src, float* dst, int dtype, long long n, int accumulate, void* stream);
+
+/* ---- convolution, CUDA-core implicit GEMM (nn.Conv2d stride 1 "same": src/EGM-UNet.py:49,52,962,1211-1215,1258-1292; cuDNN/cuBLAS today) ---- */
+int egm_pack_conv_weight(const float* w, float* wf, float* wd, int Cout, int Cin_g, int kh, int kw, int groups, void* stream);
+int egm_unpack_conv_wgrad(const float* dw_packed, float* dw, int Cout, int Cin_g, int kh, int kw, float beta, void* stream);
+int egm_kernel_embed(float* big, float* small_, long long CoCi, int kb, int ks, int mode, int accumulate, void* stream);
+int egm_conv2d_direct(const void* x, long long x_cstride, long long x_coff, const float* w_packed, const float* bias, void* y,
+                      long long y_cstride, long long y_coff, int accumulate, int dtype, int N, int H, int W, int Cin, int Cout,
+                      int kh, int kw, int dil, int groups, void* stream);
+int egm_conv2d_wgrad_direct(const void* x, long long x_cstride, long long x_coff, const void* dy, long long dy_cstride, long long dy_coff,
+                            float* dw_packed, int dtype, int N, int H, int W, int Cin, int Cout, int kh, int kw, int dil, int groups,
+                            void* stream);
+
+/* ---- convolution, tcgen05 tensor-core implicit GEMM, bf16 NHWC, TMA-staged (DoubleConv: src/EGM-UNet.py:44-55, src/unet.py:7-18) ---- */
+long long egm_conv2d_tc_workspace_bytes(int N, int H, int W, int Cin, int Cout, int kh, int dil);
+int egm_conv2d_tc_supported(int Cin, int Cout, int kh, int kw, int dil, int groups);
+int egm_pack_conv_weight_tc(const float* w, void* wf_bf16, void* wd_bf16, int Cout, int Cin, int kh, int kw, void* stream);
+int egm_conv2d_tc(const void* x, const void* w_packed_bf16, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
+                  int kh, int kw, int dil, void* stream);
+int egm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_packed, int N, int H, int W, int Cin, int Cout, int kh, int kw, int dil,
+                        void* stream);
+
+/* ---- BatchNorm2d (+ReLU / sigmoid gate / residual) (nn.BatchNorm2d: src/EGM-UNet.py:50,53,879,966; ATen native_batch_norm today) ---- */
+int egm_bn_stats(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, void* stream);
+int egm_bn_finalize(const double* sums, long long M, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                    long long* num_batches_tracked, float momentum, float eps, int training, int C,
+                    float* scale, float* shift, float* mean, float* rstd, void* stream);
+int egm_bn_act_fwd(const void* z, long long z_cstride, long long z_coff, const float* scale, const float* shift, int act, int mode,
+                   const void* aux, float alpha, void* y, long long y_cstride, long long y_coff, int dtype, long long M, int C, void* stream);
+int egm_bn_act_bwd_reduce(const void* dy, long long dy_cstride, long long dy_coff, const void* z, const float* scale, const float* shift,
+                          const float* mean, const float* rstd, int act, int mode, const void* aux, float alpha, int dtype, long long M, int C,
+                          double* sums, void* stream);
+int egm_bn_bwd_finalize(const double* sums, long long M, const float* gamma, const float* rstd, int C, float* coef, float* dgamma,
+                        float* dbeta, int training, void* stream);
+int egm_bn_act_bwd_apply(const void* dy, long long dy_cstride, long long dy_coff, const void* z, const float* scale, const float* shift,
+                         const float* mean, const float* rstd, const float* coef, int act, int mode, const void* aux, float alpha,
+                         void* dz, void* daux, int daux_accumulate, int dtype, long long M, int C, void* stream);
+int egm_channel_sum(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* scratch, float* out, void* stream);
+
+/* ---- down / up sampling (nn.MaxPool2d :908, nn.Upsample+F.pad+cat :931-947) ---- */
+int egm_maxpool2x2_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream);
+int egm_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int accumulate, int dtype, int N, int H, int W, int C, void* stream);
+int egm_upsample_concat_fwd(const void* skip, const void* low, void* out, int dtype, int N, int Hl, int Wl, int H, int W, int Cs, int Cu, void* stream);
+int egm_upsample_concat_bwd_low(const void* dcat, void* dlow, int dtype, int N, int Hl, int Wl, int H, int W, int Cs, int Cu, void* stream);
+
+/* ---- MCALayer (src/EGM-UNet.py:686-791, MCAGate :836-869) ---- */
+long long egm_mca_vec_len(int N, int H, int W, int C);
+long long egm_mca_vec_off_w(int N, int H);
+long long egm_mca_vec_off_c(int N, int H, int W);
+int egm_mca_stats(const void* x, int dtype, int N, int H, int W, int C, double* sums, void* stream);
+int egm_mca_prod_sums(const void* a, const void* b, int dtype, int N, int H, int W, int C, double* sums, void* stream);
+int egm_mca_gates(const double* sums, int N, int H, int W, int C, const float* w_h, const float* k_h, int ks_h, const float* w_w,
+                  const float* k_w, int ks_w, const float* w_c, const float* k_c, int ks_c, float* gates, float* avg, float* stdv, void* stream);
+int egm_mca_apply(const void* x, const float* gates, void* y, unsigned char* argidx, int dtype, int N, int H, int W, int C, void* stream);
+int egm_mca_bwd_du(const void* x, const float* gates, const void* dy, const unsigned char* argidx, void* E_scratch, void* du, int dtype, int N,
+                   int H, int W, int C, void* stream);
+int egm_mca_gates_bwd(const double* dG, int N, int H, int W, int C, const float* gates, const float* avg, const float* stdv, const float* w_h,
+                      const float* k_h, int ks_h, const float* w_w, const float* k_w, int ks_w, const float* w_c, const float* k_c, int ks_c,
+                      float* coef_a, float* coef_b, float* dw_h, float* dk_h, float* dw_w, float* dk_w, float* dw_c, float* dk_c, void* stream);
+int egm_mca_bwd_dx(const void* du, const void* x, const float* gates, const float* coef_a, const float* coef_b, void* dx, int dtype, int N,
+                   int H, int W, int C, void* stream);
+
+/* ---- edge enhancer / FusionConv attention / GRFB tail / RGA gating (src/EGM-UNet.py:872-886, 1171-1236, 1289-1323, 458-547) ---- */
+int egm_highpass3(const void* in, void* out, int accumulate, int dtype, int N, int H, int W, int C, void* stream);
+int egm_pixel_dot(const void* a, const void* b, const float* cvec, float* out, int dtype, int N, long long HW, int C, void* stream);
+int egm_sample_chan_dot(const void* a, const void* b, const float* pvec, float* out, int dtype, int N, long long HW, int C, void* stream);
+int egm_mul_pixel_gate(const void* a, const void* g, void* y, int dtype, long long M, int C, int Gc, int mode, void* stream);
+int egm_pixel_gate_bwd(const float* dot, const void* g, void* dg, int dtype, long long M, int Gc, int mode, void* stream);
+int egm_unary(const void* a, const void* b, const float* scalar_dev, void* y, int dtype, long long n, int op, void* stream);
+int egm_dot_all(const void* a, const void* b, float* out, int dtype, long long n, void* stream);
+int egm_chan_meanmax(const void* s, float* mm, unsigned char* amax, int dtype, long long M, int C, void* stream);
+int egm_sa_conv_fwd(const float* mm, const float* w, float* sa, int N, int H, int W, void* stream);
+int egm_sa_conv_bwd(const float* dsa, const float* sa, const float* mm, const float* w, float* dmm, float* dw, int N, int H, int W, void* stream);
+int egm_gap_gmp(const void* f, float* avg, float* mx, int* arg, void* scratch, int dtype, int N, long long HW, int C, void* stream);
+int egm_ca_mlp_fwd(const float* avg, const float* mx, const float* w0, const float* w2, float* ca, float* hid, int N, int C, int Cr, void* stream);
+int egm_ca_mlp_bwd(const float* dca, const float* ca, const float* avg, const float* mx, const float* hid, const float* w0, const float* w2,
+                   float* dw0, float* dw2, float* davg, float* dmx, int N, int C, int Cr, void* stream);
+int egm_fuse_mix_fwd(const void* f, const void* s, const float* sa, const float* ca, void* t, int dtype, int N, long long HW, int C, void* stream);
+int egm_fuse_mix_bwd_s(const void* dt, const float* sa, const float* ca, const float* dmm, const unsigned char* amax, void* ds, int dtype, int N,
+                       long long HW, int C, void* stream);
+int egm_fuse_df_finish(void* df, const void* dt, const float* davg, const float* dmx, const int* arg, int accumulate, int dtype, int N, long long HW, int C, void* stream);
+
+/* ---- loss, optimiser, metrics (train_utils/train_and_eval.py:7-19, dice_coefficient_loss.py, train.py:113-118, distributed_utils.py:76-167) ---- */
+long long egm_loss_workspace_bytes(int N, int C, int H, int W);
+int egm_loss_fwd_bwd(const float* logits, const long long* target, const float* class_weight, int N, int C, int H, int W, int ignore_index,
+                     int with_dice, float grad_scale, float* loss_out, float* dlogits, void* workspace, long long workspace_bytes, void* stream);
+int egm_sgd_step(float* params, const float* grads, float* momentum_buf, long long n, const float* hyper_dev, void* stream);
+int egm_eval_metrics(const float* logits, const long long* target, int N, int C, int H, int W, int ignore_index, long long* confmat,
+                     double* dice_acc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGM_B200_H */
