@@ -95,15 +95,43 @@ def call(name: str, *args):
             raise RuntimeError("egm_b200: " + L.last_error())
         L.device_checked = True
     stream = torch.cuda.current_stream().cuda_stream
+    if _PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = L.fn["egm_" + name](*[_conv_arg(a) for a in args], stream)
     if rc != 0:
         raise RuntimeError(f"egm_{name} failed ({rc}): {L.last_error()}")
+    if _PROFILE is not None:
+        e1.record()
+        _PROFILE.append((name, e0, e1))
     LAUNCH_COUNTER[0] += 1
 
 
 def query(name: str, *args):
     """Call a host-only helper (no stream argument, returns its value)."""
     return lib().fn["egm_" + name](*args)
+
+
+_PROFILE = None
+
+
+def profile_step(fn):
+    """Run fn() once with a CUDA-event pair around every C-ABI call (on the launch stream); returns
+    {entry point: {"ms": summed device time, "calls": n}}.  Diagnostic only -- never inside a timed region."""
+    global _PROFILE
+    torch.cuda.synchronize()
+    _PROFILE = []
+    try:
+        fn()
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in _PROFILE:
+            d = out.setdefault(name, {"ms": 0.0, "calls": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["calls"] += 1
+    finally:
+        _PROFILE = None
+    return dict(sorted(out.items(), key=lambda kv: -kv[1]["ms"]))
 
 
 # number of C-ABI compute calls issued (bench.py reports launches per step from this)

@@ -20,7 +20,7 @@ class _CriterionFn(torch.autograd.Function):
         ws_bytes = abi.query("loss_workspace_bytes", n, c, h, w)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=lg.device)
         out = torch.empty(8, dtype=torch.float32, device=lg.device)
-        need = logits.requires_grad and torch.is_grad_enabled()
+        need = bool(fctx.needs_input_grad[0])
         dl = torch.empty_like(lg) if need else None
         wt = None if weight is None else weight.detach().float().contiguous()
         call("loss_fwd_bwd", lg, tg, wt, n, c, h, w, int(ignore_index), int(with_dice), 1.0, out, dl, ws, ws_bytes)

@@ -260,7 +260,7 @@ class _NetFn(torch.autograd.Function):
     @staticmethod
     def forward(fctx, model, x, *params):
         store = _store_for(model)
-        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        need = any(fctx.needs_input_grad)      # (grad mode is off inside Function.forward)
         ctx = Ctx(model.compute_dtype, x.device, model.training, need, store.grad_slot, use_tc=model.use_tensor_cores)
         logits, lv = net_forward(ctx, model, x.detach().float(), model.variant)
         fctx.ectx, fctx.lv, fctx.store, fctx.nparams = ctx, lv, store, len(params)

@@ -1,0 +1,283 @@
+"""GPU: every engine op (forward + hand-written backward) against torch CPU autograd on the same inputs, in fp32 check mode
+(tolerance 2e-4 rel-to-max) and bf16 production mode (4e-2)."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from oracle import egm_oracle as O
+from tests.util import Harness, TOL, rel_err, cosine
+
+pytestmark = pytest.mark.gpu
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def _rand(*s, seed=0):
+    return torch.randn(*s, generator=torch.Generator().manual_seed(seed))
+
+
+def _q(x, dtype):
+    """round inputs to the storage dtype so both sides see identical values"""
+    return x.to(dtype).float()
+
+
+CONV_CASES = [  # cin, cout, k, dil, groups, bias, H, W
+    (3, 32, 3, 1, 1, False, 20, 24), (32, 64, 3, 1, 1, False, 17, 19), (64, 16, 1, 1, 1, False, 12, 12), (16, 16, 3, 12, 1, False, 30, 26),
+    (8, 16, 3, 1, 8, False, 14, 14), (8, 16, 3, 1, 2, False, 14, 14), (16, 16, 7, 1, 1, True, 15, 13), (64, 3, 3, 1, 1, True, 10, 10),
+    (16, 1, 1, 1, 1, True, 9, 9), (32, 2, 1, 1, 1, True, 11, 7), (24, 24, 3, 1, 24, True, 9, 10), (112, 16, 1, 1, 1, True, 8, 8),
+    (16, 16, 3, 36, 1, False, 30, 30)]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_direct(case, dtype):
+    from egm_unet_b200.engine import conv_module
+    cin, cout, k, dil, groups, bias, H, W = case
+    torch.manual_seed(1)
+    m = nn.Conv2d(cin, cout, k, padding=dil * (k - 1) // 2, dilation=dil, groups=groups, bias=bias)
+    x = _q(_rand(2, cin, H, W), dtype)
+    g = _q(_rand(2, cout, H, W, seed=3), dtype)
+    hs = Harness(dtype, use_tc=False)
+    xv = hs.var(x)
+    mc = m.cuda()
+    yv = conv_module(hs.ctx, xv, mc)
+    y = hs.out(yv)
+    xr = x.clone().requires_grad_(True)
+    m = m.cpu()
+    yr = m(xr)
+    yr.backward(g)
+    tol = TOL[dtype]
+    assert rel_err(y, yr.detach()) < tol
+    hs.backward(yv, g)
+    assert rel_err(hs.grad(xv), xr.grad) < tol
+    assert rel_err(hs.pgrad(mc.weight), m.weight.grad) < tol
+    if bias:
+        assert rel_err(hs.pgrad(mc.bias), m.bias.grad) < tol
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mode", ["relu", "none", "edge", "residual", "eval"])
+def test_bn_act(mode, dtype):
+    from egm_unet_b200 import engine as E
+    C, H, W = 24, 13, 11
+    torch.manual_seed(2)
+    bn = nn.BatchNorm2d(C, momentum=0.01 if mode == "none" else 0.1)
+    with torch.no_grad():
+        bn.weight.copy_(1 + 0.2 * torch.randn(C)); bn.bias.copy_(0.1 * torch.randn(C))
+        bn.running_mean.copy_(0.1 * torch.randn(C)); bn.running_var.copy_(1 + 0.2 * torch.rand(C))
+    import copy
+    bn_ref = copy.deepcopy(bn)
+    z = _q(_rand(3, C, H, W) * 1.5 + 0.3, dtype)
+    aux = _q(_rand(3, C, H, W, seed=5), dtype)
+    g = _q(_rand(3, C, H, W, seed=7), dtype)
+    training = mode != "eval"
+    hs = Harness(dtype, training=training)
+    zv, av = hs.var(z), hs.var(aux)
+    bnc = bn.cuda()
+    if mode in ("relu", "eval"):
+        yv = E.bn_act(hs.ctx, zv, bnc, E.ACT_RELU)
+    elif mode == "none":
+        yv = E.bn_act(hs.ctx, zv, bnc, E.ACT_NONE)
+    elif mode == "edge":
+        yv = E.bn_act(hs.ctx, zv, bnc, E.ACT_SIGMOID, E.MODE_EDGE_GATE, aux=av)
+    else:
+        yv = E.bn_act(hs.ctx, zv, bnc, E.ACT_NONE, E.MODE_RESIDUAL, aux=av, alpha=0.1)
+    y = hs.out(yv)
+    zr, ar = z.clone().requires_grad_(True), aux.clone().requires_grad_(True)
+    bn_ref.train(training)
+    b = bn_ref(zr)
+    yr = {"relu": lambda: F.relu(b), "eval": lambda: F.relu(b), "none": lambda: b, "edge": lambda: torch.sigmoid(b) * ar + ar,
+          "residual": lambda: F.relu(0.1 * ar + b)}[mode]()
+    yr.backward(g)
+    tol = TOL[dtype]
+    assert rel_err(y, yr.detach()) < tol
+    hs.backward(yv, g)
+    assert rel_err(hs.grad(zv), zr.grad) < tol * 3
+    assert rel_err(hs.pgrad(bnc.weight), bn_ref.weight.grad) < tol * 3
+    assert rel_err(hs.pgrad(bnc.bias), bn_ref.bias.grad) < tol * 3
+    if mode in ("edge", "residual"):
+        assert rel_err(hs.grad(av), ar.grad) < tol
+    if training:
+        assert rel_err(bnc.running_mean.cpu(), bn_ref.running_mean) < 1e-4 if dtype == torch.float32 else True
+        assert rel_err(bnc.running_var.cpu(), bn_ref.running_var) < 1e-4 if dtype == torch.float32 else True
+        assert int(bnc.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("hw", [(12, 16), (13, 15)])
+def test_maxpool(hw, dtype):
+    from egm_unet_b200 import engine as E
+    x = _q(_rand(2, 16, *hw), dtype)
+    x[:, :, 2:6, 2:6] = 0.0          # ties: first-max rule
+    hs = Harness(dtype)
+    xv = hs.var(x)
+    yv = E.maxpool2(hs.ctx, xv)
+    xr = x.clone().requires_grad_(True)
+    yr = F.max_pool2d(xr, 2, 2)
+    g = _q(_rand(*yr.shape, seed=9), dtype)
+    yr.backward(g)
+    assert rel_err(hs.out(yv), yr.detach()) < 1e-6
+    hs.backward(yv, g)
+    assert rel_err(hs.grad(xv), xr.grad) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [((6, 7), (12, 14)), ((6, 7), (13, 15)), ((5, 5), (11, 10))])
+def test_upsample_concat(shape, dtype):
+    from egm_unet_b200 import engine as E
+    (hl, wl), (h, w) = shape
+    low, skip = _q(_rand(2, 16, hl, wl), dtype), _q(_rand(2, 8, h, w, seed=4), dtype)
+    hs = Harness(dtype)
+    lv, sv = hs.var(low), hs.var(skip)
+    ov = E.upsample_concat(hs.ctx, lv, sv)
+    lr, sr = low.clone().requires_grad_(True), skip.clone().requires_grad_(True)
+    up = F.interpolate(lr, scale_factor=2, mode="bilinear", align_corners=True)
+    dy, dx = h - up.shape[2], w - up.shape[3]
+    ref = torch.cat([sr, F.pad(up, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])], 1)
+    g = _q(_rand(*ref.shape, seed=6), dtype)
+    ref.backward(g)
+    tol = TOL[dtype]
+    assert rel_err(hs.out(ov), ref.detach()) < tol
+    hs.backward(ov, g)
+    assert rel_err(hs.grad(lv), lr.grad) < tol
+    assert rel_err(hs.grad(sv), sr.grad) < tol
+
+
+def _wrap(mod):
+    return nn.ModuleDict({"m": mod})
+
+
+def _run_block(fn_engine, fn_oracle, mod, x, dtype, training=True, tol_scale=1.0, grad_cos=0.999):
+    """forward + backward of one block on both sides; returns nothing, asserts parity"""
+    import copy
+    from oracle import synth
+    wrapped = _wrap(mod)
+    sd = synth.fill_state_dict(wrapped.state_dict())
+    wrapped.load_state_dict(sd)
+    ref_sd = {k: v.clone() for k, v in sd.items()}
+    names = [k for k, _ in wrapped.named_parameters()]
+    for k in names:
+        ref_sd[k].requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    yr = fn_oracle(ref_sd, "m", xr)
+    g = _q(_rand(*yr.shape, seed=11), dtype)
+    yr.backward(g)
+    hs = Harness(dtype, training=training, use_tc=False)
+    wrapped.cuda()
+    xv = hs.var(x)
+    yv = fn_engine(hs.ctx, xv, wrapped["m"])
+    tol = TOL[dtype] * tol_scale
+    e = rel_err(hs.out(yv), yr.detach())
+    assert e < tol, f"forward rel err {e}"
+    hs.backward(yv, g)
+    e = rel_err(hs.grad(xv), xr.grad)
+    assert e < tol * 5, f"input grad rel err {e}"
+    bad = []
+    if dtype == torch.bfloat16:
+        grad_cos = min(grad_cos, 0.98)
+    gmax = max(float(ref_sd[k].grad.norm()) for k in names if ref_sd[k].grad is not None)
+    for k, p in wrapped.named_parameters():
+        gr = ref_sd[k].grad
+        # parameters shifted away by a following train-mode BN have an analytically ZERO gradient (pure round-off): skip
+        if gr is None or float(gr.norm()) < 1e-5 * gmax:
+            continue
+        got = hs.pgrad(p)
+        if got.numel() > 4:
+            ok = cosine(got, gr) > grad_cos and abs(float(got.norm()) / float(gr.norm()) - 1) < (0.05 if dtype == torch.float32 else 0.15)
+        else:
+            ok = rel_err(got, gr) < max(tol * 20, 2e-3)
+        if not ok:
+            bad.append((k, rel_err(got, gr), cosine(got, gr)))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C,hw", [(64, (12, 10)), (256, (7, 9)), (16, (9, 9))])
+def test_mca_layer(C, hw, dtype):
+    from egm_unet_b200 import engine as E
+    from egm_unet_b200.models import MCALayer
+    x = _q(F.relu(_rand(2, C, *hw)), dtype)           # post-ReLU input, many exact zeros -> exercises the tie rules
+    _run_block(lambda c, v, m: E.mca_layer(c, v, m), lambda sd, p, t: O.mca_layer(sd, p, t), MCALayer(C), x, dtype, tol_scale=2.0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_edge_enhancer(dtype):
+    from egm_unet_b200 import engine as E
+    from egm_unet_b200.models import EdgeAwareFeatureEnhancer
+    x = _q(_rand(2, 16, 11, 13), dtype)
+    _run_block(lambda c, v, m: E.edge_enhancer(c, v, m), lambda sd, p, t: O.edge_enhancer(sd, p, t, True, None), EdgeAwareFeatureEnhancer(16), x, dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fusion_conv(dtype):
+    from egm_unet_b200 import graph as G
+    from egm_unet_b200.models import FusionConv
+    x = _q(_rand(2, 40, 10, 12), dtype)
+    _run_block(lambda c, v, m: G.fusion_conv(c, v, m), lambda sd, p, t: O.fusion_conv(sd, p, t), FusionConv(40, 32), x, dtype, tol_scale=2.0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C,hw", [(64, (16, 14)), (128, (9, 8))])
+def test_grfb(C, hw, dtype):
+    from egm_unet_b200 import graph as G
+    from egm_unet_b200.models import EdgeEnhancedGRFB
+    x = _q(F.relu(_rand(2, C, *hw)), dtype)
+    _run_block(lambda c, v, m: G.grfb(c, v, m), lambda sd, p, t: O.grfb(sd, p, t, True, None), EdgeEnhancedGRFB(C, C), x, dtype,
+               tol_scale=3.0, grad_cos=0.995)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_rga(dtype):
+    from egm_unet_b200 import graph as G
+    from egm_unet_b200.models import RecursiveGatedAttention
+    x = _q(_rand(2, 64, 6, 7), dtype)
+    _run_block(lambda c, v, m: G.rga(c, v, m), lambda sd, p, t: O.rga(sd, p, t), RecursiveGatedAttention(64), x, dtype, tol_scale=2.0)
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 24, 20), (3, 2, 17, 33), (2, 3, 16, 16)])
+def test_fused_loss(shape):
+    import egm_unet_b200 as EG
+    from oracle import synth
+    n, c, h, w = shape
+    logits = _rand(n, c, h, w) * 2
+    target = torch.randint(0, c, (n, h, w), generator=torch.Generator().manual_seed(5))
+    target[:, :3] = 255
+    lw = torch.tensor([1.0, 2.0, 0.5][:c])
+    lr = logits.clone().requires_grad_(True)
+    ref = O.criterion(lr, target, lw, num_classes=c)
+    ref.backward()
+    lg = logits.cuda().requires_grad_(True)
+    loss = EG.criterion({"out": lg}, target.cuda(), lw.cuda(), num_classes=c, ignore_index=255)
+    (loss * 1.0).backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    assert rel_err(lg.grad.cpu(), lr.grad) < 1e-4
+    terms = O.loss_terms(logits, target, lw, c)
+    from egm_unet_b200.loss import loss_terms
+    got = loss_terms(logits.cuda(), target.cuda(), lw.cuda(), 255)
+    for k in terms:
+        assert abs(float(got[k]) - float(terms[k])) < 1e-5 * max(1.0, abs(float(terms[k]))), k
+    # CE-only mode (dice=False)
+    l2 = EG.criterion({"out": logits.cuda()}, target.cuda(), lw.cuda(), num_classes=c, dice=False, ignore_index=255)
+    assert abs(float(l2) - float(terms["ce"])) < 1e-5
+
+
+def test_eval_metrics_and_sgd():
+    import numpy as np, os
+    from egm_unet_b200.loss import EvalMetrics
+    from egm_unet_b200.abi import call
+    from oracle import synth
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics_2x64x48.npz"))
+    _, target = synth.make_inputs(2, 64, 48, blobs=True)
+    m = EvalMetrics(2, 255)
+    m.update(torch.from_numpy(fx["logits"]).cuda(), target.cuda())
+    assert np.array_equal(m.confusion().cpu().numpy(), fx["mat"])
+    assert abs(m.dice - float(fx["dice"])) < 1e-6
+    # fused SGD vs torch.optim.SGD
+    p = torch.randn(1000); g1, g2 = torch.randn(1000), torch.randn(1000)
+    pr = torch.nn.Parameter(p.clone()); opt = torch.optim.SGD([pr], lr=0.02, momentum=0.9, weight_decay=1e-4)
+    pc, buf = p.cuda(), torch.zeros(1000, device="cuda")
+    hp = torch.tensor([0.02, 0.9, 1e-4, 1.0], device="cuda")
+    for g in (g1, g2):
+        pr.grad = g.clone(); opt.step()
+        call("sgd_step", pc, g.cuda(), buf, 1000, hp)
+    assert rel_err(pc.cpu(), pr.detach()) < 1e-6
