@@ -1,7 +1,447 @@
-// placeholder until the tcgen05 kernels land
+// tcgen05 tensor-core implicit-GEMM convolution for sm_100a: bf16 NHWC activations, fp32 accumulation in TMEM,
+// operands staged by TMA (4-D NHWC tensor maps; padding = TMA out-of-bounds zero fill, so there is no im2col buffer).
+// Replaces the cuDNN kernels behind nn.Conv2d in DoubleConv (src/EGM-UNet.py:44-55, src/unet.py:7-18) and every other
+// dense conv with Cin % 16 == 0 and Cout % 16 == 0.
+//
+//  forward / dgrad  (k_conv_tc):   D[128 pixels x Cout] += A[128 pixels x 16*k ch] . B[Cout x 16*k ch]^T  per (tap, ch-chunk)
+//      M = 128 output pixels (an 8x16 spatial patch), N = Cout (16..256), K = taps*Cin.  Both operands K-major.
+//      dgrad is the same kernel on dy with the flipped / transposed weights (egm_pack_conv_weight_tc writes both).
+//  wgrad            (k_wgrad_tc):  D[Cout x Cin] += dY[128 pixels x Cout]^T . X_shifted[128 pixels x Cin]   per tap
+//      M = Cout chunk (64/128), N = Cin chunk (<= 64), K = pixels.  Both operands MN-major (channels contiguous).
+//      Split over pixel ranges across CTAs; partial sums are reduced with fp32 red.global.add into dw[tap][ci][co].
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (one TMEM lane quarter each).  smem ring of mbarrier-guarded stages; double-buffered accumulators.
 #include "common.cuh"
+#include <cuda.h>
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+               "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+               "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version=1 <<46 | layout <<61
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         (1ull << 46) | ((uint64_t)layout << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32, a=b=BF16, majors, N>>3 at bit 17, M>>4 at bit 24
+__device__ __host__ inline uint32_t umma_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+static inline int swz_layout(int row_bytes) { return row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6); }   // SWIZZLE_128B / 64B / 32B
+
+// ------------------------------------------------------------------ tensor-map creation (driver entry point, no libcuda link)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+static CUtensorMapSwizzle swz_enum(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+// NHWC bf16 tensor [N,H,W,C] -> 4-D map (C, W, H, N), box (bc, bw, bh, 1)
+static int make_map_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, int C, int bc, int bw, int bh) {
+  PFN_encodeTiled enc = get_encode();
+  EGM_REQUIRE(enc, EGM_E_ARCH, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swz_enum(bc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EGM_REQUIRE(r == CUDA_SUCCESS, EGM_E_BADARG, "cuTensorMapEncodeTiled(nhwc %dx%dx%dx%d box %d,%d,%d) failed: %d", N, H, W, C, bc, bw, bh, (int)r);
+  return EGM_OK;
+}
+// packed weights [taps][Cout][Cin] bf16 -> 3-D map (Cin, Cout, taps), box (bc, Cout, 1)
+static int make_map_w(CUtensorMap* tm, const void* ptr, int taps, int Cout, int Cin, int bc) {
+  PFN_encodeTiled enc = get_encode();
+  EGM_REQUIRE(enc, EGM_E_ARCH, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * 2 * Cout};
+  cuuint32_t box[3] = {(cuuint32_t)bc, (cuuint32_t)Cout, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swz_enum(bc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EGM_REQUIRE(r == CUDA_SUCCESS, EGM_E_BADARG, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  return EGM_OK;
+}
+
+constexpr int TILE_H = 8, TILE_W = 16, TILE_PIX = 128;
+constexpr int TC_THREADS = 192;
+
+// =================================================================== forward / dgrad
+struct ConvTcParams {
+  int N, H, W, Cin, Cout, kh, kw, dil, pad;
+  int tilesH, tilesW, numTiles, kChunks, bkc;       // bkc = channels per K chunk (64/32/16)
+  int stages, aBytes, bStride, tmemCols, accCols;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                                                          __nv_bfloat16* __restrict__ y, const float* __restrict__ bias, ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + (size_t)p.stages * p.aBytes;
+  uint64_t* full = (uint64_t*)(sB + (size_t)p.stages * p.bStride);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tfull = empty + p.stages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int taps = p.kh * p.kw;
+  const int kIters = taps * p.kChunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+        int n = tile / (p.tilesH * p.tilesW); int r = tile - n * p.tilesH * p.tilesW;
+        int h0 = (r / p.tilesW) * TILE_H, w0 = (r % p.tilesW) * TILE_W;
+        for (int t = 0; t < taps; ++t) {
+          int dh = (t / p.kw) * p.dil - p.pad, dw = (t % p.kw) * p.dil - p.pad;
+          for (int kc = 0; kc < p.kChunks; ++kc) {
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], (uint32_t)(p.aBytes + p.Cout * p.bkc * 2));
+            tma_load_4d(sA + (size_t)s * p.aBytes, &tmX, &full[s], kc * p.bkc, w0 + dw, h0 + dh, n);
+            tma_load_3d(sB + (size_t)s * p.bStride, &tmW, &full[s], kc * p.bkc, 0, t);
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(128, p.Cout, 0, 0);
+      const int rowB = p.bkc * 2;                       // bytes per smem row == swizzle span
+      const uint32_t layout = rowB == 128 ? 2u : (rowB == 64 ? 4u : 6u);
+      const uint32_t sbo = 8u * rowB;                   // 8-row core-matrix group stride
+      int s = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(acc * p.accCols);
+        for (int it = 0; it < kIters; ++it) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA + (size_t)s * p.aBytes), b0 = smem_u32(sB + (size_t)s * p.bStride);
+          for (int k = 0; k < p.bkc / 16; ++k)
+            umma_bf16(d, umma_desc(a0 + k * 32, 16, sbo, layout), umma_desc(b0 + k * 32, 16, sbo, layout), idesc, (it | k) ? 1u : 0u);
+          umma_commit(&empty[s]);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+        if (++acc == 2) { acc = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;                       // pixel index inside the 8x16 patch
+    int acc = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+      int n = tile / (p.tilesH * p.tilesW); int r = tile - n * p.tilesH * p.tilesW;
+      int h = (r / p.tilesW) * TILE_H + row / TILE_W, w = (r % p.tilesW) * TILE_W + row % TILE_W;
+      const bool valid = h < p.H && w < p.W;
+      __nv_bfloat16* yp = y + (((long long)n * p.H + h) * p.W + w) * p.Cout;
+      mbar_wait(&tfull[acc], aph);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.accCols);
+      for (int c = 0; c < p.Cout; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(t0 + c, v);
+        tmem_ld_wait();
+        if (valid) {
+          uint4 o[2]; __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
+            if (bias) { f0 += bias[c + 2 * j]; f1 += bias[c + 2 * j + 1]; }
+            ob[j] = __floats2bfloat162_rn(f0, f1);
+          }
+          *reinterpret_cast<uint4*>(yp + c) = o[0];
+          *reinterpret_cast<uint4*>(yp + c + 8) = o[1];
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; aph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmemCols); }
+}
+
+static int pow2_cols(int c) { int v = 32; while (v < c) v <<= 1; return v; }
+
+extern "C" int egm_conv2d_tc_supported(int Cin, int Cout, int kh, int kw, int dil, int groups) {
+  if (groups != 1 || kh != kw || !(kh & 1) || dil < 1) return 0;
+  if (Cin % 16 || Cout % 16 || Cout < 16 || Cout > 256 || Cin < 16) return 0;
+  if (Cin > 64 && Cin % 64) return 0;
+  if (Cin < 64 && Cin != 16 && Cin != 32) return 0;
+  return 1;
+}
 extern "C" long long egm_conv2d_tc_workspace_bytes(int, int, int, int, int, int, int) { return 0; }
-extern "C" int egm_conv2d_tc_supported(int, int, int, int, int, int) { return 0; }
-extern "C" int egm_pack_conv_weight_tc(const float*, void*, void*, int, int, int, int, void*) { egm_set_error("tc path not built"); return EGM_E_ARCH; }
-extern "C" int egm_conv2d_tc(const void*, const void*, const float*, void*, int, int, int, int, int, int, int, int, void*) { egm_set_error("tc path not built"); return EGM_E_ARCH; }
-extern "C" int egm_conv2d_wgrad_tc(const void*, const void*, float*, int, int, int, int, int, int, int, int, void*) { egm_set_error("tc path not built"); return EGM_E_ARCH; }
+
+extern "C" int egm_conv2d_tc(const void* x, const void* w_packed_bf16, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
+                             int kh, int kw, int dil, void* stream) {
+  EGM_REQUIRE(egm_conv2d_tc_supported(Cin, Cout, kh, kw, dil, 1), EGM_E_SHAPE, "conv2d_tc: unsupported shape %d->%d k%d", Cin, Cout, kh);
+  EGM_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)w_packed_bf16 & 15) == 0, EGM_E_ALIGN, "conv2d_tc: pointers must be 16-byte aligned");
+  if ((long long)N * H * W == 0) return EGM_OK;
+  ConvTcParams p{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
+  p.tilesH = cdiv(H, TILE_H); p.tilesW = cdiv(W, TILE_W); p.numTiles = N * p.tilesH * p.tilesW;
+  p.bkc = Cin >= 64 ? 64 : Cin; p.kChunks = Cin / p.bkc;
+  p.aBytes = TILE_PIX * p.bkc * 2;                               // 16 KB / 8 KB / 4 KB: multiples of 1024
+  p.bStride = (Cout * p.bkc * 2 + 1023) / 1024 * 1024;
+  int per = p.aBytes + p.bStride;
+  p.stages = (200 * 1024) / per; if (p.stages > 8) p.stages = 8; if (p.stages < 2) p.stages = 2;
+  p.accCols = (Cout + 31) / 32 * 32; p.tmemCols = pow2_cols(2 * p.accCols);
+  CUtensorMap tmX, tmW;
+  int e = make_map_nhwc(&tmX, x, N, H, W, Cin, p.bkc, TILE_W, TILE_H); if (e) return e;
+  e = make_map_w(&tmW, w_packed_bf16, kh * kw, Cout, Cin, p.bkc); if (e) return e;
+  size_t smem = (size_t)p.stages * per + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+  int grid = p.numTiles < egm_num_sms() ? p.numTiles : egm_num_sms();
+  k_conv_tc<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmX, tmW, (__nv_bfloat16*)y, bias, p);
+  EGM_LAUNCH_CHECK("conv2d_tc"); return EGM_OK;
+}
+
+// weights fp32 [Cout][Cin][kh][kw] -> bf16 wf [taps][Cout][Cin] (forward) and wd [taps_flipped][Cin][Cout] (dgrad: roles swapped)
+__global__ void k_pack_w_tc(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int taps) {
+  long long total = (long long)Cout * Cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int t = (int)(i % taps); long long q = i / taps; int ci = (int)(q % Cin); int co = (int)(q / Cin);
+    __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
+    if (wf) wf[((long long)t * Cout + co) * Cin + ci] = v;
+    if (wd) wd[((long long)(taps - 1 - t) * Cin + ci) * Cout + co] = v;
+  }
+}
+extern "C" int egm_pack_conv_weight_tc(const float* w, void* wf_bf16, void* wd_bf16, int Cout, int Cin, int kh, int kw, void* stream) {
+  long long total = (long long)Cout * Cin * kh * kw;
+  if (total == 0) return EGM_OK;
+  k_pack_w_tc<<<egm_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wf_bf16, (__nv_bfloat16*)wd_bf16, Cout, Cin, kh * kw);
+  EGM_LAUNCH_CHECK("pack_conv_weight_tc"); return EGM_OK;
+}
+
+// =================================================================== wgrad
+// work unit = (tap group of <= 3 taps, Cout chunk mch, Cin chunk nch) x pixel split; stage = dY tile + the group's shifted X tiles.
+struct WgradParams {
+  int N, H, W, Cin, Cout, kh, kw, dil, pad;
+  int tilesH, tilesW, numTiles;
+  int tapGroups, coChunks, ciChunks, splits, tilesPerSplit;
+  int mch, nch, mAtoms, aAtomBytes, bTileBytes, aBytes, stageBytes, stages, tmemCols, ummaM;
+};
+constexpr int WG_TAPS = 3;
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                                                           float* __restrict__ dwp, WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + (size_t)p.stages * p.stageBytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tfull = empty + p.stages;
+  uint32_t* tmem_slot = (uint32_t*)(tfull + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // decode the work unit
+  int u = blockIdx.x;
+  const int sp = u % p.splits; u /= p.splits;
+  const int cic = u % p.ciChunks; u /= p.ciChunks;
+  const int coc = u % p.coChunks; u /= p.coChunks;
+  const int tg = u;
+  const int taps = p.kh * p.kw;
+  const int t0 = tg * WG_TAPS;
+  const int nt = (taps - t0) < WG_TAPS ? (taps - t0) : WG_TAPS;
+  const int tileBeg = sp * p.tilesPerSplit;
+  int tileEnd = tileBeg + p.tilesPerSplit; if (tileEnd > p.numTiles) tileEnd = p.numTiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = tileBeg; tile < tileEnd; ++tile) {
+        int n = tile / (p.tilesH * p.tilesW); int r = tile - n * p.tilesH * p.tilesW;
+        int h0 = (r / p.tilesW) * TILE_H, w0 = (r % p.tilesW) * TILE_W;
+        uint8_t* st = smem + (size_t)s * p.stageBytes;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], (uint32_t)(p.mAtoms * p.aAtomBytes + nt * p.bTileBytes));
+        for (int a = 0; a < p.mAtoms; ++a)
+          tma_load_4d(st + (size_t)a * p.aAtomBytes, &tmDY, &full[s], coc * p.mch + a * 64, w0, h0, n);
+        for (int j = 0; j < nt; ++j) {
+          int t = t0 + j; int dh = (t / p.kw) * p.dil - p.pad, dw = (t % p.kw) * p.dil - p.pad;
+          tma_load_4d(st + p.aBytes + (size_t)j * p.bTileBytes, &tmX, &full[s], cic * p.nch, w0 + dw, h0 + dh, n);
+        }
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(p.ummaM, p.nch, 1, 1);
+      const int rowA = (p.mch >= 64 ? 64 : p.mch) * 2, rowB = p.nch * 2;
+      const uint32_t layA = rowA == 128 ? 2u : (rowA == 64 ? 4u : 6u), layB = rowB == 128 ? 2u : (rowB == 64 ? 4u : 6u);
+      int s = 0; uint32_t ph = 0; bool first = true;
+      for (int tile = tileBeg; tile < tileEnd; ++tile) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem + (size_t)s * p.stageBytes);
+        for (int j = 0; j < nt; ++j) {
+          const uint32_t b0 = a0 + p.aBytes + j * p.bTileBytes;
+          for (int k = 0; k < TILE_PIX / 16; ++k)      // 16 pixels (= 2 groups of 8 K-rows) per MMA
+            umma_bf16(tmem_base + (uint32_t)(j * p.nch), umma_desc(a0 + k * 16 * rowA, (uint32_t)p.aAtomBytes, 8u * rowA, layA),
+                      umma_desc(b0 + k * 16 * rowB, (uint32_t)p.bTileBytes, 8u * rowB, layB), idesc, (first && k == 0) ? 0u : 1u);
+        }
+        first = false;
+        umma_commit(&empty[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+      umma_commit(tfull);
+    }
+  } else if (tileBeg < tileEnd) {
+    const int q = warp & 3;
+    const int co_local = q * 32 + lane;                  // TMEM lane = output channel inside the chunk
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int co = coc * p.mch + co_local;
+    const bool valid = co_local < p.mch && co < p.Cout && co_local < p.ummaM;
+    if (q * 32 < p.ummaM) {
+      for (int j = 0; j < nt; ++j) {
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.nch);
+        for (int c = 0; c < p.nch; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(ta + c, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              int ci = cic * p.nch + c + i;
+              atomicAdd(dwp + ((long long)(t0 + j) * p.Cin + ci) * p.Cout + co, __uint_as_float(v[i]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmemCols); }
+}
+
+// dw_packed fp32 [taps][Cin][Cout] (same layout as the direct path; zeroed here)
+extern "C" int egm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_packed, int N, int H, int W, int Cin, int Cout, int kh, int kw, int dil,
+                                   void* stream) {
+  EGM_REQUIRE(egm_conv2d_tc_supported(Cin, Cout, kh, kw, dil, 1) && Cout >= 32, EGM_E_SHAPE, "wgrad_tc: unsupported shape %d->%d", Cin, Cout);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(dw_packed, 0, sizeof(float) * (size_t)kh * kw * Cin * Cout, st);
+  if ((long long)N * H * W == 0) return EGM_OK;
+  WgradParams p{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
+  p.tilesH = cdiv(H, TILE_H); p.tilesW = cdiv(W, TILE_W); p.numTiles = N * p.tilesH * p.tilesW;
+  p.mch = Cout >= 128 ? 128 : Cout;                 // 128 / 64 / 32
+  p.ummaM = 128;                                     // always M=128 (lane i == row i); rows >= mch read unused smem and are ignored
+  p.mAtoms = p.mch >= 64 ? p.mch / 64 : 1;
+  int aAtomCh = p.mch >= 64 ? 64 : p.mch;
+  p.aAtomBytes = TILE_PIX * aAtomCh * 2;
+  p.aBytes = (p.ummaM / aAtomCh) * p.aAtomBytes;     // room for the atoms the MMA addresses (>= loaded atoms)
+  if (p.aBytes < p.mAtoms * p.aAtomBytes) p.aBytes = p.mAtoms * p.aAtomBytes;
+  p.nch = Cin >= 64 ? 64 : Cin;                     // 64 / 32 / 16
+  p.bTileBytes = TILE_PIX * p.nch * 2;
+  p.stageBytes = p.aBytes + WG_TAPS * p.bTileBytes;
+  p.stages = (200 * 1024) / p.stageBytes; if (p.stages > 6) p.stages = 6; if (p.stages < 2) p.stages = 2;
+  p.tmemCols = pow2_cols(WG_TAPS * p.nch);
+  p.tapGroups = cdiv(kh * kw, WG_TAPS); p.coChunks = cdiv(Cout, p.mch); p.ciChunks = Cin / p.nch;
+  long long units = (long long)p.tapGroups * p.coChunks * p.ciChunks;
+  long long want = ((long long)egm_num_sms() * 2 + units - 1) / units;
+  if (want > p.numTiles) want = p.numTiles; if (want < 1) want = 1;
+  p.tilesPerSplit = cdiv(p.numTiles, want); p.splits = cdiv(p.numTiles, p.tilesPerSplit);
+  CUtensorMap tmDY, tmX;
+  int e = make_map_nhwc(&tmDY, dy, N, H, W, Cout, aAtomCh, TILE_W, TILE_H); if (e) return e;
+  e = make_map_nhwc(&tmX, x, N, H, W, Cin, p.nch, TILE_W, TILE_H); if (e) return e;
+  size_t smem = (size_t)p.stages * p.stageBytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+  long long grid = units * p.splits;
+  EGM_REQUIRE(grid < (1ll << 31), EGM_E_SHAPE, "wgrad_tc: grid too large");
+  k_wgrad_tc<<<(unsigned)grid, TC_THREADS, smem, st>>>(tmDY, tmX, dw_packed, p);
+  EGM_LAUNCH_CHECK("conv2d_wgrad_tc"); return EGM_OK;
+}
