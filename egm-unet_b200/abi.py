@@ -103,7 +103,10 @@ def call(name: str, *args):
         raise RuntimeError(f"egm_{name} failed ({rc}): {L.last_error()}")
     if _PROFILE is not None:
         e1.record()
-        _PROFILE.append((name, e0, e1))
+        key = name
+        if _PROFILE_DETAIL and name.startswith("conv2d"):
+            key = name + ":" + ",".join(str(a) for a in args if isinstance(a, int))
+        _PROFILE.append((key, e0, e1))
     LAUNCH_COUNTER[0] += 1
 
 
@@ -113,6 +116,7 @@ def query(name: str, *args):
 
 
 _PROFILE = None
+_PROFILE_DETAIL = bool(os.environ.get("EGM_PROFILE_DETAIL"))
 
 
 def profile_step(fn):

@@ -112,12 +112,12 @@ static int make_map_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, 
   return EGM_OK;
 }
 // packed weights [taps][Cout][Cin] bf16 -> 3-D map (Cin, Cout, taps), box (bc, Cout, 1)
-static int make_map_w(CUtensorMap* tm, const void* ptr, int taps, int Cout, int Cin, int bc) {
+static int make_map_w(CUtensorMap* tm, const void* ptr, int taps, int Cout, int Cin, int bc, int brows) {
   PFN_encodeTiled enc = get_encode();
   EGM_REQUIRE(enc, EGM_E_ARCH, "cuTensorMapEncodeTiled unavailable");
   cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
   cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * 2 * Cout};
-  cuuint32_t box[3] = {(cuuint32_t)bc, (cuuint32_t)Cout, 1};
+  cuuint32_t box[3] = {(cuuint32_t)bc, (cuuint32_t)brows, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swz_enum(bc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -133,6 +133,7 @@ struct ConvTcParams {
   int N, H, W, Cin, Cout, kh, kw, dil, pad;
   int tilesH, tilesW, numTiles, kChunks, bkc;       // bkc = channels per K chunk (64/32/16)
   int stages, aBytes, bStride, tmemCols, accCols;
+  int nChunk, coChunks;                               // Cout is processed in coChunks slices of nChunk (<= 256) channels
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
@@ -165,15 +166,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
-        int n = tile / (p.tilesH * p.tilesW); int r = tile - n * p.tilesH * p.tilesW;
+        const int chunk = tile % p.coChunks, sp_t = tile / p.coChunks;
+        int n = sp_t / (p.tilesH * p.tilesW); int r = sp_t - n * p.tilesH * p.tilesW;
         int h0 = (r / p.tilesW) * TILE_H, w0 = (r % p.tilesW) * TILE_W;
         for (int t = 0; t < taps; ++t) {
           int dh = (t / p.kw) * p.dil - p.pad, dw = (t % p.kw) * p.dil - p.pad;
           for (int kc = 0; kc < p.kChunks; ++kc) {
             mbar_wait(&empty[s], ph ^ 1);
-            mbar_expect_tx(&full[s], (uint32_t)(p.aBytes + p.Cout * p.bkc * 2));
+            mbar_expect_tx(&full[s], (uint32_t)(p.aBytes + p.nChunk * p.bkc * 2));
             tma_load_4d(sA + (size_t)s * p.aBytes, &tmX, &full[s], kc * p.bkc, w0 + dw, h0 + dh, n);
-            tma_load_3d(sB + (size_t)s * p.bStride, &tmW, &full[s], kc * p.bkc, 0, t);
+            tma_load_3d(sB + (size_t)s * p.bStride, &tmW, &full[s], kc * p.bkc, chunk * p.nChunk, t);
             if (++s == p.stages) { s = 0; ph ^= 1; }
           }
         }
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc(128, p.Cout, 0, 0);
+      const uint32_t idesc = umma_idesc(128, p.nChunk, 0, 0);
       const int rowB = p.bkc * 2;                       // bytes per smem row == swizzle span
       const uint32_t layout = rowB == 128 ? 2u : (rowB == 64 ? 4u : 6u);
       const uint32_t sbo = 8u * rowB;                   // 8-row core-matrix group stride
@@ -208,14 +210,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     const int row = q * 32 + lane;                       // pixel index inside the 8x16 patch
     int acc = 0; uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
-      int n = tile / (p.tilesH * p.tilesW); int r = tile - n * p.tilesH * p.tilesW;
+      const int chunk = tile % p.coChunks, sp_t = tile / p.coChunks;
+      int n = sp_t / (p.tilesH * p.tilesW); int r = sp_t - n * p.tilesH * p.tilesW;
       int h = (r / p.tilesW) * TILE_H + row / TILE_W, w = (r % p.tilesW) * TILE_W + row % TILE_W;
       const bool valid = h < p.H && w < p.W;
-      __nv_bfloat16* yp = y + (((long long)n * p.H + h) * p.W + w) * p.Cout;
+      __nv_bfloat16* yp = y + (((long long)n * p.H + h) * p.W + w) * p.Cout + chunk * p.nChunk;
+      const float* bp = bias ? bias + chunk * p.nChunk : nullptr;
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.accCols);
-      for (int c = 0; c < p.Cout; c += 16) {
+      for (int c = 0; c < p.nChunk; c += 16) {
         uint32_t v[16];
         tmem_ld16(t0 + c, v);
         tmem_ld_wait();
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
-            if (bias) { f0 += bias[c + 2 * j]; f1 += bias[c + 2 * j + 1]; }
+            if (bp) { f0 += bp[c + 2 * j]; f1 += bp[c + 2 * j + 1]; }
             ob[j] = __floats2bfloat162_rn(f0, f1);
           }
           *reinterpret_cast<uint4*>(yp + c) = o[0];
@@ -242,12 +246,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 }
 
 static int pow2_cols(int c) { int v = 32; while (v < c) v <<= 1; return v; }
+static int pick_bkc(int C) { return C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16); }       // channels per K chunk (row = 128/64/32 bytes)
 
 extern "C" int egm_conv2d_tc_supported(int Cin, int Cout, int kh, int kw, int dil, int groups) {
   if (groups != 1 || kh != kw || !(kh & 1) || dil < 1) return 0;
-  if (Cin % 16 || Cout % 16 || Cout < 16 || Cout > 256 || Cin < 16) return 0;
-  if (Cin > 64 && Cin % 64) return 0;
-  if (Cin < 64 && Cin != 16 && Cin != 32) return 0;
+  if (Cin % 16 || Cout % 16 || Cout < 16 || Cin < 16 || Cout > 2048 || Cin > 4096) return 0;
+  int chunks = (Cout + 255) / 256;
+  if (Cout % chunks || (Cout / chunks) % 16) return 0;
   return 1;
 }
 extern "C" long long egm_conv2d_tc_workspace_bytes(int, int, int, int, int, int, int) { return 0; }
@@ -259,16 +264,17 @@ extern "C" int egm_conv2d_tc(const void* x, const void* w_packed_bf16, const flo
   if ((long long)N * H * W == 0) return EGM_OK;
   ConvTcParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
-  p.tilesH = cdiv(H, TILE_H); p.tilesW = cdiv(W, TILE_W); p.numTiles = N * p.tilesH * p.tilesW;
-  p.bkc = Cin >= 64 ? 64 : Cin; p.kChunks = Cin / p.bkc;
+  p.coChunks = (Cout + 255) / 256; p.nChunk = Cout / p.coChunks;
+  p.tilesH = cdiv(H, TILE_H); p.tilesW = cdiv(W, TILE_W); p.numTiles = N * p.tilesH * p.tilesW * p.coChunks;
+  p.bkc = pick_bkc(Cin); p.kChunks = Cin / p.bkc;
   p.aBytes = TILE_PIX * p.bkc * 2;                               // 16 KB / 8 KB / 4 KB: multiples of 1024
-  p.bStride = (Cout * p.bkc * 2 + 1023) / 1024 * 1024;
+  p.bStride = (p.nChunk * p.bkc * 2 + 1023) / 1024 * 1024;
   int per = p.aBytes + p.bStride;
   p.stages = (200 * 1024) / per; if (p.stages > 8) p.stages = 8; if (p.stages < 2) p.stages = 2;
-  p.accCols = (Cout + 31) / 32 * 32; p.tmemCols = pow2_cols(2 * p.accCols);
+  p.accCols = (p.nChunk + 31) / 32 * 32; p.tmemCols = pow2_cols(2 * p.accCols);
   CUtensorMap tmX, tmW;
   int e = make_map_nhwc(&tmX, x, N, H, W, Cin, p.bkc, TILE_W, TILE_H); if (e) return e;
-  e = make_map_w(&tmW, w_packed_bf16, kh * kw, Cout, Cin, p.bkc); if (e) return e;
+  e = make_map_w(&tmW, w_packed_bf16, kh * kw, Cout, Cin, p.bkc, p.nChunk); if (e) return e;
   size_t smem = (size_t)p.stages * per + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
@@ -410,26 +416,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
 // dw_packed fp32 [taps][Cin][Cout] (same layout as the direct path; zeroed here)
 extern "C" int egm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_packed, int N, int H, int W, int Cin, int Cout, int kh, int kw, int dil,
                                    void* stream) {
-  EGM_REQUIRE(egm_conv2d_tc_supported(Cin, Cout, kh, kw, dil, 1) && Cout >= 32, EGM_E_SHAPE, "wgrad_tc: unsupported shape %d->%d", Cin, Cout);
+  EGM_REQUIRE(egm_conv2d_tc_supported(Cin, Cout, kh, kw, dil, 1), EGM_E_SHAPE, "wgrad_tc: unsupported shape %d->%d", Cin, Cout);
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(dw_packed, 0, sizeof(float) * (size_t)kh * kw * Cin * Cout, st);
   if ((long long)N * H * W == 0) return EGM_OK;
   WgradParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
   p.tilesH = cdiv(H, TILE_H); p.tilesW = cdiv(W, TILE_W); p.numTiles = N * p.tilesH * p.tilesW;
-  p.mch = Cout >= 128 ? 128 : Cout;                 // 128 / 64 / 32
+  p.mch = Cout % 128 == 0 ? 128 : pick_bkc(Cout);   // 128 / 64 / 32 / 16 output channels per work unit
   p.ummaM = 128;                                     // always M=128 (lane i == row i); rows >= mch read unused smem and are ignored
   p.mAtoms = p.mch >= 64 ? p.mch / 64 : 1;
   int aAtomCh = p.mch >= 64 ? 64 : p.mch;
   p.aAtomBytes = TILE_PIX * aAtomCh * 2;
   p.aBytes = (p.ummaM / aAtomCh) * p.aAtomBytes;     // room for the atoms the MMA addresses (>= loaded atoms)
   if (p.aBytes < p.mAtoms * p.aAtomBytes) p.aBytes = p.mAtoms * p.aAtomBytes;
-  p.nch = Cin >= 64 ? 64 : Cin;                     // 64 / 32 / 16
+  p.nch = pick_bkc(Cin);                            // 64 / 32 / 16 input channels per work unit
   p.bTileBytes = TILE_PIX * p.nch * 2;
   p.stageBytes = p.aBytes + WG_TAPS * p.bTileBytes;
   p.stages = (200 * 1024) / p.stageBytes; if (p.stages > 6) p.stages = 6; if (p.stages < 2) p.stages = 2;
   p.tmemCols = pow2_cols(WG_TAPS * p.nch);
-  p.tapGroups = cdiv(kh * kw, WG_TAPS); p.coChunks = cdiv(Cout, p.mch); p.ciChunks = Cin / p.nch;
+  p.tapGroups = cdiv(kh * kw, WG_TAPS); p.coChunks = Cout / p.mch; p.ciChunks = Cin / p.nch;
   long long units = (long long)p.tapGroups * p.coChunks * p.ciChunks;
   long long want = ((long long)egm_num_sms() * 2 + units - 1) / units;
   if (want > p.numTiles) want = p.numTiles; if (want < 1) want = 1;

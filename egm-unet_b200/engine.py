@@ -135,7 +135,7 @@ class PackedConv:
         co, cig, kh, kw = weight.shape
         self.co, self.cig, self.kh, self.kw, self.groups, self.dil = co, cig, kh, kw, groups, dilation
         self.cin = cig * groups
-        self.tc = bool(tc_ok and ctx.use_tc and co >= 32 and self.cin >= 32 and abi.query("conv2d_tc_supported", self.cin, co, kh, kw, dilation, groups)
+        self.tc = bool(tc_ok and ctx.use_tc and abi.query("conv2d_tc_supported", self.cin, co, kh, kw, dilation, groups)
                        and abi.query("conv2d_tc_supported", co, self.cin, kh, kw, dilation, groups))
         n = weight.numel()
         if self.tc:

@@ -286,7 +286,9 @@ def test_eval_metrics_and_sgd():
 TC_CASES = [  # cin, cout, k, dil, H, W, N
     (32, 32, 3, 1, 16, 32, 1), (32, 64, 3, 1, 30, 30, 2), (64, 64, 3, 1, 20, 40, 2), (64, 128, 3, 1, 24, 24, 1), (128, 128, 3, 1, 17, 19, 2),
     (256, 256, 3, 1, 15, 15, 1), (512, 256, 3, 1, 12, 12, 1), (256, 128, 3, 1, 16, 16, 1), (64, 32, 3, 1, 33, 47, 1),
-    (32, 32, 3, 12, 30, 30, 1), (64, 64, 1, 1, 20, 20, 1), (32, 32, 7, 1, 18, 18, 1), (128, 384, 1, 1, 9, 9, 1)]
+    (32, 32, 3, 12, 30, 30, 1), (64, 64, 1, 1, 20, 20, 1), (32, 32, 7, 1, 18, 18, 1), (128, 384, 1, 1, 9, 9, 1),
+    (16, 16, 7, 1, 20, 24, 2), (112, 16, 1, 1, 16, 16, 1), (16, 16, 3, 24, 30, 30, 1), (64, 16, 1, 1, 10, 10, 1), (16, 64, 1, 1, 10, 10, 1),
+    (256, 512, 3, 1, 10, 10, 1), (224, 32, 1, 1, 12, 12, 1)]
 
 
 @pytest.mark.parametrize("case", TC_CASES)
@@ -304,8 +306,6 @@ def test_conv_tc(case):
     hs = Harness(torch.bfloat16, use_tc=True)
     xv = hs.var(x)
     mc = m.cuda()
-    if cout > 256:
-        pytest.skip("Cout > 256 runs on the direct path")
     assert abi.query("conv2d_tc_supported", cin, cout, k, k, dil, 1) == 1
     yv = conv_module(hs.ctx, xv, mc)
     y = hs.out(yv)
