@@ -95,9 +95,11 @@ class Ctx:
         if self.record:
             self.tape.append(fn)
 
-    def backward(self):
+    def backward(self, after_each: Optional[Callable] = None):
         while self.tape:
             self.tape.pop()()
+            if after_each is not None:
+                after_each()
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:

@@ -236,11 +236,16 @@ class ParamStore:
             p.data = v
             self._gview[id(p)] = self.grads[o:o + n].view(p.shape)
         self._ptrs = [p.data_ptr() for p in self.plist]
+        self.index = {id(p): i for i, p in enumerate(self.plist)}
+        self.on_grad = None          # optional callback(param_index) -- the DDP bucket reducer hooks in here
+        self.ranges = [(o, (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN) for p, o in zip(self.plist, self.offsets)]
 
     def valid(self) -> bool:
         return all(p.data_ptr() == q for p, q in zip(self.plist, self._ptrs))
 
     def grad_slot(self, p: torch.Tensor) -> torch.Tensor:
+        if self.on_grad is not None:
+            self.on_grad(self.index[id(p)])
         return self._gview[id(p)]
 
 

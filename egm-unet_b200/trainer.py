@@ -16,6 +16,7 @@ from .abi import call
 from .engine import Ctx, seed_grad_from_nchw
 from .graph import net_forward
 from .models import _store_for
+from .ddp import BucketReducer
 
 
 class Trainer:
@@ -39,6 +40,9 @@ class Trainer:
         self.loss_terms = None
         self.comm_stream = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
         self.num_buckets = num_buckets
+        self.reducer = None
+        if self.world > 1:
+            self.reducer = BucketReducer(self.store.grads, self.store.ranges, num_buckets, process_group, self.comm_stream)
         self._set_hp()
 
     def _set_hp(self):
@@ -64,7 +68,15 @@ class Trainer:
         dl = torch.empty_like(logits)
         call("loss_fwd_bwd", logits, target, self.cw, n, c, h, w, self.ignore_index, int(self.dice), 1.0, out, dl, ws, ws_bytes)
         seed_grad_from_nchw(ctx, lv, dl)
-        ctx.backward()
+        if self.reducer is not None:          # overlap: buckets are all-reduced on the comm stream as backward completes them
+            st.on_grad = self.reducer.mark
+            try:
+                ctx.backward(after_each=self.reducer.flush_ready)
+            finally:
+                st.on_grad = None
+            self.reducer.finish()
+        else:
+            ctx.backward()
         self.loss_terms = out
         return out[0]
 
@@ -72,8 +84,5 @@ class Trainer:
         """image [N,3,H,W] fp32 cuda, target [N,H,W] int64 cuda -> loss (0-dim device tensor)."""
         loss = self.forward_backward(image, target)
         st = self.store
-        if self.world > 1:
-            # one flat bucket: 25 MB over NVSwitch is ~0.1 ms, launched on the compute stream right after the last wgrad
-            dist.all_reduce(st.grads, op=dist.ReduceOp.SUM, group=self.pg)
         call("sgd_step", st.params, st.grads, self.mom_buf, st.total, self.hp)
         return loss

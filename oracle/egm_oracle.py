@@ -34,6 +34,16 @@ Tensor = torch.Tensor
 # --------------------------------------------------------------------------- #
 # primitives
 # --------------------------------------------------------------------------- #
+# Optional storage-rounding model: with STORAGE = torch.bfloat16 every activation tensor the CUDA path materialises
+# (conv outputs, BN+activation outputs, block outputs) is rounded to bf16 and back, arithmetic staying fp32.  This is the
+# "reference computed with bf16-stored activations" the bf16 parity tests compare against (tests/test_model_gpu.py).
+STORAGE = None
+
+
+def _r(x: Tensor) -> Tensor:
+    return x if STORAGE is None else x.to(STORAGE).to(x.dtype)
+
+
 def _bn(sd, p: str, x: Tensor, train: bool, momentum: float, upd: Optional[dict], eps: float = 1e-5) -> Tensor:
     """nn.BatchNorm2d: batch stats + biased var for normalisation in
     training, running stats in eval; unbiased var into running_var."""
@@ -54,28 +64,28 @@ def _bn(sd, p: str, x: Tensor, train: bool, momentum: float, upd: Optional[dict]
 
 
 def _conv(sd, p: str, x: Tensor, padding=0, dilation=1, groups=1) -> Tensor:
-    return F.conv2d(x, sd[p + ".weight"], sd.get(p + ".bias"), 1, padding, dilation, groups)
+    return _r(F.conv2d(x, sd[p + ".weight"], sd.get(p + ".bias"), 1, padding, dilation, groups))
 
 
 def double_conv(sd, p, x, train, upd, i0=0, i1=3):
     """DoubleConv: src/unet.py:7-18 == src/EGM-UNet.py:44-55 (conv idx i0,i1; BN idx +1)."""
-    x = F.relu(_bn(sd, f"{p}.{i0 + 1}", _conv(sd, f"{p}.{i0}", x, 1), train, 0.1, upd))
-    x = F.relu(_bn(sd, f"{p}.{i1 + 1}", _conv(sd, f"{p}.{i1}", x, 1), train, 0.1, upd))
+    x = _r(F.relu(_bn(sd, f"{p}.{i0 + 1}", _conv(sd, f"{p}.{i0}", x, 1), train, 0.1, upd)))
+    x = _r(F.relu(_bn(sd, f"{p}.{i1 + 1}", _conv(sd, f"{p}.{i1}", x, 1), train, 0.1, upd)))
     return x
 
 
 def basic_conv(sd, p, x, train, upd, padding=0, dilation=1, groups=1, relu=True):
     """BasicConv: src/EGM-UNet.py:958-975 (BN momentum 0.01)."""
     x = _bn(sd, p + ".bn", _conv(sd, p + ".conv", x, padding, dilation, groups), train, 0.01, upd)
-    return F.relu(x) if relu else x
+    return _r(F.relu(x) if relu else x)
 
 
 def edge_enhancer(sd, p, x, train, upd):
     """EdgeAwareFeatureEnhancer: src/EGM-UNet.py:872-886."""
-    e = x - F.avg_pool2d(x, 3, 1, 1)                      # count_include_pad=True -> /9
+    e = _r(x - F.avg_pool2d(x, 3, 1, 1))                  # count_include_pad=True -> /9
     z = _conv(sd, p + ".weight_generator.0", e)
     w = torch.sigmoid(_bn(sd, p + ".weight_generator.1", z, train, 0.1, upd))
-    return w * x + x
+    return _r(w * x + x)
 
 
 def mca_gate(sd, p, x):
@@ -103,7 +113,7 @@ def mca_layer(sd, p, x):
     var = F.avg_pool2d((u - mean) ** 2, 3, 1, 1)
     n, c, h, w = u.shape
     shuf = u.view(n, 4, c // 4, h, w).transpose(1, 2).reshape(n, c, h, w)
-    return 0.4 * u + 0.2 * rng + 0.2 * var + 0.1 * (1.1 * u) + 0.1 * shuf
+    return _r(0.4 * u + 0.2 * rng + 0.2 * var + 0.1 * (1.1 * u) + 0.1 * shuf)
 
 
 def fusion_conv(sd, p, x):
@@ -115,7 +125,7 @@ def fusion_conv(sd, p, x):
     def mlp(v):
         return F.conv2d(F.relu(F.conv2d(v, sd[p + ".channel_attention.fc.0.weight"])), sd[p + ".channel_attention.fc.2.weight"])
     ca = torch.sigmoid(mlp(F.adaptive_avg_pool2d(f, 1)) + mlp(F.adaptive_max_pool2d(f, 1)))
-    return _conv(sd, p + ".up", f + s * ca)
+    return _conv(sd, p + ".up", _r(f + s * ca))
 
 
 def grfb(sd, p, x, train, upd, visual=12, scale=0.1):
@@ -136,9 +146,10 @@ def grfb(sd, p, x, train, upd, visual=12, scale=0.1):
     c = basic_conv(sd, p + ".branch_ctx.3", c, train, upd)
     cat = torch.cat([x, d, e, c], 1)
     out = fusion_conv(sd, p + ".fusion_conv", cat)
-    out = F.relu(out * scale + basic_conv(sd, p + ".shortcut", x, train, upd, relu=False))
+    zs = _conv(sd, p + ".shortcut.conv", x)
+    out = _r(F.relu(out * scale + _bn(sd, p + ".shortcut.bn", zs, train, 0.01, upd)))
     t = torch.sigmoid(_conv(sd, p + ".target_enhancer.0", out, 1))
-    return out * (1 + t.mean(1, keepdim=True))
+    return _r(out * (1 + t.mean(1, keepdim=True)))
 
 
 def rga(sd, p, x):
@@ -147,13 +158,13 @@ def rga(sd, p, x):
     half = dim // 2
     fused = _conv(sd, p + ".proj_in", x)
     base, gates = fused[:, :half], fused[:, half:]
-    gates = _conv(sd, p + ".dwconv", gates, 1, 1, gates.shape[1]) * sd[p + ".scale"]
+    gates = _r(_conv(sd, p + ".dwconv", gates, 1, 1, gates.shape[1]) * sd[p + ".scale"])
     out = base
     for i in range(2):
         g = gates[:, i * half:(i + 1) * half]
-        g = F.gelu(_conv(sd, f"{p}.gate_convs.{i}.0", g))
+        g = _r(F.gelu(_conv(sd, f"{p}.gate_convs.{i}.0", g)))
         g = torch.sigmoid(_conv(sd, f"{p}.gate_convs.{i}.2", g))
-        out = out * g
+        out = _r(out * g)
         if i == 0:
             out = _conv(sd, p + ".transform_convs.0", out)
     return _conv(sd, p + ".proj_out", out)
@@ -166,7 +177,7 @@ def up_block(sd, p, x1, x2, train, upd):
     else:
         x1 = F.interpolate(x1, scale_factor=2, mode="bilinear", align_corners=True)
     dy, dx = x2.shape[2] - x1.shape[2], x2.shape[3] - x1.shape[3]
-    x1 = F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
+    x1 = _r(F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2]))
     return double_conv(sd, p + ".conv", torch.cat([x2, x1], 1), train, upd)
 
 
@@ -177,20 +188,20 @@ def down_block(sd, p, x, train, upd, variant):
     q = p + ".1"
     if variant == "unet":
         return double_conv(sd, q, x, train, upd)
-    x = F.relu(_bn(sd, q + ".1", _conv(sd, q + ".0", x, 1), train, 0.1, upd))
+    x = _r(F.relu(_bn(sd, q + ".1", _conv(sd, q + ".0", x, 1), train, 0.1, upd)))
     if variant == "egm":
         x = mca_layer(sd, q + ".3", x)
         c2, g = 4, 7
     else:
         c2, g = 3, 6
-    x = F.relu(_bn(sd, f"{q}.{c2 + 1}", _conv(sd, f"{q}.{c2}", x, 1), train, 0.1, upd))
+    x = _r(F.relu(_bn(sd, f"{q}.{c2 + 1}", _conv(sd, f"{q}.{c2}", x, 1), train, 0.1, upd)))
     return grfb(sd, f"{q}.{g}", x, train, upd)
 
 
 def forward(sd: Dict[str, Tensor], x: Tensor, variant: str = "egm", train: bool = True,
             bn_updates: Optional[dict] = None) -> Tensor:
     """Whole-model forward -> logits [N,num_classes,H,W]. variant in {'unet','egm','yuan'}."""
-    x1 = double_conv(sd, "in_conv", x, train, bn_updates)
+    x1 = double_conv(sd, "in_conv", _r(x), train, bn_updates)
     x2 = down_block(sd, "down1", x1, train, bn_updates, variant)
     x3 = down_block(sd, "down2", x2, train, bn_updates, variant)
     x4 = down_block(sd, "down3", x3, train, bn_updates, variant)
