@@ -303,3 +303,25 @@ extern "C" int egm_kernel_embed(float* big, float* small_, long long CoCi, int k
   k_embed<<<egm_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(big, small_, CoCi, kb, ks, mode, accumulate);
   EGM_LAUNCH_CHECK("kernel_embed"); return EGM_OK;
 }
+
+// Lift a (possibly grouped, possibly thin) conv weight to a dense zero-padded one so it can run on the tcgen05 path:
+//   mode 0: wp[CoutP][CinP][taps] (zeroed here) <- w[Cout][Cin_g][taps] placed on the block diagonal (ci = group*Cin_g + cil)
+//   mode 1: w <- the same entries read back out of wp (gradient extraction)
+__global__ void k_weight_lift(float* __restrict__ w, float* __restrict__ wp, int Cout, int Cin_g, int groups, int taps, int CinP, int mode) {
+  const int Cout_g = Cout / groups;
+  long long total = (long long)Cout * Cin_g * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int t = (int)(i % taps); long long q = i / taps; int cil = (int)(q % Cin_g); int co = (int)(q / Cin_g);
+    long long j = ((long long)co * CinP + (co / Cout_g) * Cin_g + cil) * taps + t;
+    if (mode == 0) wp[j] = w[i]; else w[i] = wp[j];
+  }
+}
+extern "C" int egm_conv_weight_lift(float* w, float* wp, int Cout, int Cin_g, int groups, int taps, int CoutP, int CinP, int mode, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  EGM_REQUIRE(CoutP >= Cout && CinP >= Cin_g * groups && Cout % groups == 0, EGM_E_SHAPE, "weight_lift: bad padded shape");
+  if (mode == 0) cudaMemsetAsync(wp, 0, sizeof(float) * (size_t)CoutP * CinP * taps, st);
+  long long total = (long long)Cout * Cin_g * taps;
+  if (total == 0) return EGM_OK;
+  k_weight_lift<<<egm_grid_for(total, 256), 256, 0, st>>>(w, wp, Cout, Cin_g, groups, taps, CinP, mode);
+  EGM_LAUNCH_CHECK("conv_weight_lift"); return EGM_OK;
+}

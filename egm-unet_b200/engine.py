@@ -170,6 +170,9 @@ def conv2d(ctx: Ctx, x: Var, weight: torch.Tensor, bias: Optional[torch.Tensor],
     cin = cig * groups
     assert (x_cin or ctot - x_coff) == cin, (x.shape, weight.shape, x_coff)
     sliced = not (x_coff == 0 and cin == ctot)
+    native_tc = ctx.use_tc and tc_ok and not sliced and abi.query("conv2d_tc_supported", cin, co, kh, kw, dilation, groups)
+    if ctx.use_tc and tc_ok and not native_tc and abi.query("conv2d_tc_supported", _pad16(cin), _pad16(co), kh, kw, dilation, 1):
+        return _conv2d_lifted(ctx, x, wparam, bparam, weight, bias, groups, dilation, x_coff, cin, wgrad_sink, bgrad_sink)
     pk = PackedConv(ctx, weight, groups, dilation, tc_ok and not sliced)
     y = ctx.empty(n, h, w, co)
     _conv_run(ctx, pk, x.t, ctot, x_coff, pk.wf, bias, y, co, 0, 0, n, h, w, cin, co)
@@ -207,6 +210,77 @@ def conv2d(ctx: Ctx, x: Var, weight: torch.Tensor, bias: Optional[torch.Tensor],
                     call("axpby", gx, tmp, ctx.code, tmp.numel(), 1.0, 1.0)
                 else:
                     call("conv2d_direct", dy, co, 0, pk.wd, None, gx, ctot, x_coff, acc, ctx.code, n, h, w, co, cin, kh, kw, dilation, groups)
+        ctx.push(bwd)
+    return out
+
+
+def _pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+def _conv2d_lifted(ctx, x, wparam, bparam, weight, bias, groups, dilation, x_coff, cin, wgrad_sink, bgrad_sink) -> Var:
+    """Thin (C < 16 or C % 16 != 0), grouped or channel-sliced conv on the tcgen05 path: activations are copied into
+    zero-padded 16-channel-aligned scratch tensors and the weight is lifted to a dense zero-padded (block-diagonal) one;
+    outputs / gradients are sliced back.  MMA work on the padding is irrelevant -- these layers are bandwidth-bound."""
+    n, h, w, ctot = x.shape
+    co, cig, kh, kw = weight.shape
+    M, taps = n * h * w, kh * kw
+    cinp, cop = _pad16(cin), _pad16(co)
+    sliced = not (x_coff == 0 and cin == ctot)
+    if cinp == ctot and not sliced:
+        xp = x.t
+    else:
+        xp = ctx.empty(n, h, w, cinp)
+        if cinp != cin:
+            call("memset_zero", xp, xp.numel() * 2)
+        call("copy_slice", x.t, xp, ctx.code, M, cin, ctot, x_coff, cinp, 0, 0)
+    wpd = torch.empty(cop, cinp, kh, kw, **ctx.f32)
+    call("conv_weight_lift", weight, wpd, co, cig, groups, taps, cop, cinp, 0)
+    bp = None
+    if bias is not None:
+        bp = ctx.zeros_f32(cop)
+        call("copy_slice", bias, bp, abi.F32, 1, co, co, 0, cop, 0, 0)
+    wf = torch.empty(wpd.numel(), dtype=torch.bfloat16, device=ctx.device)
+    wd = torch.empty(wpd.numel(), dtype=torch.bfloat16, device=ctx.device) if ctx.record else None
+    call("pack_conv_weight_tc", wpd, wf, wd, cop, cinp, kh, kw)
+    yp = ctx.empty(n, h, w, cop)
+    call("conv2d_tc", xp, wf, bp, yp, n, h, w, cinp, cop, kh, kw, dilation)
+    if cop == co:
+        y = yp
+    else:
+        y = ctx.empty(n, h, w, co)
+        call("copy_slice", yp, y, ctx.code, M, co, cop, 0, co, 0, 0)
+    out = Var(y)
+    if ctx.record:
+        def bwd():
+            dy = out.grad
+            out.grad = None
+            if dy is None:
+                return
+            if cop == co:
+                dyp = dy
+            else:
+                dyp = ctx.empty(n, h, w, cop)
+                call("memset_zero", dyp, dyp.numel() * 2)
+                call("copy_slice", dy, dyp, ctx.code, M, co, co, 0, cop, 0, 0)
+            dwpk = torch.empty(wpd.numel(), **ctx.f32)
+            call("conv2d_wgrad_tc", xp, dyp, dwpk, n, h, w, cinp, cop, kh, kw, dilation)
+            dwd = torch.empty_like(wpd)
+            call("unpack_conv_wgrad", dwpk, dwd, cop, cinp, kh, kw, 0.0)
+            dw = torch.empty_like(weight) if wgrad_sink is not None else ctx.grad_slot(wparam)
+            call("conv_weight_lift", dw, dwd, co, cig, groups, taps, cop, cinp, 1)
+            if wgrad_sink is not None:
+                wgrad_sink(dw)
+            if bias is not None:
+                gb = torch.empty(co, **ctx.f32) if bgrad_sink is not None else ctx.grad_slot(bparam)
+                call("channel_sum", dy, ctx.code, M, co, co, 0, ctx.f64(co), gb)
+                if bgrad_sink is not None:
+                    bgrad_sink(gb)
+            if x.needs_grad:
+                gxp = ctx.empty(n, h, w, cinp)
+                call("conv2d_tc", dyp, wd, None, gxp, n, h, w, cop, cinp, kh, kw, dilation)
+                gx, acc = x.grad_target(partial=sliced)
+                call("copy_slice", gxp, gx, ctx.code, M, cin, cinp, 0, ctot, x_coff, acc)
         ctx.push(bwd)
     return out
 

@@ -130,7 +130,7 @@ def grfb(ctx: Ctx, x: Var, m) -> Var:
     fo = fusion_conv(ctx, cat, m.fusion_conv)
     zs = conv_module(ctx, x, m.shortcut.conv)
     o = bn_act(ctx, zs, m.shortcut.bn, ACT_NONE, MODE_RESIDUAL, aux=fo, alpha=float(m.scale))
-    tz = conv_module(ctx, o, m.target_enhancer[0], tc_ok=False)          # [N,H,W,3]
+    tz = conv_module(ctx, o, m.target_enhancer[0])          # [N,H,W,3]
     y = Var(ctx.empty(n, h, w, o.C))
     call("mul_pixel_gate", o.t, tz.t, y.t, ctx.code, M, o.C, 3, 1)
     if ctx.record:
@@ -200,15 +200,15 @@ def rga(ctx: Ctx, x: Var, m) -> Var:
     s0, stot = m.split_sizes[0], sum(m.split_sizes)
     fused = conv_module(ctx, x, m.proj_in)
     base = slice_channels(ctx, fused, 0, s0)
-    gconv = conv_module(ctx, fused, m.dwconv, x_coff=s0, x_cin=stot, tc_ok=False)
+    gconv = conv_module(ctx, fused, m.dwconv, x_coff=s0, x_cin=stot)
     gates = _unary(ctx, gconv, 2, 2, scalar=m.scale)
     out = base
     off = 0
     for i in range(m.order):
         ci = m.split_sizes[i]
-        g = conv_module(ctx, gates, m.gate_convs[i][0], x_coff=off, x_cin=ci, tc_ok=False)
+        g = conv_module(ctx, gates, m.gate_convs[i][0], x_coff=off, x_cin=ci)
         g = _unary(ctx, g, 0, 1)
-        g = conv_module(ctx, g, m.gate_convs[i][2], tc_ok=False)
+        g = conv_module(ctx, g, m.gate_convs[i][2])
         out = _gate_mul(ctx, out, g)
         if i < m.order - 1:
             out = conv_module(ctx, out, m.transform_convs[i])
@@ -261,5 +261,5 @@ def net_forward(ctx: Ctx, model, x_nchw: torch.Tensor, variant: str):
     y = up_block(ctx, y, x3, model.up2)
     y = up_block(ctx, y, x2, model.up3)
     y = up_block(ctx, y, x1, model.up4)
-    lv = conv_module(ctx, y, model.out_conv[0], tc_ok=False)
+    lv = conv_module(ctx, y, model.out_conv[0])
     return to_nchw(ctx, lv), lv

@@ -40,6 +40,7 @@ int egm_cast_to_f32(const void* src, float* dst, int dtype, long long n, int acc
 /* ---- convolution, CUDA-core implicit GEMM (nn.Conv2d stride 1 "same": src/EGM-UNet.py:49,52,962,1211-1215,1258-1292; cuDNN/cuBLAS today) ---- */
 int egm_pack_conv_weight(const float* w, float* wf, float* wd, int Cout, int Cin_g, int kh, int kw, int groups, void* stream);
 int egm_unpack_conv_wgrad(const float* dw_packed, float* dw, int Cout, int Cin_g, int kh, int kw, float beta, void* stream);
+int egm_conv_weight_lift(float* w, float* wp, int Cout, int Cin_g, int groups, int taps, int CoutP, int CinP, int mode, void* stream);
 int egm_kernel_embed(float* big, float* small_, long long CoCi, int kb, int ks, int mode, int accumulate, void* stream);
 int egm_conv2d_direct(const void* x, long long x_cstride, long long x_coff, const float* w_packed, const float* bias, void* y,
                       long long y_cstride, long long y_coff, int accumulate, int dtype, int N, int H, int W, int Cin, int Cout,

@@ -317,3 +317,31 @@ def test_conv_tc(case):
     hs.backward(yv, g)
     assert rel_err(hs.grad(xv), xr.grad) < 1e-2, "dgrad"
     assert rel_err(hs.pgrad(mc.weight), m.weight.grad) < 1e-2, "wgrad"
+
+
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[2] * c[3] < 40])
+def test_conv_lifted_to_tc(case):
+    """thin / grouped / odd-channel convs lifted onto the tcgen05 path (zero-padded dense weights): same results as torch."""
+    from egm_unet_b200.engine import conv_module
+    cin, cout, k, dil, groups, bias, H, W = case
+    torch.manual_seed(1)
+    m = nn.Conv2d(cin, cout, k, padding=dil * (k - 1) // 2, dilation=dil, groups=groups, bias=bias)
+    with torch.no_grad():
+        m.weight.copy_(m.weight.to(torch.bfloat16).float())
+    x = _q(_rand(2, cin, H, W), torch.bfloat16)
+    g = _q(_rand(2, cout, H, W, seed=3), torch.bfloat16)
+    hs = Harness(torch.bfloat16, use_tc=True)
+    xv = hs.var(x)
+    mc = m.cuda()
+    yv = conv_module(hs.ctx, xv, mc)
+    y = hs.out(yv)
+    xr = x.clone().requires_grad_(True)
+    m = m.cpu()
+    yr = m(xr)
+    yr.backward(g)
+    assert rel_err(y, yr.detach()) < 1e-2, "forward"
+    hs.backward(yv, g)
+    assert rel_err(hs.grad(xv), xr.grad) < 1e-2, "dgrad"
+    assert rel_err(hs.pgrad(mc.weight), m.weight.grad) < 1e-2, "wgrad"
+    if bias:
+        assert rel_err(hs.pgrad(mc.bias), m.bias.grad) < 1e-2
