@@ -245,8 +245,160 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmemCols); }
 }
 
+#include <stdlib.h>
 static int pow2_cols(int c) { int v = 32; while (v < c) v <<= 1; return v; }
 static int pick_bkc(int C) { return C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16); }       // channels per K chunk (row = 128/64/32 bytes)
+
+
+// =================================================================== forward / dgrad, halo-reuse variant (small-channel layers)
+// One (16+2p)x(8+2p) input HALO tile per 16x8 output tile is fetched by a single TMA load; the k*k taps are then consumed by
+// UMMA descriptors whose start address is shifted by (r*haloW + s) rows and whose 8-row-group stride (SBO) is the halo row
+// pitch -- the 128/64/32B swizzle is a function of the absolute smem address, so shifted starts read exactly what TMA
+// wrote.  The whole packed weight tensor [taps][Cout][Cin] stays resident in smem (loaded once per CTA).  Per output tile
+// this issues 1 TMA load of ~180 rows instead of k*k loads of 128 rows + k*k weight tiles.
+struct ConvHaloParams {
+  int N, H, W, Cin, Cout, kh, kw, dil, pad;
+  int tilesH, tilesW, numTiles;
+  int rowB, haloW, haloH, haloBytes, haloStride, wTapStride, stages, tmemCols, accCols;
+};
+constexpr int HT_H = 16, HT_W = 8;
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                                                               __nv_bfloat16* __restrict__ y, const float* __restrict__ bias, ConvHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int taps = p.kh * p.kw;
+  uint8_t* sW = smem;
+  uint8_t* sA = sW + (size_t)taps * p.wTapStride;
+  uint64_t* full = (uint64_t*)(sA + (size_t)p.stages * p.haloStride);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tfull = empty + p.stages;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* wfull = tempty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(wfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    mbar_init(wfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wfull, (uint32_t)(taps * p.Cout * p.rowB));
+      for (int t = 0; t < taps; ++t) tma_load_3d(sW + (size_t)t * p.wTapStride, &tmW, wfull, 0, 0, t);
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+        int n = tile / (p.tilesH * p.tilesW); int r = tile - n * p.tilesH * p.tilesW;
+        int h0 = (r / p.tilesW) * HT_H, w0 = (r % p.tilesW) * HT_W;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], (uint32_t)p.haloBytes);
+        tma_load_4d(sA + (size_t)s * p.haloStride, &tmX, &full[s], 0, w0 - p.pad, h0 - p.pad, n);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(128, p.Cout, 0, 0);
+      const uint32_t layout = p.rowB == 128 ? 2u : (p.rowB == 64 ? 4u : 6u);
+      const uint32_t sboA = (uint32_t)(p.haloW * p.rowB), sboB = 8u * p.rowB;
+      const uint32_t w0a = smem_u32(sW);
+      mbar_wait(wfull, 0);
+      int s = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], aph ^ 1);
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(acc * p.accCols);
+        const uint32_t a0 = smem_u32(sA + (size_t)s * p.haloStride);
+        for (int t = 0; t < taps; ++t) {
+          const uint32_t aoff = (uint32_t)(((t / p.kw) * p.dil * p.haloW + (t % p.kw) * p.dil) * p.rowB);
+          for (int k = 0; k < p.rowB / 32; ++k)
+            umma_bf16(d, umma_desc(a0 + aoff + k * 32, 16, sboA, layout), umma_desc(w0a + t * p.wTapStride + k * 32, 16, sboB, layout), idesc,
+                      (t | k) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+        umma_commit(&tfull[acc]);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+        if (++acc == 2) { acc = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                       // pixel index inside the 16x8 patch (row-major, 8 wide)
+    int acc = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+      int n = tile / (p.tilesH * p.tilesW); int r = tile - n * p.tilesH * p.tilesW;
+      int h = (r / p.tilesW) * HT_H + row / HT_W, w = (r % p.tilesW) * HT_W + row % HT_W;
+      const bool valid = h < p.H && w < p.W;
+      __nv_bfloat16* yp = y + (((long long)n * p.H + h) * p.W + w) * p.Cout;
+      mbar_wait(&tfull[acc], aph);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.accCols);
+      for (int c = 0; c < p.Cout; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(t0 + c, v);
+        tmem_ld_wait();
+        if (valid) {
+          uint4 o[2]; __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
+            if (bias) { f0 += bias[c + 2 * j]; f1 += bias[c + 2 * j + 1]; }
+            ob[j] = __floats2bfloat162_rn(f0, f1);
+          }
+          *reinterpret_cast<uint4*>(yp + c) = o[0];
+          *reinterpret_cast<uint4*>(yp + c + 8) = o[1];
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; aph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmemCols); }
+}
+
+static bool halo_disabled() { static int v = -1; if (v < 0) { const char* e = getenv("EGM_NO_HALO"); v = (e && e[0] == '1') ? 1 : 0; } return v == 1; }
+// eligible: single K chunk (Cin in {16,32,64}), Cout <= 256, halo of <= 3 pixels, resident weights <= 100 KB
+static bool halo_eligible(int Cin, int Cout, int kh, int dil) {
+  if (halo_disabled()) return false;
+  if (!(Cin == 16 || Cin == 32 || Cin == 64) || Cout > 256) return false;
+  int pad = dil * (kh - 1) / 2;
+  if (pad > 3) return false;
+  long long wbytes = (long long)kh * kh * ((Cout * Cin * 2 + 1023) / 1024 * 1024);
+  return wbytes <= 100 * 1024;
+}
+static int launch_conv_halo(const void* x, const void* wpk, const float* bias, void* y, int N, int H, int W, int Cin, int Cout, int kh, int kw, int dil,
+                            cudaStream_t st) {
+  ConvHaloParams p{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
+  p.tilesH = cdiv(H, HT_H); p.tilesW = cdiv(W, HT_W); p.numTiles = N * p.tilesH * p.tilesW;
+  p.rowB = Cin * 2; p.haloW = HT_W + 2 * p.pad; p.haloH = HT_H + 2 * p.pad;
+  p.haloBytes = p.haloW * p.haloH * p.rowB; p.haloStride = (p.haloBytes + 1023) / 1024 * 1024;
+  p.wTapStride = (Cout * p.rowB + 1023) / 1024 * 1024;
+  size_t wres = (size_t)kh * kw * p.wTapStride;
+  p.stages = (int)((200 * 1024 - wres) / p.haloStride); if (p.stages > 6) p.stages = 6; if (p.stages < 2) p.stages = 2;
+  p.accCols = (Cout + 31) / 32 * 32; p.tmemCols = pow2_cols(2 * p.accCols);
+  CUtensorMap tmX, tmW;
+  int e = make_map_nhwc(&tmX, x, N, H, W, Cin, Cin, p.haloW, p.haloH); if (e) return e;
+  e = make_map_w(&tmW, wpk, kh * kw, Cout, Cin, Cin, Cout); if (e) return e;
+  size_t smem = wres + (size_t)p.stages * p.haloStride + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_conv_tc_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+  int grid = p.numTiles < egm_num_sms() ? p.numTiles : egm_num_sms();
+  k_conv_tc_halo<<<grid, TC_THREADS, smem, st>>>(tmX, tmW, (__nv_bfloat16*)y, bias, p);
+  return egm_check_launch("conv2d_tc_halo");
+}
 
 extern "C" int egm_conv2d_tc_supported(int Cin, int Cout, int kh, int kw, int dil, int groups) {
   if (groups != 1 || kh != kw || !(kh & 1) || dil < 1) return 0;
@@ -262,6 +414,7 @@ extern "C" int egm_conv2d_tc(const void* x, const void* w_packed_bf16, const flo
   EGM_REQUIRE(egm_conv2d_tc_supported(Cin, Cout, kh, kw, dil, 1), EGM_E_SHAPE, "conv2d_tc: unsupported shape %d->%d k%d", Cin, Cout, kh);
   EGM_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)w_packed_bf16 & 15) == 0, EGM_E_ALIGN, "conv2d_tc: pointers must be 16-byte aligned");
   if ((long long)N * H * W == 0) return EGM_OK;
+  if (halo_eligible(Cin, Cout, kh, dil)) return launch_conv_halo(x, w_packed_bf16, bias, y, N, H, W, Cin, Cout, kh, kw, dil, (cudaStream_t)stream);
   ConvTcParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
   p.coChunks = (Cout + 255) / 256; p.nChunk = Cout / p.coChunks;
