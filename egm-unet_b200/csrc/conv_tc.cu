@@ -70,6 +70,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+                 "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+                 "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr));
+}
+// convert 16 fp32 accumulator columns (+bias) to bf16 and store them as two 16-byte vectors
+__device__ __forceinline__ void store16(__nv_bfloat16* yp, const uint32_t* v, const float* bp) {
+  uint4 o[2]; __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
+    if (bp) { f0 += bp[2 * j]; f1 += bp[2 * j + 1]; }
+    ob[j] = __floats2bfloat162_rn(f0, f1);
+  }
+  *reinterpret_cast<uint4*>(yp) = o[0];
+  *reinterpret_cast<uint4*>(yp + 8) = o[1];
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version=1 <<46 | layout <<61
@@ -260,6 +280,8 @@ struct ConvHaloParams {
   int N, H, W, Cin, Cout, kh, kw, dil, pad;
   int tilesH, tilesW, numTiles;
   int rowB, haloW, haloH, haloBytes, haloStride, wTapStride, stages, tmemCols, accCols;
+  int nacc;                                          // TMEM accumulator buffers in flight (2..8)
+  int exp;                                           // timing experiments only (EGM_EXP): 1 = skip stores, 2 = rotate accumulators
 };
 constexpr int HT_H = 16, HT_W = 8;
 
@@ -273,14 +295,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
   uint64_t* full = (uint64_t*)(sA + (size_t)p.stages * p.haloStride);
   uint64_t* empty = full + p.stages;
   uint64_t* tfull = empty + p.stages;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* wfull = tempty + 2;
-  uint32_t* tmem_slot = (uint32_t*)(wfull + 1);
+  uint64_t* tempty = tfull + 8;
+  uint64_t* wfull = tempty + 8;
+  uint64_t* tapB = wfull + 1;                          // [taps] UMMA descriptor of each tap's resident weight tile
+  uint32_t* tapA = (uint32_t*)(tapB + 64);             // [taps] (row offset of the tap inside the halo tile) >> 4
+  uint32_t* tmem_slot = tapA + 64;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < taps) {
+    const int t = threadIdx.x;
+    const uint32_t layout = p.rowB == 128 ? 2u : (p.rowB == 64 ? 4u : 6u);
+    tapB[t] = umma_desc(smem_u32(sW + (size_t)t * p.wTapStride), 16, 8u * p.rowB, layout);
+    tapA[t] = (uint32_t)(((t / p.kw) * p.dil * p.haloW + (t % p.kw) * p.dil) * p.rowB) >> 4;
+  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    for (int i = 0; i < p.nacc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -299,8 +329,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
         int n = tile / (p.tilesH * p.tilesW); int r = tile - n * p.tilesH * p.tilesW;
         int h0 = (r / p.tilesW) * HT_H, w0 = (r % p.tilesW) * HT_W;
         mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], (uint32_t)p.haloBytes);
-        tma_load_4d(sA + (size_t)s * p.haloStride, &tmX, &full[s], 0, w0 - p.pad, h0 - p.pad, n);
+        if (p.exp & 8) { mbar_arrive(&full[s]); }
+        else {
+          mbar_expect_tx(&full[s], (uint32_t)p.haloBytes);
+          tma_load_4d(sA + (size_t)s * p.haloStride, &tmX, &full[s], 0, w0 - p.pad, h0 - p.pad, n);
+        }
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
@@ -308,8 +341,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(128, p.Cout, 0, 0);
       const uint32_t layout = p.rowB == 128 ? 2u : (p.rowB == 64 ? 4u : 6u);
-      const uint32_t sboA = (uint32_t)(p.haloW * p.rowB), sboB = 8u * p.rowB;
-      const uint32_t w0a = smem_u32(sW);
+      const uint32_t sboA = (uint32_t)(p.haloW * p.rowB);
+      const int ksteps = p.rowB / 32;
       mbar_wait(wfull, 0);
       int s = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
       for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
@@ -317,17 +350,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(acc * p.accCols);
-        const uint32_t a0 = smem_u32(sA + (size_t)s * p.haloStride);
-        for (int t = 0; t < taps; ++t) {
-          const uint32_t aoff = (uint32_t)(((t / p.kw) * p.dil * p.haloW + (t % p.kw) * p.dil) * p.rowB);
-          for (int k = 0; k < p.rowB / 32; ++k)
-            umma_bf16(d, umma_desc(a0 + aoff + k * 32, 16, sboA, layout), umma_desc(w0a + t * p.wTapStride + k * 32, 16, sboB, layout), idesc,
-                      (t | k) ? 1u : 0u);
+        const uint64_t ad0 = umma_desc(smem_u32(sA + (size_t)s * p.haloStride), 16, sboA, layout);
+        uint32_t accf = 0;
+        for (int t = 0; t < ((p.exp & 4) ? 0 : taps); ++t) {   // per tap: one 64-bit LDS (B descriptor) + one 32-bit LDS (A row offset >> 4)
+          const uint64_t ad = ad0 + tapA[t], bd = tapB[t];
+          if (ksteps == 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, accf); accf = 1; }
+          } else if (ksteps == 2) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) { umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, accf); accf = 1; }
+          } else { umma_bf16(d, ad, bd, idesc, accf); accf = 1; }
         }
         umma_commit(&empty[s]);
         umma_commit(&tfull[acc]);
         if (++s == p.stages) { s = 0; ph ^= 1; }
-        if (++acc == 2) { acc = 0; aph ^= 1; }
+        if (++acc == p.nacc) { acc = 0; aph ^= 1; }
       }
     }
   } else {
@@ -342,25 +380,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.accCols);
-      for (int c = 0; c < p.Cout; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(t0 + c, v);
-        tmem_ld_wait();
-        if (valid) {
-          uint4 o[2]; __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
-            if (bias) { f0 += bias[c + 2 * j]; f1 += bias[c + 2 * j + 1]; }
-            ob[j] = __floats2bfloat162_rn(f0, f1);
-          }
-          *reinterpret_cast<uint4*>(yp + c) = o[0];
-          *reinterpret_cast<uint4*>(yp + c + 8) = o[1];
+      if ((p.Cout & 31) == 0) {
+        for (int c = 0; c < p.Cout; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(t0 + c, v);
+          tmem_ld_wait();
+          if (valid && !(p.exp & 1)) { store16(yp + c, v, bias ? bias + c : nullptr); store16(yp + c + 16, v + 16, bias ? bias + c + 16 : nullptr); }
+        }
+      } else {
+        for (int c = 0; c < p.Cout; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(t0 + c, v);
+          tmem_ld_wait();
+          if (valid) store16(yp + c, v, bias ? bias + c : nullptr);
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
-      if (++acc == 2) { acc = 0; aph ^= 1; }
+      if (++acc == p.nacc) { acc = 0; aph ^= 1; }
     }
   }
   tc_fence_before();
@@ -387,12 +424,15 @@ static int launch_conv_halo(const void* x, const void* wpk, const float* bias, v
   p.haloBytes = p.haloW * p.haloH * p.rowB; p.haloStride = (p.haloBytes + 1023) / 1024 * 1024;
   p.wTapStride = (Cout * p.rowB + 1023) / 1024 * 1024;
   size_t wres = (size_t)kh * kw * p.wTapStride;
-  p.stages = (int)((200 * 1024 - wres) / p.haloStride); if (p.stages > 6) p.stages = 6; if (p.stages < 2) p.stages = 2;
-  p.accCols = (Cout + 31) / 32 * 32; p.tmemCols = pow2_cols(2 * p.accCols);
+  p.stages = (int)((198 * 1024 - wres) / p.haloStride); if (p.stages > 8) p.stages = 8; if (p.stages < 2) p.stages = 2;
+  p.accCols = (Cout + 31) / 32 * 32;
+  p.nacc = 512 / p.accCols; if (p.nacc > 8) p.nacc = 8; if (p.nacc < 2) p.nacc = 2;
+  { const char* ev = getenv("EGM_EXP"); p.exp = ev ? atoi(ev) : 0; const char* na = getenv("EGM_NACC"); if (na) p.nacc = atoi(na); }
+  p.tmemCols = pow2_cols(p.nacc * p.accCols);
   CUtensorMap tmX, tmW;
   int e = make_map_nhwc(&tmX, x, N, H, W, Cin, Cin, p.haloW, p.haloH); if (e) return e;
   e = make_map_w(&tmW, wpk, kh * kw, Cout, Cin, Cin, Cout); if (e) return e;
-  size_t smem = wres + (size_t)p.stages * p.haloStride + 1024 + 256;
+  size_t smem = wres + (size_t)p.stages * p.haloStride + 1024 + 1408;
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(k_conv_tc_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
   int grid = p.numTiles < egm_num_sms() ? p.numTiles : egm_num_sms();

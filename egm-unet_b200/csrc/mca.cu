@@ -162,71 +162,104 @@ __device__ __forceinline__ FVec<V> mca_u(const T* x, const McaGeom& g, int n, in
   for (int j = 0; j < V; ++j) a.v[j] = a.v[j] * ((gcv.v[j] + s) * (1.f / 3.f));
   return a;
 }
+// Three streaming passes (each 16-byte vectorised, 9-point stencils served by L1/L2) instead of one 25-point gather per output:
+//   U : u  = x * (g_c + g_h + g_w) / 3                                  (1 read, 1 write)
+//   D : d2 = (u - avg3x3(u))^2                                          (9 cached reads, 1 write)
+//   O : y  = 0.51 u + 0.2 (max3x3 u - min3x3 u) + 0.2 avg3x3(d2) + 0.1 shuffle4(u)  (+ arg-max/min byte map)
 template <typename T, int V>
-__global__ void __launch_bounds__(256) k_mca_apply(const T* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ idx, McaGeom g) {
+__global__ void k_mca_u(const T* __restrict__ x, T* __restrict__ u, McaGeom g) {
   const int CV = g.C / V;
   long long total = (long long)g.N * g.H * g.W * CV;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % CV) * V; long long p = i / CV; int w = (int)(p % g.W); long long q = p / g.W; int h = (int)(q % g.H); int n = (int)(q / g.H);
     FVec<V> gcv = ldv<V>(g.gc + n * g.C + c);
-    // u on the 5x5 neighbourhood (zero outside the image)
-    float u[5][5][V];
+    FVec<V> o = mca_u<T, V>(x, g, n, h, w, c, gcv);
+    stv<V>(u + p * g.C + c, o);
+  }
+}
+template <typename T, int V>
+__global__ void k_mca_d2(const T* __restrict__ u, T* __restrict__ d2, int N, int H, int W, int CV) {
+  const int C = CV * V; long long total = (long long)N * H * W * CV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % CV) * V; long long p = i / CV; int w = (int)(p % W); long long q = p / W; int h = (int)(q % H);
+    FVec<V> s, ctr;
 #pragma unroll
-    for (int a = 0; a < 5; ++a)
+    for (int j = 0; j < V; ++j) { s.v[j] = 0.f; ctr.v[j] = 0.f; }
 #pragma unroll
-      for (int b = 0; b < 5; ++b) {
-        int hh = h + a - 2, ww = w + b - 2;
-        if (hh >= 0 && hh < g.H && ww >= 0 && ww < g.W) { FVec<V> t = mca_u<T, V>(x, g, n, hh, ww, c, gcv);
+    for (int a = -1; a <= 1; ++a)
 #pragma unroll
-          for (int j = 0; j < V; ++j) u[a][b][j] = t.v[j]; }
-        else {
+      for (int b = -1; b <= 1; ++b) {
+        int hh = h + a, ww = w + b;
+        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+        FVec<V> t = ldv<V>(u + (p + (long long)a * W + b) * C + c);
 #pragma unroll
-          for (int j = 0; j < V; ++j) u[a][b][j] = 0.f; }
+        for (int j = 0; j < V; ++j) s.v[j] += t.v[j];
+        if (a == 0 && b == 0) ctr = t;
       }
-    FVec<V> o; unsigned char code[V];
+    FVec<V> o;
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      float mx = -INFINITY, mn = INFINITY; int amx = 4, amn = 4; float var = 0.f;
+    for (int j = 0; j < V; ++j) { float d = ctr.v[j] - s.v[j] * (1.f / 9.f); o.v[j] = d * d; }
+    stv<V>(d2 + p * C + c, o);
+  }
+}
+template <typename T, int V>
+__global__ void k_mca_out(const T* __restrict__ u, const T* __restrict__ d2, T* __restrict__ y, unsigned char* __restrict__ idx, int N, int H, int W, int CV) {
+  const int C = CV * V; long long total = (long long)N * H * W * CV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % CV) * V; long long p = i / CV; int w = (int)(p % W); long long q = p / W; int h = (int)(q % H);
+    float mx[V], mn[V], var[V], uc[V]; int amx[V], amn[V];
 #pragma unroll
-      for (int a = 0; a < 3; ++a)
+    for (int j = 0; j < V; ++j) { mx[j] = -INFINITY; mn[j] = INFINITY; var[j] = 0.f; uc[j] = 0.f; amx[j] = 4; amn[j] = 4; }
 #pragma unroll
-        for (int b = 0; b < 3; ++b) {
-          int hh = h + a - 1, ww = w + b - 1;
-          if (hh < 0 || hh >= g.H || ww < 0 || ww >= g.W) continue;
-          float v = u[a + 1][b + 1][j];
-          if (v > mx) { mx = v; amx = a * 3 + b; }
-          if (v < mn) { mn = v; amn = a * 3 + b; }
-          float m = 0.f;
+    for (int a = 0; a < 3; ++a)
 #pragma unroll
-          for (int e = 0; e < 3; ++e)
+      for (int b = 0; b < 3; ++b) {
+        int hh = h + a - 1, ww = w + b - 1;
+        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+        long long off = (p + (long long)(a - 1) * W + (b - 1)) * C + c;
+        FVec<V> t = ldv<V>(u + off), d = ldv<V>(d2 + off);
 #pragma unroll
-            for (int f = 0; f < 3; ++f) m += u[a + e][b + f][j];
-          float d = v - m * (1.f / 9.f);
-          var += d * d;
+        for (int j = 0; j < V; ++j) {
+          if (t.v[j] > mx[j]) { mx[j] = t.v[j]; amx[j] = a * 3 + b; }
+          if (t.v[j] < mn[j]) { mn[j] = t.v[j]; amn[j] = a * 3 + b; }
+          var[j] += d.v[j];
+          if (a == 1 && b == 1) uc[j] = t.v[j];
         }
-      o.v[j] = 0.51f * u[2][2][j] + 0.2f * (mx - mn) + 0.2f * var * (1.f / 9.f);
-      code[j] = (unsigned char)(amx | (amn << 4));
-    }
-    // channel shuffle (groups=4): out[c'] = u[(c' % 4) * (C/4) + c' / 4] at the same pixel
-    const T* xp = x + p * g.C; float s = g.gh[n * g.H + h] + g.gw[n * g.W + w];
+      }
+    FVec<V> o;
+    const T* up = u + p * C;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      int cc = c + j, src = (cc & 3) * (g.C >> 2) + (cc >> 2);
-      o.v[j] += 0.1f * ldf(xp + src) * ((g.gc[n * g.C + src] + s) * (1.f / 3.f));
+      int cc = c + j, src = (cc & 3) * (C >> 2) + (cc >> 2);          // channel shuffle (groups = 4)
+      o.v[j] = 0.51f * uc[j] + 0.2f * (mx[j] - mn[j]) + 0.2f * var[j] * (1.f / 9.f) + 0.1f * ldf(up + src);
     }
-    stv<V>(y + p * g.C + c, o);
+    stv<V>(y + p * C + c, o);
     if (idx) {
 #pragma unroll
-      for (int j = 0; j < V; ++j) idx[p * g.C + c + j] = code[j];
+      for (int j = 0; j < V; ++j) idx[p * C + c + j] = (unsigned char)(amx[j] | (amn[j] << 4));
     }
   }
 }
-extern "C" int egm_mca_apply(const void* x, const float* gates, void* y, unsigned char* argidx, int dtype, int N, int H, int W, int C, void* stream) {
+// u_scratch, d2_scratch: two tensors shaped like x (caller-owned); u_scratch holds u = x_out of the reference on return
+extern "C" int egm_mca_apply(const void* x, const float* gates, void* y, unsigned char* argidx, void* u_scratch, void* d2_scratch, int dtype, int N, int H,
+                             int W, int C, void* stream) {
   EGM_REQUIRE(C % 4 == 0, EGM_E_SHAPE, "mca: C %% 4 != 0");
   long long total = (long long)N * H * W * C;
   if (total == 0) return EGM_OK;
   McaGeom g{N, H, W, C, gates, gates + mca_ow(N, H), gates + mca_oc(N, H, W)};
-  EGM_DISPATCH_DTYPE(dtype, (k_mca_apply<T, 2><<<egm_grid_for(total / 2, 256, 16), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, argidx, g)));
+  cudaStream_t st = (cudaStream_t)stream;
+  int v = egm_pick_vec(C); if (v > 8) v = 8; if (v < 4) v = 4;
+  EGM_DISPATCH_DTYPE(dtype, {
+    if (v == 8) {
+      k_mca_u<T, 8><<<egm_grid_for(total / 8, 256), 256, 0, st>>>((const T*)x, (T*)u_scratch, g);
+      k_mca_d2<T, 8><<<egm_grid_for(total / 8, 256), 256, 0, st>>>((const T*)u_scratch, (T*)d2_scratch, N, H, W, C / 8);
+      k_mca_out<T, 8><<<egm_grid_for(total / 8, 256), 256, 0, st>>>((const T*)u_scratch, (const T*)d2_scratch, (T*)y, argidx, N, H, W, C / 8);
+    } else {
+      k_mca_u<T, 4><<<egm_grid_for(total / 4, 256), 256, 0, st>>>((const T*)x, (T*)u_scratch, g);
+      k_mca_d2<T, 4><<<egm_grid_for(total / 4, 256), 256, 0, st>>>((const T*)u_scratch, (T*)d2_scratch, N, H, W, C / 4);
+      k_mca_out<T, 4><<<egm_grid_for(total / 4, 256), 256, 0, st>>>((const T*)u_scratch, (const T*)d2_scratch, (T*)y, argidx, N, H, W, C / 4);
+    }
+  });
   EGM_LAUNCH_CHECK("mca_apply"); return EGM_OK;
 }
 

@@ -440,7 +440,7 @@ def mca_layer(ctx: Ctx, x: Var, m) -> Var:
     call("mca_gates", sums, n, h, w, c, *P, gates, avg, std)
     y = Var(ctx.empty(n, h, w, c))
     idx = torch.empty(n * h * w * c, dtype=torch.uint8, device=ctx.device) if ctx.record else None
-    call("mca_apply", x.t, gates, y.t, idx, ctx.code, n, h, w, c)
+    call("mca_apply", x.t, gates, y.t, idx, ctx.empty(n, h, w, c), ctx.empty(n, h, w, c), ctx.code, n, h, w, c)
     if ctx.record:
         def bwd():
             dy, y.grad = y.grad, None

@@ -89,7 +89,8 @@ int egm_mca_stats(const void* x, int dtype, int N, int H, int W, int C, double* 
 int egm_mca_prod_sums(const void* a, const void* b, int dtype, int N, int H, int W, int C, double* sums, void* stream);
 int egm_mca_gates(const double* sums, int N, int H, int W, int C, const float* w_h, const float* k_h, int ks_h, const float* w_w,
                   const float* k_w, int ks_w, const float* w_c, const float* k_c, int ks_c, float* gates, float* avg, float* stdv, void* stream);
-int egm_mca_apply(const void* x, const float* gates, void* y, unsigned char* argidx, int dtype, int N, int H, int W, int C, void* stream);
+int egm_mca_apply(const void* x, const float* gates, void* y, unsigned char* argidx, void* u_scratch, void* d2_scratch, int dtype, int N, int H,
+                  int W, int C, void* stream);
 int egm_mca_bwd_du(const void* x, const float* gates, const void* dy, const unsigned char* argidx, void* E_scratch, void* du, int dtype, int N,
                    int H, int W, int C, void* stream);
 int egm_mca_gates_bwd(const double* dG, int N, int H, int W, int C, const float* gates, const float* avg, const float* stdv, const float* w_h,
