@@ -606,6 +606,163 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmemCols); }
 }
 
+
+// =================================================================== wgrad, halo-reuse variant
+// Work unit = (Cout chunk, Cin chunk nch, group of R kernel rows) x pixel split.  Per 16x8 pixel tile ONE dY tile and ONE X
+// halo tile are fetched; one MMA per (16-pixel K-step, kernel row) covers the kw taps of that row at once: the B operand is
+// MN-major with N = kw*nch, whose N-atoms (one per tap) are the halo tile shifted by `dil` rows (LBO = dil*rowB) -- legal
+// because the swizzle is a function of the absolute smem address.  8*R MMAs and 2-3 TMA loads per tile instead of 72 / 12.
+struct WgradHaloParams {
+  int N, H, W, Cin, Cout, kh, kw, dil, pad;
+  int tilesH, tilesW, numTiles;
+  int coChunks, ciChunks, rowGroups, rowsPerGroup, splits, tilesPerSplit;
+  int mch, nch, mAtoms, aAtomCh, aAtomBytes, aBytes, rowA, rowB, haloW, haloH, haloBytes, haloStride, stageBytes, stages, tmemCols;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                                                                float* __restrict__ dwp, WgradHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + (size_t)p.stages * p.stageBytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tfull = empty + p.stages;
+  uint32_t* tmem_slot = (uint32_t*)(tfull + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int u = blockIdx.x;
+  const int sp = u % p.splits; u /= p.splits;
+  const int cic = u % p.ciChunks; u /= p.ciChunks;
+  const int coc = u % p.coChunks; u /= p.coChunks;
+  const int r0 = u * p.rowsPerGroup;                                   // first kernel row of this unit
+  const int R = (p.kh - r0) < p.rowsPerGroup ? (p.kh - r0) : p.rowsPerGroup;
+  const int nN = p.kw * p.nch;                                         // UMMA N: all taps of one kernel row
+  const int tileBeg = sp * p.tilesPerSplit;
+  int tileEnd = tileBeg + p.tilesPerSplit; if (tileEnd > p.numTiles) tileEnd = p.numTiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = tileBeg; tile < tileEnd; ++tile) {
+        int n = tile / (p.tilesH * p.tilesW); int r = tile - n * p.tilesH * p.tilesW;
+        int h0 = (r / p.tilesW) * HT_H, w0 = (r % p.tilesW) * HT_W;
+        uint8_t* st = smem + (size_t)s * p.stageBytes;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], (uint32_t)(p.mAtoms * p.aAtomBytes + p.haloBytes));
+        for (int a = 0; a < p.mAtoms; ++a)
+          tma_load_4d(st + (size_t)a * p.aAtomBytes, &tmDY, &full[s], coc * p.mch + a * p.aAtomCh, w0, h0, n);
+        tma_load_4d(st + p.aBytes, &tmX, &full[s], cic * p.nch, w0 - p.pad, h0 - p.pad, n);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(128, nN, 1, 1);
+      const uint32_t layA = p.rowA == 128 ? 2u : (p.rowA == 64 ? 4u : 6u), layB = p.rowB == 128 ? 2u : (p.rowB == 64 ? 4u : 6u);
+      const uint32_t kA = (uint32_t)(16 * p.rowA) >> 4;                 // A advance per 16-pixel K step (16-byte units)
+      const uint32_t kB = (uint32_t)(2 * p.haloW * p.rowB) >> 4;        // B advance per K step: two halo rows
+      const uint32_t rB = (uint32_t)(p.dil * p.haloW * p.rowB) >> 4;    // B advance per kernel row
+      int s = 0; uint32_t ph = 0; uint32_t accf = 0;
+      for (int tile = tileBeg; tile < tileEnd; ++tile) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem + (size_t)s * p.stageBytes);
+        const uint64_t ad0 = umma_desc(a0, (uint32_t)p.aAtomBytes, 8u * p.rowA, layA);
+        const uint64_t bd0 = umma_desc(a0 + p.aBytes, (uint32_t)(p.dil * p.rowB), (uint32_t)(p.haloW * p.rowB), layB) + (uint64_t)(r0 * rB);
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t ad = ad0 + k * kA;
+          uint64_t bd = bd0 + k * kB;
+          uint32_t dcol = tmem_base;
+          for (int r = 0; r < R; ++r) { umma_bf16(dcol, ad, bd, idesc, accf); bd += rB; dcol += (uint32_t)nN; }
+          accf = 1;
+        }
+        umma_commit(&empty[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+      umma_commit(tfull);
+    }
+  } else if (tileBeg < tileEnd) {
+    const int q = warp & 3;
+    const int co_local = q * 32 + lane;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int co = coc * p.mch + co_local;
+    const bool valid = co_local < p.mch;
+    if (q * 32 < p.mch) {
+      for (int r = 0; r < R; ++r)
+        for (int sidx = 0; sidx < p.kw; ++sidx) {
+          const int tap = (r0 + r) * p.kw + sidx;
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * nN + sidx * p.nch);
+          for (int c = 0; c < p.nch; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(ta + c, v);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                atomicAdd(dwp + ((long long)tap * p.Cin + cic * p.nch + c + i) * p.Cout + co, __uint_as_float(v[i]));
+            }
+          }
+        }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmemCols); }
+}
+
+static bool wgrad_halo_eligible(int Cin, int Cout, int kh, int kw, int dil) {
+  if (halo_disabled()) return false;
+  int pad = dil * (kh - 1) / 2;
+  if (pad > 3) return false;
+  int nch = pick_bkc(Cin);
+  return kw * nch <= 256;
+}
+static int launch_wgrad_halo(const void* x, const void* dy, float* dwp, int N, int H, int W, int Cin, int Cout, int kh, int kw, int dil, cudaStream_t st) {
+  WgradHaloParams p{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
+  p.tilesH = cdiv(H, HT_H); p.tilesW = cdiv(W, HT_W); p.numTiles = N * p.tilesH * p.tilesW;
+  p.mch = Cout % 128 == 0 ? 128 : pick_bkc(Cout);
+  p.aAtomCh = p.mch >= 64 ? 64 : p.mch; p.mAtoms = p.mch / p.aAtomCh;
+  p.rowA = p.aAtomCh * 2; p.aAtomBytes = TILE_PIX * p.rowA;
+  p.aBytes = (128 / p.aAtomCh) * p.aAtomBytes;                         // the M=128 MMA addresses 128/aAtomCh atoms (only mAtoms are loaded)
+  p.nch = pick_bkc(Cin); p.rowB = p.nch * 2;
+  p.haloW = HT_W + 2 * p.pad; p.haloH = HT_H + 2 * p.pad;
+  p.haloBytes = p.haloW * p.haloH * p.rowB; p.haloStride = (p.haloBytes + (kw - 1) * dil * p.rowB + 1023) / 1024 * 1024;   // + slack read by the last taps
+  p.stageBytes = p.aBytes + p.haloStride;
+  p.stages = (200 * 1024) / p.stageBytes; if (p.stages > 6) p.stages = 6; if (p.stages < 2) p.stages = 2;
+  int perRow = kw * p.nch;
+  p.rowsPerGroup = 512 / perRow; if (p.rowsPerGroup > kh) p.rowsPerGroup = kh;
+  p.rowGroups = cdiv(kh, p.rowsPerGroup);
+  p.tmemCols = pow2_cols(p.rowsPerGroup * perRow);
+  p.coChunks = Cout / p.mch; p.ciChunks = Cin / p.nch;
+  long long units = (long long)p.rowGroups * p.coChunks * p.ciChunks;
+  long long want = ((long long)egm_num_sms() * 2 + units - 1) / units;
+  if (want > p.numTiles) want = p.numTiles; if (want < 1) want = 1;
+  p.tilesPerSplit = cdiv(p.numTiles, want); p.splits = cdiv(p.numTiles, p.tilesPerSplit);
+  CUtensorMap tmDY, tmX;
+  int e = make_map_nhwc(&tmDY, dy, N, H, W, Cout, p.aAtomCh, HT_W, HT_H); if (e) return e;
+  e = make_map_nhwc(&tmX, x, N, H, W, Cin, p.nch, p.haloW, p.haloH); if (e) return e;
+  size_t smem = (size_t)p.stages * p.stageBytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_wgrad_tc_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+  long long grid = units * p.splits;
+  EGM_REQUIRE(grid < (1ll << 31), EGM_E_SHAPE, "wgrad_tc: grid too large");
+  k_wgrad_tc_halo<<<(unsigned)grid, TC_THREADS, smem, st>>>(tmDY, tmX, dwp, p);
+  return egm_check_launch("conv2d_wgrad_tc_halo");
+}
+
 // dw_packed fp32 [taps][Cin][Cout] (same layout as the direct path; zeroed here)
 extern "C" int egm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_packed, int N, int H, int W, int Cin, int Cout, int kh, int kw, int dil,
                                    void* stream) {
@@ -613,6 +770,7 @@ extern "C" int egm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_pack
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(dw_packed, 0, sizeof(float) * (size_t)kh * kw * Cin * Cout, st);
   if ((long long)N * H * W == 0) return EGM_OK;
+  if (wgrad_halo_eligible(Cin, Cout, kh, kw, dil)) return launch_wgrad_halo(x, dy, dw_packed, N, H, W, Cin, Cout, kh, kw, dil, st);
   WgradParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
   p.tilesH = cdiv(H, TILE_H); p.tilesW = cdiv(W, TILE_W); p.numTiles = N * p.tilesH * p.tilesW;
