@@ -112,6 +112,7 @@ def main():
     ap.add_argument("--variant", default="egm")
     ap.add_argument("--check-mode", action="store_true", help="fp32 check mode (not a bench number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel CUDA-event breakdown of one step here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -138,7 +139,8 @@ def main():
     model = model.to(dev).train()
     if args.check_mode:
         model.set_check_mode(True)
-    tr = Trainer(model, lr=0.02, momentum=0.9, weight_decay=1e-4, class_weight=[1.0, 2.0], ignore_index=255)
+    tr = Trainer(model, lr=0.02, momentum=0.9, weight_decay=1e-4, class_weight=[1.0, 2.0], ignore_index=255, use_graph=not args.no_graph)
+    tr_eager = tr if args.no_graph else None
     if world > 1:   # identical replicas: broadcast rank 0's parameters / buffers once
         dist.broadcast(tr.store.params, 0)
         for b in model.buffers():
@@ -186,7 +188,11 @@ def main():
     sampler.join(timeout=3)
 
     # ---- per-kernel breakdown of ONE step with CUDA events on the launch stream (outside the timed region)
+    tr.use_graph = False                    # the per-kernel event breakdown needs real launches
+    launches_eager0 = abi.LAUNCH_COUNTER[0]
     prof = abi.profile_step(step_resident)
+    if launches == 0:
+        launches = abi.LAUNCH_COUNTER[0] - launches_eager0     # kernels inside one replayed graph == kernels of one eager step
     tc_ms = sum(v["ms"] for k, v in prof.items() if k in ("conv2d_tc", "conv2d_wgrad_tc"))
     flops = doubleconv_flops_per_image() * args.batch
     peaks = {}
@@ -223,7 +229,7 @@ def main():
                                        f"batch {args.batch}/GPU, 3x{H}x{W}, 2 classes", "global_batch": gb, "parallelism": f"dp{world}",
                            "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush needed"},
                 "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
-                "gpu_launches": int(launches), "roofline": roof, "clocks": sampler.summary()}
+                "gpu_launches": int(launches), "cuda_graph": not args.no_graph, "roofline": roof, "clocks": sampler.summary()}
         if cb is not None:
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)

@@ -104,7 +104,7 @@ def call(name: str, *args):
     if _PROFILE is not None:
         e1.record()
         key = name
-        if _PROFILE_DETAIL and name.startswith("conv2d"):
+        if _PROFILE_DETAIL and (name.startswith("conv2d") or name.startswith("bn_act") or name in ("bn_stats", "copy_slice", "mca_bwd_du", "highpass3")):
             key = name + ":" + ",".join(str(a) for a in args if isinstance(a, int))
         _PROFILE.append((key, e0, e1))
     LAUNCH_COUNTER[0] += 1

@@ -23,6 +23,7 @@ __device__ __forceinline__ void chan_reduce(F f, long long M, int C, double* __r
   for (int k = 0; k < K; ++k)
 #pragma unroll
     for (int j = 0; j < V; ++j) acc[k][j] = 0.f;
+  f.prepare(cv * V);                                    // per-channel constants live in registers for the whole loop
   if (r < rpi)
     for (long long m = (long long)blockIdx.x * rpi + r; m < M; m += (long long)gridDim.x * rpi) f(m, cv * V, acc);
   // smem layout [rpi][K][C]
@@ -51,6 +52,7 @@ static inline int reduce_blocks(long long M, int threads, int C, int V) {
 template <typename T, int V>
 struct StatsF {
   const T* x; long long cs, co;
+  __device__ void prepare(int) {}
   __device__ void operator()(long long m, int c, float (&acc)[2][V]) const {
     FVec<V> a = ldv<V>(x + m * cs + co + c);
 #pragma unroll
@@ -108,10 +110,11 @@ extern "C" int egm_bn_finalize(const double* sums, long long M, const float* gam
 template <typename T, int V>
 __global__ void k_bn_act_fwd(const T* __restrict__ z, long long zcs, long long zco, BnArgs a, const T* __restrict__ aux, T* __restrict__ y,
                              long long ycs, long long yco, long long M, int CV) {
-  long long total = M * CV;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long m = i / CV; int c = (int)(i - m * CV) * V;
-    FVec<V> zv = ldv<V>(z + m * zcs + zco + c), sc = ldv<V>(a.scale + c), sh = ldv<V>(a.shift + c), xv, o;
+  // blockDim.x = CV * rpb: every thread keeps ONE channel vector, so scale/shift are loaded once
+  const int rpb = blockDim.x / CV, cv = threadIdx.x % CV, r = threadIdx.x / CV, c = cv * V;
+  const FVec<V> sc = ldv<V>(a.scale + c), sh = ldv<V>(a.shift + c);
+  for (long long m = (long long)blockIdx.x * rpb + r; m < M; m += (long long)gridDim.x * rpb) {
+    FVec<V> zv = ldv<V>(z + m * zcs + zco + c), xv, o;
     if (a.mode != 0) xv = ldv<V>(aux + m * (long long)(CV * V) + c);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -123,13 +126,20 @@ __global__ void k_bn_act_fwd(const T* __restrict__ z, long long zcs, long long z
     stv<V>(y + m * ycs + yco + c, o);
   }
 }
+static inline int ew_blocks(long long M, int threads, int C, int V) {
+  int rpb = threads / (C / V);
+  long long b = (M + (long long)rpb * 4 - 1) / ((long long)rpb * 4);
+  long long cap = (long long)egm_num_sms() * 8;
+  if (b > cap) b = cap; if (b < 1) b = 1; return (int)b;
+}
 extern "C" int egm_bn_act_fwd(const void* z, long long z_cstride, long long z_coff, const float* scale, const float* shift, int act, int mode,
                               const void* aux, float alpha, void* y, long long y_cstride, long long y_coff, int dtype, long long M, int C, void* stream) {
   if (M * C == 0) return EGM_OK;
   EGM_REQUIRE(mode == 0 || aux, EGM_E_BADARG, "bn_act_fwd: mode %d needs aux", mode);
   int v = egm_pick_vec(C, z_cstride, z_coff), v2 = egm_pick_vec(C, y_cstride, y_coff); if (v2 < v) v = v2;
   BnArgs a{scale, shift, nullptr, nullptr, nullptr, act, mode, alpha};
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_act_fwd<T, V><<<egm_grid_for(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>(
+  const int threads = reduce_threads(C, v);
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_act_fwd<T, V><<<ew_blocks(M, threads, C, V), threads, 0, (cudaStream_t)stream>>>(
       (const T*)z, z_cstride, z_coff, a, (const T*)aux, (T*)y, y_cstride, y_coff, M, C / V))));
   EGM_LAUNCH_CHECK("bn_act_fwd"); return EGM_OK;
 }
@@ -152,9 +162,10 @@ __device__ __forceinline__ void bn_local_grad(const BnArgs& a, float dy, float z
 template <typename T, int V>
 struct BwdRedF {
   const T* dy; long long dcs, dco; const T* z; const T* aux; BnArgs a; int C;
+  FVec<V> sc, sh, mu, rs;
+  __device__ void prepare(int c) { sc = ldv<V>(a.scale + c); sh = ldv<V>(a.shift + c); mu = ldv<V>(a.mean + c); rs = ldv<V>(a.rstd + c); }
   __device__ void operator()(long long m, int c, float (&acc)[2][V]) const {
-    FVec<V> d = ldv<V>(dy + m * dcs + dco + c), zv = ldv<V>(z + m * (long long)C + c), sc = ldv<V>(a.scale + c), sh = ldv<V>(a.shift + c),
-            mu = ldv<V>(a.mean + c), rs = ldv<V>(a.rstd + c), xv;
+    FVec<V> d = ldv<V>(dy + m * dcs + dco + c), zv = ldv<V>(z + m * (long long)C + c), xv;
     if (a.mode != 0) xv = ldv<V>(aux + m * (long long)C + c);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -174,11 +185,11 @@ extern "C" int egm_bn_act_bwd_reduce(const void* dy, long long dy_cstride, long 
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
   if (M == 0) return EGM_OK;
-  int v = egm_pick_vec(C, dy_cstride, dy_coff);
+  int v = egm_pick_vec(C, dy_cstride, dy_coff); if (v > 4) v = 4;      // 4-wide: fewer live registers -> more warps in flight (streaming kernel)
   int threads = reduce_threads(C, v); size_t sm = (size_t)(threads / (C / v)) * 2 * C * sizeof(float);
   BnArgs a{scale, shift, mean, rstd, nullptr, act, mode, alpha};
   EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_bwd_reduce<T, V><<<reduce_blocks(M, threads, C, v), threads, sm, st>>>(
-      BwdRedF<T, V>{(const T*)dy, dy_cstride, dy_coff, (const T*)z, (const T*)aux, a, C}, M, C, sums))));
+      BwdRedF<T, V>{(const T*)dy, dy_cstride, dy_coff, (const T*)z, (const T*)aux, a, C, {}, {}, {}, {}}, M, C, sums))));
   EGM_LAUNCH_CHECK("bn_act_bwd_reduce"); return EGM_OK;
 }
 
@@ -204,11 +215,11 @@ template <typename T, int V>
 __global__ void k_bn_bwd_apply(const T* __restrict__ dy, long long dcs, long long dco, const T* __restrict__ z, const T* __restrict__ aux, BnArgs a,
                                T* __restrict__ dz, T* __restrict__ daux, int daux_acc, long long M, int CV) {
   const int C = CV * V;
-  long long total = M * CV;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long m = i / CV; int c = (int)(i - m * CV) * V;
-    FVec<V> d = ldv<V>(dy + m * dcs + dco + c), zv = ldv<V>(z + m * (long long)C + c), sc = ldv<V>(a.scale + c), sh = ldv<V>(a.shift + c),
-            mu = ldv<V>(a.mean + c), rs = ldv<V>(a.rstd + c), k0 = ldv<V>(a.coef + c), k1 = ldv<V>(a.coef + C + c), k2 = ldv<V>(a.coef + 2 * C + c), xv, o, oa;
+  const int rpb = blockDim.x / CV, cv = threadIdx.x % CV, r = threadIdx.x / CV, c = cv * V;
+  const FVec<V> sc = ldv<V>(a.scale + c), sh = ldv<V>(a.shift + c), mu = ldv<V>(a.mean + c), rs = ldv<V>(a.rstd + c),
+                k0 = ldv<V>(a.coef + c), k1 = ldv<V>(a.coef + C + c), k2 = ldv<V>(a.coef + 2 * C + c);
+  for (long long m = (long long)blockIdx.x * rpb + r; m < M; m += (long long)gridDim.x * rpb) {
+    FVec<V> d = ldv<V>(dy + m * dcs + dco + c), zv = ldv<V>(z + m * (long long)C + c), xv, o, oa;
     if (a.mode != 0) xv = ldv<V>(aux + m * (long long)C + c);
     if (a.mode != 0 && daux && daux_acc) oa = ldv<V>(daux + m * (long long)C + c);
 #pragma unroll
@@ -226,9 +237,10 @@ extern "C" int egm_bn_act_bwd_apply(const void* dy, long long dy_cstride, long l
                                     const float* mean, const float* rstd, const float* coef, int act, int mode, const void* aux, float alpha,
                                     void* dz, void* daux, int daux_accumulate, int dtype, long long M, int C, void* stream) {
   if (M * C == 0) return EGM_OK;
-  int v = egm_pick_vec(C, dy_cstride, dy_coff);
+  int v = egm_pick_vec(C, dy_cstride, dy_coff); if (v > 4) v = 4;
   BnArgs a{scale, shift, mean, rstd, coef, act, mode, alpha};
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_bwd_apply<T, V><<<egm_grid_for(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>(
+  const int threads = reduce_threads(C, v);
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_bwd_apply<T, V><<<ew_blocks(M, threads, C, V), threads, 0, (cudaStream_t)stream>>>(
       (const T*)dy, dy_cstride, dy_coff, (const T*)z, (const T*)aux, a, (T*)dz, (T*)daux, daux_accumulate, M, C / V))));
   EGM_LAUNCH_CHECK("bn_act_bwd_apply"); return EGM_OK;
 }
@@ -237,6 +249,7 @@ extern "C" int egm_bn_act_bwd_apply(const void* dy, long long dy_cstride, long l
 template <typename T, int V>
 struct SumF {
   const T* x; long long cs, co;
+  __device__ void prepare(int) {}
   __device__ void operator()(long long m, int c, float (&acc)[1][V]) const {
     FVec<V> a = ldv<V>(x + m * cs + co + c);
 #pragma unroll

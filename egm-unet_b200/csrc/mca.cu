@@ -235,8 +235,11 @@ __global__ void k_mca_out(const T* __restrict__ u, const T* __restrict__ d2, T* 
     }
     stv<V>(y + p * C + c, o);
     if (idx) {
+      unsigned char codes[V];
 #pragma unroll
-      for (int j = 0; j < V; ++j) idx[p * C + c + j] = (unsigned char)(amx[j] | (amn[j] << 4));
+      for (int j = 0; j < V; ++j) codes[j] = (unsigned char)(amx[j] | (amn[j] << 4));
+      if constexpr (V == 8) *reinterpret_cast<uint2*>(idx + p * C + c) = *reinterpret_cast<uint2*>(codes);
+      else *reinterpret_cast<unsigned int*>(idx + p * C + c) = *reinterpret_cast<unsigned int*>(codes);
     }
   }
 }
@@ -311,9 +314,13 @@ __global__ void __launch_bounds__(256) k_mca_bwd_du(const T* __restrict__ dy, co
         long long off = (((long long)n * g.H + hh) * g.W + ww) * g.C + c;
         FVec<V> d = ldv<V>(dy + off), e = ldv<V>(E + off);
         int want = (1 - a) * 3 + (1 - b);          // position of (h,w) inside the window centred at (hh,ww)
+        unsigned char codes[V];                    // V arg-index bytes in one aligned load
+        if constexpr (V == 8) *reinterpret_cast<uint2*>(codes) = *reinterpret_cast<const uint2*>(idx + off);
+        else if constexpr (V == 4) *reinterpret_cast<unsigned int*>(codes) = *reinterpret_cast<const unsigned int*>(idx + off);
+        else { for (int j = 0; j < V; ++j) codes[j] = idx[off + j]; }
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-          unsigned char code = idx[off + j];
+          unsigned char code = codes[j];
           float r = ((code & 15) == want ? d.v[j] : 0.f) - ((code >> 4) == want ? d.v[j] : 0.f);
           o.v[j] += 0.2f * r; se.v[j] += e.v[j];
           if (a == 0 && b == 0) o.v[j] += 0.51f * d.v[j] + e.v[j];
@@ -335,8 +342,13 @@ extern "C" int egm_mca_bwd_du(const void* x, const float* gates, const void* dy,
   McaGeom g{N, H, W, C, gates, gates + mca_ow(N, H), gates + mca_oc(N, H, W)};
   cudaStream_t st = (cudaStream_t)stream;
   EGM_DISPATCH_DTYPE(dtype, {
-    k_mca_bwd_e<T, 4><<<egm_grid_for(total / 4, 256, 16), 256, 0, st>>>((const T*)x, (const T*)dy, (T*)E_scratch, g);
-    k_mca_bwd_du<T, 4><<<egm_grid_for(total / 4, 256, 16), 256, 0, st>>>((const T*)dy, argidx, (const T*)E_scratch, (T*)du, g);
+    if (C % 8 == 0) {
+      k_mca_bwd_e<T, 8><<<egm_grid_for(total / 8, 256, 16), 256, 0, st>>>((const T*)x, (const T*)dy, (T*)E_scratch, g);
+      k_mca_bwd_du<T, 8><<<egm_grid_for(total / 8, 256, 16), 256, 0, st>>>((const T*)dy, argidx, (const T*)E_scratch, (T*)du, g);
+    } else {
+      k_mca_bwd_e<T, 4><<<egm_grid_for(total / 4, 256, 16), 256, 0, st>>>((const T*)x, (const T*)dy, (T*)E_scratch, g);
+      k_mca_bwd_du<T, 4><<<egm_grid_for(total / 4, 256, 16), 256, 0, st>>>((const T*)dy, argidx, (const T*)E_scratch, (T*)du, g);
+    }
   });
   EGM_LAUNCH_CHECK("mca_bwd_du"); return EGM_OK;
 }

@@ -22,7 +22,7 @@ from .ddp import BucketReducer
 class Trainer:
     def __init__(self, model, lr: float = 0.02, momentum: float = 0.9, weight_decay: float = 1e-4,
                  class_weight: Optional[Sequence[float]] = (1.0, 2.0), ignore_index: int = 255, dice: bool = True,
-                 process_group=None, num_buckets: int = 4):
+                 process_group=None, num_buckets: int = 4, use_graph: bool = False):
         self.model = model
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
@@ -40,6 +40,10 @@ class Trainer:
         self.loss_terms = None
         self.comm_stream = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
         self.num_buckets = num_buckets
+        self.use_graph = use_graph
+        self._graph = None            # CUDA graph of forward + loss + backward (+ SGD when single-rank)
+        self._gkey = None
+        self._calls = 0
         self.reducer = None
         if self.world > 1:
             self.reducer = BucketReducer(self.store.grads, self.store.ranges, num_buckets, process_group, self.comm_stream)
@@ -82,7 +86,42 @@ class Trainer:
 
     def step(self, image: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """image [N,3,H,W] fp32 cuda, target [N,H,W] int64 cuda -> loss (0-dim device tensor)."""
+        self._calls += 1
+        if self.use_graph and self._calls > 1:
+            return self._graph_step(image, target)
         loss = self.forward_backward(image, target)
         st = self.store
         call("sgd_step", st.params, st.grads, self.mom_buf, st.total, self.hp)
         return loss
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the whole step
+    def _graph_step(self, image: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """The ~1300 kernel launches of a step are captured once (all kernels take plain pointers and never sync or
+        allocate; torch's allocator serves the capture from a private pool) and replayed with new inputs copied into
+        static buffers.  With several ranks the graph holds forward+backward; the flat-bucket all-reduce and the fused
+        SGD run right after it on the same stream."""
+        key = (tuple(image.shape), tuple(target.shape), self.model.compute_dtype)
+        if self._graph is None or key != self._gkey:
+            self._gkey = key
+            self._s_img = torch.empty_like(image)
+            self._s_tgt = torch.empty_like(target)
+            self._s_img.copy_(image)
+            self._s_tgt.copy_(target)
+            reducer, self.reducer = self.reducer, None          # no side-stream traffic inside the capture
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    loss = self.forward_backward(self._s_img, self._s_tgt)
+                    if self.world == 1:
+                        call("sgd_step", self.store.params, self.store.grads, self.mom_buf, self.store.total, self.hp)
+            finally:
+                self.reducer = reducer
+            self._graph, self._s_loss = g, loss
+        else:
+            self._s_img.copy_(image, non_blocking=True)
+            self._s_tgt.copy_(target, non_blocking=True)
+        self._graph.replay()
+        if self.world > 1:
+            dist.all_reduce(self.store.grads, op=dist.ReduceOp.SUM, group=self.pg)
+            call("sgd_step", self.store.params, self.store.grads, self.mom_buf, self.store.total, self.hp)
+        return self._s_loss

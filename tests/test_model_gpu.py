@@ -212,3 +212,25 @@ def test_bf16_gradients_at_realistic_size(variant):
     # measured noise floor of bf16 mixed precision for this net: the REFERENCE under torch.autocast(bfloat16) on CPU has a
     # global gradient cosine of 0.949 (UNet) / 0.952 (EGM) vs its own fp32 run (worst tensor 0.81 / 0.56); see DESIGN.md
     assert gc > 0.93 and worst[0][0] > 0.2, (gc, worst[:4])
+
+
+def test_cuda_graph_step_equals_eager_step():
+    """Trainer(use_graph=True): the captured-and-replayed step produces the same parameters as eager launches."""
+    from egm_unet_b200.trainer import Trainer
+    outs = []
+    for use_graph in (False, True):
+        model = build("egm")
+        sd = synth.fill_state_dict(model.state_dict())
+        model.load_state_dict(sd)
+        model = model.cuda().train()
+        tr = Trainer(model, lr=0.02, momentum=0.9, weight_decay=1e-4, class_weight=[1.0, 2.0], ignore_index=255, use_graph=use_graph)
+        losses = []
+        for step in range(3):
+            image, target = synth.make_inputs(2, 64, 48, seed=50 + step)
+            losses.append(float(tr.step(image.cuda(), target.cuda())))
+        outs.append((losses, {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}))
+    (l0, s0), (l1, s1) = outs
+    assert all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(l0, l1)), (l0, l1)
+    # bf16 + fp32 atomics (wgrad split-K) are not bit-deterministic: allow round-off level differences
+    worst = max(rel_err(s1[k], s0[k]) for k in s0 if s0[k].numel() > 1)
+    assert worst < 6e-2, worst
