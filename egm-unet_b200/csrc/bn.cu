@@ -24,8 +24,10 @@ __device__ __forceinline__ void chan_reduce(F f, long long M, int C, double* __r
 #pragma unroll
     for (int j = 0; j < V; ++j) acc[k][j] = 0.f;
   f.prepare(cv * V);                                    // per-channel constants live in registers for the whole loop
-  if (r < rpi)
+  if (r < rpi) {
+#pragma unroll 4
     for (long long m = (long long)blockIdx.x * rpi + r; m < M; m += (long long)gridDim.x * rpi) f(m, cv * V, acc);
+  }
   // smem layout [rpi][K][C]
   if (r < rpi) {
 #pragma unroll
@@ -44,7 +46,7 @@ static inline int reduce_threads(int C, int V) { int CV = C / V; int rpi = 256 /
 static inline int reduce_blocks(long long M, int threads, int C, int V) {
   int rpi = threads / (C / V);
   long long b = (M + (long long)rpi * 8 - 1) / ((long long)rpi * 8);
-  long long cap = (long long)egm_num_sms() * 4;
+  long long cap = (long long)egm_num_sms() * 8;
   if (b > cap) b = cap; if (b < 1) b = 1; return (int)b;
 }
 
@@ -113,6 +115,7 @@ __global__ void k_bn_act_fwd(const T* __restrict__ z, long long zcs, long long z
   // blockDim.x = CV * rpb: every thread keeps ONE channel vector, so scale/shift are loaded once
   const int rpb = blockDim.x / CV, cv = threadIdx.x % CV, r = threadIdx.x / CV, c = cv * V;
   const FVec<V> sc = ldv<V>(a.scale + c), sh = ldv<V>(a.shift + c);
+#pragma unroll 2
   for (long long m = (long long)blockIdx.x * rpb + r; m < M; m += (long long)gridDim.x * rpb) {
     FVec<V> zv = ldv<V>(z + m * zcs + zco + c), xv, o;
     if (a.mode != 0) xv = ldv<V>(aux + m * (long long)(CV * V) + c);
@@ -218,6 +221,7 @@ __global__ void k_bn_bwd_apply(const T* __restrict__ dy, long long dcs, long lon
   const int rpb = blockDim.x / CV, cv = threadIdx.x % CV, r = threadIdx.x / CV, c = cv * V;
   const FVec<V> sc = ldv<V>(a.scale + c), sh = ldv<V>(a.shift + c), mu = ldv<V>(a.mean + c), rs = ldv<V>(a.rstd + c),
                 k0 = ldv<V>(a.coef + c), k1 = ldv<V>(a.coef + C + c), k2 = ldv<V>(a.coef + 2 * C + c);
+#pragma unroll 2
   for (long long m = (long long)blockIdx.x * rpb + r; m < M; m += (long long)gridDim.x * rpb) {
     FVec<V> d = ldv<V>(dy + m * dcs + dco + c), zv = ldv<V>(z + m * (long long)C + c), xv, o, oa;
     if (a.mode != 0) xv = ldv<V>(aux + m * (long long)C + c);

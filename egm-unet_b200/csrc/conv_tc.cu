@@ -148,30 +148,38 @@ static int make_map_w(CUtensorMap* tm, const void* ptr, int taps, int Cout, int 
 constexpr int TILE_H = 8, TILE_W = 16, TILE_PIX = 128;
 constexpr int TC_THREADS = 192;
 
-// =================================================================== forward / dgrad
+// =================================================================== forward / dgrad (per-tap tiles; any dilation / channel count)
 struct ConvTcParams {
   int N, H, W, Cin, Cout, kh, kw, dil, pad;
   int tilesH, tilesW, numTiles, kChunks, bkc;       // bkc = channels per K chunk (64/32/16)
   int stages, aBytes, bStride, tmemCols, accCols;
   int nChunk, coChunks;                               // Cout is processed in coChunks slices of nChunk (<= 256) channels
+  int wres;                                           // 1: the whole packed weight tensor stays resident in smem (single Cout slice)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                                                           __nv_bfloat16* __restrict__ y, const float* __restrict__ bias, ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int taps = p.kh * p.kw;
+  const int kIters = taps * p.kChunks;
   uint8_t* sA = smem;
-  uint8_t* sB = sA + (size_t)p.stages * p.aBytes;
-  uint64_t* full = (uint64_t*)(sB + (size_t)p.stages * p.bStride);
+  uint8_t* sB = sA + (size_t)p.stages * p.aBytes;                       // ring of weight tiles, or the resident [taps][kChunks] tiles
+  const int nB = p.wres ? kIters : p.stages;
+  uint64_t* full = (uint64_t*)(sB + (size_t)nB * p.bStride);
   uint64_t* empty = full + p.stages;
   uint64_t* tfull = empty + p.stages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  uint64_t* wfull = tempty + 2;
+  int2* tapOff = (int2*)(wfull + 1);                                    // [taps] (dw, dh) of each tap
+  uint32_t* tmem_slot = (uint32_t*)(tapOff + 64);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < taps) tapOff[threadIdx.x] = make_int2((threadIdx.x % p.kw) * p.dil - p.pad, (threadIdx.x / p.kw) * p.dil - p.pad);
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmemCols);
@@ -179,23 +187,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int taps = p.kh * p.kw;
-  const int kIters = taps * p.kChunks;
+  const int tilesPerImg = p.tilesH * p.tilesW;
 
   if (warp == 0) {
     if (lane == 0) {
+      const uint32_t bBytes = (uint32_t)(p.nChunk * p.bkc * 2);
+      if (p.wres) {
+        mbar_expect_tx(wfull, bBytes * (uint32_t)kIters);
+        for (int t = 0; t < taps; ++t)
+          for (int kc = 0; kc < p.kChunks; ++kc) tma_load_3d(sB + (size_t)(t * p.kChunks + kc) * p.bStride, &tmW, wfull, kc * p.bkc, 0, t);
+      }
+      const uint32_t txBytes = (uint32_t)p.aBytes + (p.wres ? 0u : bBytes);
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
         const int chunk = tile % p.coChunks, sp_t = tile / p.coChunks;
-        int n = sp_t / (p.tilesH * p.tilesW); int r = sp_t - n * p.tilesH * p.tilesW;
-        int h0 = (r / p.tilesW) * TILE_H, w0 = (r % p.tilesW) * TILE_W;
+        const int n = sp_t / tilesPerImg, r = sp_t - n * tilesPerImg;
+        const int h0 = (r / p.tilesW) * TILE_H, w0 = (r % p.tilesW) * TILE_W, co0 = chunk * p.nChunk;
         for (int t = 0; t < taps; ++t) {
-          int dh = (t / p.kw) * p.dil - p.pad, dw = (t % p.kw) * p.dil - p.pad;
+          const int2 o = tapOff[t];
           for (int kc = 0; kc < p.kChunks; ++kc) {
             mbar_wait(&empty[s], ph ^ 1);
-            mbar_expect_tx(&full[s], (uint32_t)(p.aBytes + p.nChunk * p.bkc * 2));
-            tma_load_4d(sA + (size_t)s * p.aBytes, &tmX, &full[s], kc * p.bkc, w0 + dw, h0 + dh, n);
-            tma_load_3d(sB + (size_t)s * p.bStride, &tmW, &full[s], kc * p.bkc, chunk * p.nChunk, t);
+            mbar_expect_tx(&full[s], txBytes);
+            tma_load_4d(sA + (size_t)s * p.aBytes, &tmX, &full[s], kc * p.bkc, w0 + o.x, h0 + o.y, n);
+            if (!p.wres) tma_load_3d(sB + (size_t)s * p.bStride, &tmW, &full[s], kc * p.bkc, co0, t);
             if (++s == p.stages) { s = 0; ph ^= 1; }
           }
         }
@@ -207,17 +221,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       const int rowB = p.bkc * 2;                       // bytes per smem row == swizzle span
       const uint32_t layout = rowB == 128 ? 2u : (rowB == 64 ? 4u : 6u);
       const uint32_t sbo = 8u * rowB;                   // 8-row core-matrix group stride
+      const int ksteps = p.bkc / 16;
+      const uint64_t adBase = umma_desc(smem_u32(sA), 16, sbo, layout), bdBase = umma_desc(smem_u32(sB), 16, sbo, layout);
+      const uint32_t aStep = (uint32_t)p.aBytes >> 4, bStep = (uint32_t)p.bStride >> 4;
+      if (p.wres) mbar_wait(wfull, 0);
       int s = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
       for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
         mbar_wait(&tempty[acc], aph ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(acc * p.accCols);
+        uint32_t accf = 0;
         for (int it = 0; it < kIters; ++it) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t a0 = smem_u32(sA + (size_t)s * p.aBytes), b0 = smem_u32(sB + (size_t)s * p.bStride);
-          for (int k = 0; k < p.bkc / 16; ++k)
-            umma_bf16(d, umma_desc(a0 + k * 32, 16, sbo, layout), umma_desc(b0 + k * 32, 16, sbo, layout), idesc, (it | k) ? 1u : 0u);
+          const uint64_t ad = adBase + (uint64_t)(s * aStep), bd = bdBase + (uint64_t)((p.wres ? it : s) * bStep);
+          if (ksteps == 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, accf); accf = 1; }
+          } else if (ksteps == 2) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) { umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, accf); accf = 1; }
+          } else { umma_bf16(d, ad, bd, idesc, accf); accf = 1; }
           umma_commit(&empty[s]);
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
@@ -231,28 +255,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     int acc = 0; uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
       const int chunk = tile % p.coChunks, sp_t = tile / p.coChunks;
-      int n = sp_t / (p.tilesH * p.tilesW); int r = sp_t - n * p.tilesH * p.tilesW;
-      int h = (r / p.tilesW) * TILE_H + row / TILE_W, w = (r % p.tilesW) * TILE_W + row % TILE_W;
+      const int n = sp_t / tilesPerImg, r = sp_t - n * tilesPerImg;
+      const int h = (r / p.tilesW) * TILE_H + row / TILE_W, w = (r % p.tilesW) * TILE_W + row % TILE_W;
       const bool valid = h < p.H && w < p.W;
       __nv_bfloat16* yp = y + (((long long)n * p.H + h) * p.W + w) * p.Cout + chunk * p.nChunk;
       const float* bp = bias ? bias + chunk * p.nChunk : nullptr;
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.accCols);
-      for (int c = 0; c < p.nChunk; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(t0 + c, v);
-        tmem_ld_wait();
-        if (valid) {
-          uint4 o[2]; __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
-            if (bp) { f0 += bp[c + 2 * j]; f1 += bp[c + 2 * j + 1]; }
-            ob[j] = __floats2bfloat162_rn(f0, f1);
-          }
-          *reinterpret_cast<uint4*>(yp + c) = o[0];
-          *reinterpret_cast<uint4*>(yp + c + 8) = o[1];
+      if ((p.nChunk & 31) == 0) {
+        for (int c = 0; c < p.nChunk; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(t0 + c, v);
+          tmem_ld_wait();
+          if (valid) { store16(yp + c, v, bp ? bp + c : nullptr); store16(yp + c + 16, v + 16, bp ? bp + c + 16 : nullptr); }
+        }
+      } else {
+        for (int c = 0; c < p.nChunk; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(t0 + c, v);
+          tmem_ld_wait();
+          if (valid) store16(yp + c, v, bp ? bp + c : nullptr);
         }
       }
       tc_fence_before();
@@ -267,7 +290,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 
 #include <stdlib.h>
 static int pow2_cols(int c) { int v = 32; while (v < c) v <<= 1; return v; }
-static int pick_bkc(int C) { return C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16); }       // channels per K chunk (row = 128/64/32 bytes)
+// channels per chunk (smem row = 128/64/32 bytes).  A tail chunk that runs past C is zero-filled by TMA (out-of-bounds box).
+static int pick_bkc(int C) { return C > 32 ? 64 : (C > 16 ? 32 : 16); }
 
 
 // =================================================================== forward / dgrad, halo-reuse variant (small-channel layers)
@@ -459,16 +483,18 @@ extern "C" int egm_conv2d_tc(const void* x, const void* w_packed_bf16, const flo
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
   p.coChunks = (Cout + 255) / 256; p.nChunk = Cout / p.coChunks;
   p.tilesH = cdiv(H, TILE_H); p.tilesW = cdiv(W, TILE_W); p.numTiles = N * p.tilesH * p.tilesW * p.coChunks;
-  p.bkc = pick_bkc(Cin); p.kChunks = Cin / p.bkc;
+  p.bkc = pick_bkc(Cin); p.kChunks = cdiv(Cin, p.bkc);
   p.aBytes = TILE_PIX * p.bkc * 2;                               // 16 KB / 8 KB / 4 KB: multiples of 1024
   p.bStride = (p.nChunk * p.bkc * 2 + 1023) / 1024 * 1024;
-  int per = p.aBytes + p.bStride;
-  p.stages = (200 * 1024) / per; if (p.stages > 8) p.stages = 8; if (p.stages < 2) p.stages = 2;
+  const long long wresBytes = (long long)kh * kw * p.kChunks * p.bStride;
+  p.wres = (p.coChunks == 1 && wresBytes <= 72 * 1024) ? 1 : 0;
+  int per = p.aBytes + (p.wres ? 0 : p.bStride);
+  p.stages = (int)((198 * 1024 - (p.wres ? wresBytes : 0)) / per); if (p.stages > 8) p.stages = 8; if (p.stages < 2) p.stages = 2;
   p.accCols = (p.nChunk + 31) / 32 * 32; p.tmemCols = pow2_cols(2 * p.accCols);
   CUtensorMap tmX, tmW;
   int e = make_map_nhwc(&tmX, x, N, H, W, Cin, p.bkc, TILE_W, TILE_H); if (e) return e;
   e = make_map_w(&tmW, w_packed_bf16, kh * kw, Cout, Cin, p.bkc, p.nChunk); if (e) return e;
-  size_t smem = (size_t)p.stages * per + 1024 + 256;
+  size_t smem = (size_t)p.stages * per + (p.wres ? (size_t)wresBytes : 0) + 1024 + 1024;
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
   int grid = p.numTiles < egm_num_sms() ? p.numTiles : egm_num_sms();
@@ -582,7 +608,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
     mbar_wait(tfull, 0);
     tc_fence_after();
     const int co = coc * p.mch + co_local;
-    const bool valid = co_local < p.mch && co < p.Cout && co_local < p.ummaM;
+    const bool valid = co_local < p.mch && co < p.Cout;
     if (q * 32 < p.ummaM) {
       for (int j = 0; j < nt; ++j) {
         const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.nch);
@@ -594,7 +620,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               int ci = cic * p.nch + c + i;
-              atomicAdd(dwp + ((long long)(t0 + j) * p.Cin + ci) * p.Cout + co, __uint_as_float(v[i]));
+              if (ci < p.Cin) atomicAdd(dwp + ((long long)(t0 + j) * p.Cin + ci) * p.Cout + co, __uint_as_float(v[i]));
             }
           }
         }
@@ -698,7 +724,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_co
     mbar_wait(tfull, 0);
     tc_fence_after();
     const int co = coc * p.mch + co_local;
-    const bool valid = co_local < p.mch;
+    const bool valid = co_local < p.mch && co < p.Cout;
     if (q * 32 < p.mch) {
       for (int r = 0; r < R; ++r)
         for (int sidx = 0; sidx < p.kw; ++sidx) {
@@ -711,7 +737,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_co
             if (valid) {
 #pragma unroll
               for (int i = 0; i < 16; ++i)
-                atomicAdd(dwp + ((long long)tap * p.Cin + cic * p.nch + c + i) * p.Cout + co, __uint_as_float(v[i]));
+                if (cic * p.nch + c + i < p.Cin) atomicAdd(dwp + ((long long)tap * p.Cin + cic * p.nch + c + i) * p.Cout + co, __uint_as_float(v[i]));
             }
           }
         }
@@ -733,7 +759,7 @@ static int launch_wgrad_halo(const void* x, const void* dy, float* dwp, int N, i
   WgradHaloParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
   p.tilesH = cdiv(H, HT_H); p.tilesW = cdiv(W, HT_W); p.numTiles = N * p.tilesH * p.tilesW;
-  p.mch = Cout % 128 == 0 ? 128 : pick_bkc(Cout);
+  p.mch = Cout > 64 ? 128 : pick_bkc(Cout);
   p.aAtomCh = p.mch >= 64 ? 64 : p.mch; p.mAtoms = p.mch / p.aAtomCh;
   p.rowA = p.aAtomCh * 2; p.aAtomBytes = TILE_PIX * p.rowA;
   p.aBytes = (128 / p.aAtomCh) * p.aAtomBytes;                         // the M=128 MMA addresses 128/aAtomCh atoms (only mAtoms are loaded)
@@ -746,7 +772,7 @@ static int launch_wgrad_halo(const void* x, const void* dy, float* dwp, int N, i
   p.rowsPerGroup = 512 / perRow; if (p.rowsPerGroup > kh) p.rowsPerGroup = kh;
   p.rowGroups = cdiv(kh, p.rowsPerGroup);
   p.tmemCols = pow2_cols(p.rowsPerGroup * perRow);
-  p.coChunks = Cout / p.mch; p.ciChunks = Cin / p.nch;
+  p.coChunks = cdiv(Cout, p.mch); p.ciChunks = cdiv(Cin, p.nch);
   long long units = (long long)p.rowGroups * p.coChunks * p.ciChunks;
   long long want = ((long long)egm_num_sms() * 2 + units - 1) / units;
   if (want > p.numTiles) want = p.numTiles; if (want < 1) want = 1;
@@ -774,7 +800,7 @@ extern "C" int egm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_pack
   WgradParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
   p.tilesH = cdiv(H, TILE_H); p.tilesW = cdiv(W, TILE_W); p.numTiles = N * p.tilesH * p.tilesW;
-  p.mch = Cout % 128 == 0 ? 128 : pick_bkc(Cout);   // 128 / 64 / 32 / 16 output channels per work unit
+  p.mch = Cout > 64 ? 128 : pick_bkc(Cout);         // 128 / 64 / 32 / 16 output channels per work unit (tail zero-filled)
   p.ummaM = 128;                                     // always M=128 (lane i == row i); rows >= mch read unused smem and are ignored
   p.mAtoms = p.mch >= 64 ? p.mch / 64 : 1;
   int aAtomCh = p.mch >= 64 ? 64 : p.mch;
@@ -786,7 +812,7 @@ extern "C" int egm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_pack
   p.stageBytes = p.aBytes + WG_TAPS * p.bTileBytes;
   p.stages = (200 * 1024) / p.stageBytes; if (p.stages > 6) p.stages = 6; if (p.stages < 2) p.stages = 2;
   p.tmemCols = pow2_cols(WG_TAPS * p.nch);
-  p.tapGroups = cdiv(kh * kw, WG_TAPS); p.coChunks = Cout / p.mch; p.ciChunks = Cin / p.nch;
+  p.tapGroups = cdiv(kh * kw, WG_TAPS); p.coChunks = cdiv(Cout, p.mch); p.ciChunks = cdiv(Cin, p.nch);
   long long units = (long long)p.tapGroups * p.coChunks * p.ciChunks;
   long long want = ((long long)egm_num_sms() * 2 + units - 1) / units;
   if (want > p.numTiles) want = p.numTiles; if (want < 1) want = 1;
