@@ -3,6 +3,7 @@
 // (:958-975, momentum 0.01) and EdgeAwareFeatureEnhancer (:872-886); see SURVEY.md App. A.
 // All kernels are HBM-bound: one pass per tensor, 16-byte vector accesses, per-channel fp64 atomics.
 #include "common.cuh"
+#include <stdlib.h>
 
 // act: 0 none, 1 relu, 2 sigmoid.   mode: 0 plain, 1 edge gate (y = s*aux + aux), 2 residual (y = relu(alpha*aux + bn))
 struct BnArgs {
@@ -66,11 +67,14 @@ __global__ void k_bn_stats(StatsF<T, V> f, long long M, int C, double* out) {
   extern __shared__ float smem[];
   chan_reduce<V, 2>(f, M, C, out, smem);
 }
+static bool bn_stats_stream_launch(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, cudaStream_t st);
+static bool bn_fwd_stream_launch(const void* z, long long zcs, long long zco, const BnArgs& a, void* y, long long ycs, long long yco, int dtype, long long M, int C, cudaStream_t st);
 extern "C" int egm_bn_stats(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, void* stream) {
   EGM_REQUIRE(C >= 1 && C <= 2048, EGM_E_SHAPE, "bn_stats: C=%d unsupported", C);
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
   if (M == 0) return EGM_OK;
+  if (bn_stats_stream_launch(x, dtype, M, C, cstride, coff, sums, st)) { EGM_LAUNCH_CHECK("bn_stats(stream)"); return EGM_OK; }
   int v = egm_pick_vec(C, cstride, coff);
   int threads = reduce_threads(C, v); size_t sm = (size_t)(threads / (C / v)) * 2 * C * sizeof(float);
   EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_stats<T, V><<<reduce_blocks(M, threads, C, v), threads, sm, st>>>(
@@ -141,6 +145,7 @@ extern "C" int egm_bn_act_fwd(const void* z, long long z_cstride, long long z_co
   EGM_REQUIRE(mode == 0 || aux, EGM_E_BADARG, "bn_act_fwd: mode %d needs aux", mode);
   int v = egm_pick_vec(C, z_cstride, z_coff), v2 = egm_pick_vec(C, y_cstride, y_coff); if (v2 < v) v = v2;
   BnArgs a{scale, shift, nullptr, nullptr, nullptr, act, mode, alpha};
+  if (bn_fwd_stream_launch(z, z_cstride, z_coff, a, y, y_cstride, y_coff, dtype, M, C, (cudaStream_t)stream)) { EGM_LAUNCH_CHECK("bn_act_fwd(stream)"); return EGM_OK; }
   const int threads = reduce_threads(C, v);
   EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_act_fwd<T, V><<<ew_blocks(M, threads, C, V), threads, 0, (cudaStream_t)stream>>>(
       (const T*)z, z_cstride, z_coff, a, (const T*)aux, (T*)y, y_cstride, y_coff, M, C / V))));
@@ -162,6 +167,8 @@ __device__ __forceinline__ void bn_local_grad(const BnArgs& a, float dy, float z
     float m = fmaf(a.alpha, aux, t) > 0.f ? dy : 0.f; g = m; daux = a.alpha * m;
   }
 }
+#include "bn_stream.cuh"
+
 template <typename T, int V>
 struct BwdRedF {
   const T* dy; long long dcs, dco; const T* z; const T* aux; BnArgs a; int C;
@@ -188,9 +195,18 @@ extern "C" int egm_bn_act_bwd_reduce(const void* dy, long long dy_cstride, long 
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
   if (M == 0) return EGM_OK;
-  int v = egm_pick_vec(C, dy_cstride, dy_coff); if (v > 4) v = 4;      // 4-wide: fewer live registers -> more warps in flight (streaming kernel)
-  int threads = reduce_threads(C, v); size_t sm = (size_t)(threads / (C / v)) * 2 * C * sizeof(float);
   BnArgs a{scale, shift, mean, rstd, nullptr, act, mode, alpha};
+  if (bn_stream_eligible(mode, M, C, dy_cstride, dy_coff)) {
+    const size_t smb = bs::ring_bytes<2>(2 * bs::CONSUMERS * bs::V * sizeof(float));
+    EGM_DISPATCH_DTYPE(dtype, {
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(k_bn_bwd_reduce_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+      k_bn_bwd_reduce_stream<T><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st>>>((const T*)dy, (const T*)z, a, M * C, C, sums);
+    });
+    EGM_LAUNCH_CHECK("bn_act_bwd_reduce(stream)"); return EGM_OK;
+  }
+  int v = egm_pick_vec(C, dy_cstride, dy_coff); if (v > 4) v = 4;      // 4-wide: fewer live registers -> more warps in flight
+  int threads = reduce_threads(C, v); size_t sm = (size_t)(threads / (C / v)) * 2 * C * sizeof(float);
   EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_bwd_reduce<T, V><<<reduce_blocks(M, threads, C, v), threads, sm, st>>>(
       BwdRedF<T, V>{(const T*)dy, dy_cstride, dy_coff, (const T*)z, (const T*)aux, a, C, {}, {}, {}, {}}, M, C, sums))));
   EGM_LAUNCH_CHECK("bn_act_bwd_reduce"); return EGM_OK;
@@ -241,8 +257,17 @@ extern "C" int egm_bn_act_bwd_apply(const void* dy, long long dy_cstride, long l
                                     const float* mean, const float* rstd, const float* coef, int act, int mode, const void* aux, float alpha,
                                     void* dz, void* daux, int daux_accumulate, int dtype, long long M, int C, void* stream) {
   if (M * C == 0) return EGM_OK;
-  int v = egm_pick_vec(C, dy_cstride, dy_coff); if (v > 4) v = 4;
   BnArgs a{scale, shift, mean, rstd, coef, act, mode, alpha};
+  if (bn_stream_eligible(mode, M, C, dy_cstride, dy_coff)) {
+    const size_t smb = bs::ring_bytes<2>(0);
+    EGM_DISPATCH_DTYPE(dtype, {
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(k_bn_bwd_apply_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+      k_bn_bwd_apply_stream<T><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, (cudaStream_t)stream>>>((const T*)dy, (const T*)z, a, (T*)dz, M * C, C);
+    });
+    EGM_LAUNCH_CHECK("bn_act_bwd_apply(stream)"); return EGM_OK;
+  }
+  int v = egm_pick_vec(C, dy_cstride, dy_coff); if (v > 4) v = 4;
   const int threads = reduce_threads(C, v);
   EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_bwd_apply<T, V><<<ew_blocks(M, threads, C, V), threads, 0, (cudaStream_t)stream>>>(
       (const T*)dy, dy_cstride, dy_coff, (const T*)z, (const T*)aux, a, (T*)dz, (T*)daux, daux_accumulate, M, C / V))));
@@ -277,4 +302,31 @@ extern "C" int egm_channel_sum(const void* x, int dtype, long long M, int C, lon
   }
   k_d2f<<<cdiv(C, 128), 128, 0, st>>>(scratch, out, C);
   EGM_LAUNCH_CHECK("channel_sum"); return EGM_OK;
+}
+
+// ---------------------------------------------------------------- streaming launches declared above
+static bool bn_stats_stream_launch(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, cudaStream_t st) {
+  if (!bn_stream_eligible(0, M, C, cstride, coff) || (dtype != EGM_F32 && dtype != EGM_BF16)) return false;
+  const size_t smb = bs::ring_bytes<1>(2 * bs::CONSUMERS * bs::V * sizeof(float));
+  if (dtype == EGM_F32) {
+    static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_bn_stats_stream<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+    k_bn_stats_stream<float><<<bn_stream_grid(M * C, 4), bs::THREADS, smb, st>>>((const float*)x, M * C, C, sums);
+  } else {
+    static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_bn_stats_stream<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+    k_bn_stats_stream<__nv_bfloat16><<<bn_stream_grid(M * C, 2), bs::THREADS, smb, st>>>((const __nv_bfloat16*)x, M * C, C, sums);
+  }
+  return true;
+}
+static bool bn_fwd_stream_launch(const void* z, long long zcs, long long zco, const BnArgs& a, void* y, long long ycs, long long yco, int dtype, long long M, int C,
+                                 cudaStream_t st) {
+  if (!bn_stream_eligible(a.mode, M, C, zcs, zco) || ycs != C || yco != 0 || (dtype != EGM_F32 && dtype != EGM_BF16)) return false;
+  const size_t smb = bs::ring_bytes<1>(0);
+  if (dtype == EGM_F32) {
+    static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_bn_act_fwd_stream<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+    k_bn_act_fwd_stream<float><<<bn_stream_grid(M * C, 4), bs::THREADS, smb, st>>>((const float*)z, a, (float*)y, M * C, C);
+  } else {
+    static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_bn_act_fwd_stream<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+    k_bn_act_fwd_stream<__nv_bfloat16><<<bn_stream_grid(M * C, 2), bs::THREADS, smb, st>>>((const __nv_bfloat16*)z, a, (__nv_bfloat16*)y, M * C, C);
+  }
+  return true;
 }

@@ -1,0 +1,241 @@
+// Streaming variants of the BatchNorm backward kernels for dense, power-of-two-channel tensors (the DoubleConv / BasicConv
+// majority).  A register-staged grid-stride loop cannot keep enough bytes in flight to cover HBM latency (ncu: 64 regs ->
+// 48 % occupancy, 35 % DRAM throughput, stalls = long_scoreboard).  Here a producer warp streams 16 KB chunks of every input
+// tensor into a 4-stage shared-memory ring with cp.async.bulk (1-D TMA) + mbarriers -- 128 KB in flight per SM -- and 256
+// consumer threads read them back with 16-byte LDS.  Included by bn.cu (shares BnArgs / bn_local_grad).
+#pragma once
+
+namespace bs {
+constexpr int STAGES = 4, CHUNK_BYTES = 16384, CONSUMERS = 256, THREADS = CONSUMERS + 32, V = 8;
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* b, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n)); }
+__device__ __forceinline__ void bar_expect(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory"); }
+__device__ __forceinline__ void bar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tBS_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra BS_DONE;\n\tbra BS_WAIT;\n\tBS_DONE:\n\t}" ::"r"(s32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)), "l"(src), "r"(bytes),
+               "r"(s32(bar))
+               : "memory");
+}
+
+struct Ring {
+  uint8_t* buf; uint64_t* full; uint64_t* empty;
+};
+// carve the dynamic smem: [STAGES][NT][CHUNK_BYTES] | full[STAGES] | empty[STAGES] | tail (reduction scratch)
+template <int NT>
+__device__ __forceinline__ Ring make_ring(uint8_t* smem, float** tail) {
+  Ring r;
+  r.buf = (uint8_t*)(((uintptr_t)smem + 127) & ~(uintptr_t)127);
+  r.full = (uint64_t*)(r.buf + (size_t)STAGES * NT * CHUNK_BYTES);
+  r.empty = r.full + STAGES;
+  *tail = (float*)(r.empty + STAGES);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { bar_init(&r.full[i], 1); bar_init(&r.empty[i], CONSUMERS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  return r;
+}
+template <int NT>
+constexpr size_t ring_bytes(size_t tail_bytes) { return (size_t)STAGES * NT * CHUNK_BYTES + 2 * STAGES * 8 + tail_bytes + 256; }
+
+// producer: one lane streams this CTA's chunks of NT tensors
+template <typename T, int NT>
+__device__ __forceinline__ void produce(const Ring& r, const T* const* src, long long total, long long nChunks) {
+  constexpr long long EPC = CHUNK_BYTES / sizeof(T);
+  int s = 0; uint32_t ph = 0;
+  for (long long c = blockIdx.x; c < nChunks; c += gridDim.x) {
+    long long e0 = c * EPC, n = total - e0 < EPC ? total - e0 : EPC;
+    uint32_t bytes = (uint32_t)(n * sizeof(T));
+    bar_wait(&r.empty[s], ph ^ 1);
+    bar_expect(&r.full[s], bytes * NT);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) bulk_g2s(r.buf + ((size_t)s * NT + t) * CHUNK_BYTES, src[t] + e0, bytes, &r.full[s]);
+    if (++s == STAGES) { s = 0; ph ^= 1; }
+  }
+}
+}  // namespace bs
+
+// ------------------------------------------------------------------ sum(g), sum(g*xhat) per channel   (mode 0 only)
+template <typename T>
+__global__ void __launch_bounds__(bs::THREADS, 1) k_bn_bwd_reduce_stream(const T* __restrict__ dy, const T* __restrict__ z, BnArgs a, long long total, int C,
+                                                                        double* __restrict__ out) {
+  using namespace bs;
+  extern __shared__ uint8_t smem_raw[];
+  float* red;
+  Ring r = make_ring<2>(smem_raw, &red);
+  constexpr long long EPC = CHUNK_BYTES / sizeof(T);
+  const long long nChunks = (total + EPC - 1) / EPC;
+  if (threadIdx.x >= CONSUMERS) {
+    if (threadIdx.x == CONSUMERS) { const T* src[2] = {dy, z}; produce<T, 2>(r, src, total, nChunks); }
+    return;
+  }
+  const int t = threadIdx.x, c = (t * V) % C;                 // fixed channel vector: (CONSUMERS*V) % C == 0 and EPC % C == 0
+  const FVec<V> sc = ldv<V>(a.scale + c), sh = ldv<V>(a.shift + c), mu = ldv<V>(a.mean + c), rs = ldv<V>(a.rstd + c);
+  float acc0[V], acc1[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+  int s = 0; uint32_t ph = 0;
+  for (long long ch = blockIdx.x; ch < nChunks; ch += gridDim.x) {
+    const long long e0 = ch * EPC; const int n = (int)(total - e0 < EPC ? total - e0 : EPC);
+    const T* sd = (const T*)(r.buf + ((size_t)s * 2 + 0) * CHUNK_BYTES);
+    const T* sz = (const T*)(r.buf + ((size_t)s * 2 + 1) * CHUNK_BYTES);
+    bar_wait(&r.full[s], ph);
+#pragma unroll 4
+    for (int e = t * V; e < n; e += CONSUMERS * V) {
+      FVec<V> d = ldv<V>(sd + e), zv = ldv<V>(sz + e);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float g, da; bn_local_grad(a, d.v[j], zv.v[j], sc.v[j], sh.v[j], 0.f, g, da);
+        acc0[j] += g; acc1[j] += g * (zv.v[j] - mu.v[j]) * rs.v[j];
+      }
+    }
+    bar_arrive(&r.empty[s]);
+    if (++s == STAGES) { s = 0; ph ^= 1; }
+  }
+  // cross-thread reduction: threads with the same channel vector are CV apart
+#pragma unroll
+  for (int j = 0; j < V; ++j) { red[t * V + j] = acc0[j]; red[CONSUMERS * V + t * V + j] = acc1[j]; }
+  asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS));
+  const int CV = C / V;
+  for (int i = t; i < 2 * C; i += CONSUMERS) {
+    const int k = i / C, cc = i - k * C; float sum = 0.f;
+    for (int tt = cc / V; tt < CONSUMERS; tt += CV) sum += red[k * CONSUMERS * V + tt * V + (cc % V)];
+    atomicAdd(out + i, (double)sum);
+  }
+}
+
+// ------------------------------------------------------------------ dz = k0 * (g - k1 - xhat*k2)   (mode 0 only)
+template <typename T>
+__global__ void __launch_bounds__(bs::THREADS, 1) k_bn_bwd_apply_stream(const T* __restrict__ dy, const T* __restrict__ z, BnArgs a, T* __restrict__ dz,
+                                                                       long long total, int C) {
+  using namespace bs;
+  extern __shared__ uint8_t smem_raw[];
+  float* tail;
+  Ring r = make_ring<2>(smem_raw, &tail);
+  constexpr long long EPC = CHUNK_BYTES / sizeof(T);
+  const long long nChunks = (total + EPC - 1) / EPC;
+  if (threadIdx.x >= CONSUMERS) {
+    if (threadIdx.x == CONSUMERS) { const T* src[2] = {dy, z}; produce<T, 2>(r, src, total, nChunks); }
+    return;
+  }
+  const int t = threadIdx.x, c = (t * V) % C;
+  const FVec<V> sc = ldv<V>(a.scale + c), sh = ldv<V>(a.shift + c), mu = ldv<V>(a.mean + c), rs = ldv<V>(a.rstd + c), k0 = ldv<V>(a.coef + c),
+                k1 = ldv<V>(a.coef + C + c), k2 = ldv<V>(a.coef + 2 * C + c);
+  int s = 0; uint32_t ph = 0;
+  for (long long ch = blockIdx.x; ch < nChunks; ch += gridDim.x) {
+    const long long e0 = ch * EPC; const int n = (int)(total - e0 < EPC ? total - e0 : EPC);
+    const T* sd = (const T*)(r.buf + ((size_t)s * 2 + 0) * CHUNK_BYTES);
+    const T* sz = (const T*)(r.buf + ((size_t)s * 2 + 1) * CHUNK_BYTES);
+    bar_wait(&r.full[s], ph);
+#pragma unroll 4
+    for (int e = t * V; e < n; e += CONSUMERS * V) {
+      FVec<V> d = ldv<V>(sd + e), zv = ldv<V>(sz + e), o;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float g, da; bn_local_grad(a, d.v[j], zv.v[j], sc.v[j], sh.v[j], 0.f, g, da);
+        o.v[j] = k0.v[j] * (g - k1.v[j] - (zv.v[j] - mu.v[j]) * rs.v[j] * k2.v[j]);
+      }
+      stv<V>(dz + e0 + e, o);
+    }
+    bar_arrive(&r.empty[s]);
+    if (++s == STAGES) { s = 0; ph ^= 1; }
+  }
+}
+
+// ------------------------------------------------------------------ forward statistics sum(x), sum(x^2) per channel
+template <typename T>
+__global__ void __launch_bounds__(bs::THREADS, 1) k_bn_stats_stream(const T* __restrict__ x, long long total, int C, double* __restrict__ out) {
+  using namespace bs;
+  extern __shared__ uint8_t smem_raw[];
+  float* red;
+  Ring r = make_ring<1>(smem_raw, &red);
+  constexpr long long EPC = CHUNK_BYTES / sizeof(T);
+  const long long nChunks = (total + EPC - 1) / EPC;
+  if (threadIdx.x >= CONSUMERS) {
+    if (threadIdx.x == CONSUMERS) { const T* src[1] = {x}; produce<T, 1>(r, src, total, nChunks); }
+    return;
+  }
+  const int t = threadIdx.x;
+  float acc0[V], acc1[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+  int s = 0; uint32_t ph = 0;
+  for (long long ch = blockIdx.x; ch < nChunks; ch += gridDim.x) {
+    const long long e0 = ch * EPC; const int n = (int)(total - e0 < EPC ? total - e0 : EPC);
+    const T* sx = (const T*)(r.buf + (size_t)s * CHUNK_BYTES);
+    bar_wait(&r.full[s], ph);
+#pragma unroll 4
+    for (int e = t * V; e < n; e += CONSUMERS * V) {
+      FVec<V> v = ldv<V>(sx + e);
+#pragma unroll
+      for (int j = 0; j < V; ++j) { acc0[j] += v.v[j]; acc1[j] += v.v[j] * v.v[j]; }
+    }
+    bar_arrive(&r.empty[s]);
+    if (++s == STAGES) { s = 0; ph ^= 1; }
+  }
+#pragma unroll
+  for (int j = 0; j < V; ++j) { red[t * V + j] = acc0[j]; red[CONSUMERS * V + t * V + j] = acc1[j]; }
+  asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS));
+  const int CV = C / V;
+  for (int i = t; i < 2 * C; i += CONSUMERS) {
+    const int k = i / C, cc = i - k * C; float sum = 0.f;
+    for (int tt = cc / V; tt < CONSUMERS; tt += CV) sum += red[k * CONSUMERS * V + tt * V + (cc % V)];
+    atomicAdd(out + i, (double)sum);
+  }
+}
+
+// ------------------------------------------------------------------ y = act(z*scale + shift)   (mode 0, dense in and out)
+template <typename T>
+__global__ void __launch_bounds__(bs::THREADS, 1) k_bn_act_fwd_stream(const T* __restrict__ z, BnArgs a, T* __restrict__ y, long long total, int C) {
+  using namespace bs;
+  extern __shared__ uint8_t smem_raw[];
+  float* tail;
+  Ring r = make_ring<1>(smem_raw, &tail);
+  constexpr long long EPC = CHUNK_BYTES / sizeof(T);
+  const long long nChunks = (total + EPC - 1) / EPC;
+  if (threadIdx.x >= CONSUMERS) {
+    if (threadIdx.x == CONSUMERS) { const T* src[1] = {z}; produce<T, 1>(r, src, total, nChunks); }
+    return;
+  }
+  const int t = threadIdx.x, c = (t * V) % C;
+  const FVec<V> sc = ldv<V>(a.scale + c), sh = ldv<V>(a.shift + c);
+  int s = 0; uint32_t ph = 0;
+  for (long long ch = blockIdx.x; ch < nChunks; ch += gridDim.x) {
+    const long long e0 = ch * EPC; const int n = (int)(total - e0 < EPC ? total - e0 : EPC);
+    const T* sz = (const T*)(r.buf + (size_t)s * CHUNK_BYTES);
+    bar_wait(&r.full[s], ph);
+#pragma unroll 4
+    for (int e = t * V; e < n; e += CONSUMERS * V) {
+      FVec<V> zv = ldv<V>(sz + e), o;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float q = fmaf(zv.v[j], sc.v[j], sh.v[j]);
+        o.v[j] = a.act == 1 ? fmaxf(q, 0.f) : (a.act == 2 ? sigmoidf_(q) : q);
+      }
+      stv<V>(y + e0 + e, o);
+    }
+    bar_arrive(&r.empty[s]);
+    if (++s == STAGES) { s = 0; ph ^= 1; }
+  }
+}
+
+static inline bool bn_stream_eligible(int mode, long long M, int C, long long cstride, long long coff) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("EGM_NO_BN_STREAM"); off = (e && e[0] == '1') ? 1 : 0; }
+  if (off) return false;
+  return mode == 0 && cstride == C && coff == 0 && C >= 8 && C <= 2048 && (C & (C - 1)) == 0 && M * (long long)C >= 4 * 8192;
+}
+static inline int bn_stream_grid(long long total, size_t elem) {
+  long long nChunks = (total * (long long)elem + bs::CHUNK_BYTES - 1) / bs::CHUNK_BYTES;
+  long long g = egm_num_sms();
+  return (int)(nChunks < g ? nChunks : g);
+}
