@@ -156,3 +156,73 @@ extern "C" int egm_upsample_concat_bwd_low(const void* dcat, void* dlow, int dty
   EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_upcat_bwd_low<T, V><<<egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dcat, (T*)dlow, g))));
   EGM_LAUNCH_CHECK("upsample_concat_bwd_low"); return EGM_OK;
 }
+
+// ------------------------------------------------------------------ ConvTranspose2d(k=2, s=2) as a per-pixel GEMM + pixel shuffle
+// (UNet(bilinear=False): src/unet.py:35-37).  The GEMM is a 1x1 conv with the re-laid-out weight
+//   wT[(a*2+b)*Cout + co][ci] = W[ci][co][a][b]        (mode 0: W -> wT,  mode 1: wT -> W, used for the gradient)
+// and the kernels below scatter / gather its [N,Hl,Wl,4*Cout] output into the up-sampled half of the concat tensor.
+__global__ void k_deconv_wpack(float* __restrict__ w, float* __restrict__ wt, int Cin, int Cout, int mode) {
+  long long total = (long long)Cin * Cout * 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int ab = (int)(i & 3); long long q = i >> 2; int co = (int)(q % Cout); int ci = (int)(q / Cout);
+    long long j = ((long long)ab * Cout + co) * Cin + ci;
+    if (mode == 0) wt[j] = w[i]; else w[i] = wt[j];
+  }
+}
+extern "C" int egm_deconv_weight_pack(float* w, float* wt, int Cin, int Cout, int mode, void* stream) {
+  long long total = (long long)Cin * Cout * 4;
+  if (total == 0) return EGM_OK;
+  k_deconv_wpack<<<egm_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, wt, Cin, Cout, mode);
+  EGM_LAUNCH_CHECK("deconv_weight_pack"); return EGM_OK;
+}
+// out[N,H,W,Cs+Cu] = cat([skip, pad(pixel_shuffle(z[N,Hl,Wl,4*Cu]))])
+template <typename T, int V>
+__global__ void k_shufcat_fwd(const T* __restrict__ skip, const T* __restrict__ z, T* __restrict__ out, UpGeom g) {
+  const int C = g.Cs + g.Cu, CV = C / V;
+  long long total = (long long)g.N * g.H * g.W * CV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % CV) * V; long long p = i / CV; int w = (int)(p % g.W); long long q = p / g.W; int h = (int)(q % g.H); int n = (int)(q / g.H);
+    FVec<V> o;
+    if (c < g.Cs) o = ldv<V>(skip + p * g.Cs + c);
+    else {
+      int uh = h - g.padt, uw = w - g.padl;
+      if (uh < 0 || uh >= 2 * g.Hl || uw < 0 || uw >= 2 * g.Wl) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) o.v[j] = 0.f;
+      } else {
+        int ab = (uh & 1) * 2 + (uw & 1);
+        o = ldv<V>(z + ((((long long)n * g.Hl + (uh >> 1)) * g.Wl + (uw >> 1)) * 4 + ab) * g.Cu + (c - g.Cs));
+      }
+    }
+    stv<V>(out + p * C + c, o);
+  }
+}
+// dz[N,Hl,Wl,4*Cu] gathered from dcat[..., Cs:]
+template <typename T, int V>
+__global__ void k_shufcat_bwd(const T* __restrict__ dcat, T* __restrict__ dz, UpGeom g) {
+  const int C = g.Cs + g.Cu, CV = g.Cu / V;
+  long long total = (long long)g.N * g.Hl * g.Wl * 4 * CV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int cu = (int)(i % CV) * V; long long p = i / CV; int ab = (int)(p & 3); long long pl = p >> 2;
+    int wl = (int)(pl % g.Wl); long long q = pl / g.Wl; int hl = (int)(q % g.Hl); int n = (int)(q / g.Hl);
+    int h = 2 * hl + (ab >> 1) + g.padt, w = 2 * wl + (ab & 1) + g.padl;
+    FVec<V> o = ldv<V>(dcat + (((long long)n * g.H + h) * g.W + w) * C + g.Cs + cu);
+    stv<V>(dz + p * g.Cu + cu, o);
+  }
+}
+extern "C" int egm_pixel_shuffle_concat_fwd(const void* skip, const void* z, void* out, int dtype, int N, int Hl, int Wl, int H, int W, int Cs, int Cu, void* stream) {
+  UpGeom g; int e = up_geom(g, N, Hl, Wl, H, W, Cs, Cu); if (e) return e;
+  long long total = (long long)N * H * W * (Cs + Cu);
+  if (total == 0) return EGM_OK;
+  int v = egm_pick_vec(Cs); int v2 = egm_pick_vec(Cu); if (v2 < v) v = v2;
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_shufcat_fwd<T, V><<<egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream>>>((const T*)skip, (const T*)z, (T*)out, g))));
+  EGM_LAUNCH_CHECK("pixel_shuffle_concat_fwd"); return EGM_OK;
+}
+extern "C" int egm_pixel_shuffle_concat_bwd(const void* dcat, void* dz, int dtype, int N, int Hl, int Wl, int H, int W, int Cs, int Cu, void* stream) {
+  UpGeom g; int e = up_geom(g, N, Hl, Wl, H, W, Cs, Cu); if (e) return e;
+  long long total = (long long)N * Hl * Wl * 4 * Cu;
+  if (total == 0) return EGM_OK;
+  int v = egm_pick_vec(Cu, Cs + Cu, Cs);
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_shufcat_bwd<T, V><<<egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dcat, (T*)dz, g))));
+  EGM_LAUNCH_CHECK("pixel_shuffle_concat_bwd"); return EGM_OK;
+}

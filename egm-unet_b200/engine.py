@@ -371,6 +371,46 @@ def upsample_concat(ctx: Ctx, low: Var, skip: Var) -> Var:
     return out
 
 
+def deconv_concat(ctx: Ctx, low: Var, skip: Var, up: nn.ConvTranspose2d) -> Var:
+    """cat([skip, pad(ConvTranspose2d(k=2, s=2)(low))]) -- Up.forward with bilinear=False (src/unet.py:35-37,39-49).
+    The transposed conv is a per-pixel GEMM (1x1 conv onto 4*Cout channels, tcgen05 path) followed by a pixel shuffle
+    written straight into the concat tensor."""
+    n, hl, wl, cin = low.shape
+    _, h, w, cs = skip.shape
+    cu = up.out_channels
+    assert up.kernel_size == (2, 2) and up.stride == (2, 2) and up.in_channels == cin
+    wt = torch.empty(4 * cu, cin, 1, 1, **ctx.f32)
+    call("deconv_weight_pack", _p(up.weight), wt, cin, cu, 0)
+    b4 = None
+    if up.bias is not None:
+        b4 = torch.empty(4 * cu, **ctx.f32)
+        for k in range(4):
+            call("copy_slice", _p(up.bias), b4, abi.F32, 1, cu, cu, 0, 4 * cu, k * cu, 0)
+
+    def sink_w(dwt):
+        call("deconv_weight_pack", ctx.grad_slot(up.weight), dwt, cin, cu, 1)
+
+    def sink_b(g4):
+        gb = ctx.grad_slot(up.bias)
+        for k in range(4):
+            call("copy_slice", g4, gb, abi.F32, 1, cu, 4 * cu, k * cu, cu, 0, 1 if k else 0)
+    z = conv2d(ctx, low, wt, b4, wgrad_sink=sink_w, bgrad_sink=sink_b)
+    out = Var(ctx.empty(n, h, w, cs + cu))
+    call("pixel_shuffle_concat_fwd", skip.t, z.t, out.t, ctx.code, n, hl, wl, h, w, cs, cu)
+    if ctx.record:
+        def bwd():
+            d, out.grad = out.grad, None
+            if d is None:
+                return
+            gs, acc = skip.grad_target()
+            call("copy_slice", d, gs, ctx.code, n * h * w, cs, cs + cu, 0, cs, 0, acc)
+            dz = ctx.empty(n, hl, wl, 4 * cu)
+            call("pixel_shuffle_concat_bwd", d, dz, ctx.code, n, hl, wl, h, w, cs, cu)
+            z.accum(dz)
+        ctx.push(bwd)
+    return out
+
+
 def copy_into(ctx: Ctx, src: Var, dst: Var, dst_coff: int, src_coff: int = 0, c: Optional[int] = None):
     """dst[..., dst_coff:dst_coff+c] = src[..., src_coff:src_coff+c]; gradient flows back from dst.grad."""
     c = c or src.C

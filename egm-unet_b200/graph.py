@@ -14,7 +14,7 @@ import torch.nn as nn
 from . import abi
 from .abi import call
 from .engine import (ACT_NONE, ACT_RELU, ACT_SIGMOID, MODE_PLAIN, MODE_RESIDUAL, Ctx, Var, _p, bn_act, conv2d, conv_module,
-                     copy_into, edge_enhancer, from_nchw, maxpool2, mca_layer, release_grad, slice_channels, to_nchw,
+                     copy_into, deconv_concat, edge_enhancer, from_nchw, maxpool2, mca_layer, release_grad, slice_channels, to_nchw,
                      upsample_concat)
 
 
@@ -241,9 +241,9 @@ def down_block(ctx: Ctx, x: Var, down, variant: str) -> Var:
 
 def up_block(ctx: Ctx, low: Var, skip: Var, up) -> Var:
     """Up (bilinear): src/EGM-UNet.py:927-949 == src/unet.py:29-51."""
-    if not isinstance(up.up, nn.Upsample):
-        raise NotImplementedError("egm_b200: Up(bilinear=False) (ConvTranspose2d) is not on the B200 path yet")
-    return double_conv(ctx, upsample_concat(ctx, low, skip), up.conv)
+    if isinstance(up.up, nn.Upsample):
+        return double_conv(ctx, upsample_concat(ctx, low, skip), up.conv)
+    return double_conv(ctx, deconv_concat(ctx, low, skip, up.up), up.conv)
 
 
 def net_forward(ctx: Ctx, model, x_nchw: torch.Tensor, variant: str):

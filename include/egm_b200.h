@@ -81,6 +81,10 @@ int egm_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int accumulate, 
 int egm_upsample_concat_fwd(const void* skip, const void* low, void* out, int dtype, int N, int Hl, int Wl, int H, int W, int Cs, int Cu, void* stream);
 int egm_upsample_concat_bwd_low(const void* dcat, void* dlow, int dtype, int N, int Hl, int Wl, int H, int W, int Cs, int Cu, void* stream);
 
+int egm_deconv_weight_pack(float* w, float* wt, int Cin, int Cout, int mode, void* stream);      /* nn.ConvTranspose2d(k2,s2): src/unet.py:35-37 */
+int egm_pixel_shuffle_concat_fwd(const void* skip, const void* z, void* out, int dtype, int N, int Hl, int Wl, int H, int W, int Cs, int Cu, void* stream);
+int egm_pixel_shuffle_concat_bwd(const void* dcat, void* dz, int dtype, int N, int Hl, int Wl, int H, int W, int Cs, int Cu, void* stream);
+
 /* ---- MCALayer (src/EGM-UNet.py:686-791, MCAGate :836-869) ---- */
 long long egm_mca_vec_len(int N, int H, int W, int C);
 long long egm_mca_vec_off_w(int N, int H);

@@ -14,13 +14,14 @@ from tests.util import rel_err, cosine
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-CASES = [("unet", "unet_2x64x48"), ("unet", "unet_2x77x101_odd"), ("egm", "egm_2x64x48"), ("egm", "egm_2x77x101_odd"), ("yuan", "yuan_2x64x64")]
+CASES = [("unet", "unet_2x64x48"), ("unet", "unet_2x77x101_odd"), ("egm", "egm_2x64x48"), ("egm", "egm_2x77x101_odd"), ("yuan", "yuan_2x64x64"),
+         ("unet", "unet_deconv_2x32x32")]
 
 
-def build(variant):
+def build(variant, **kw):
     import egm_unet_b200 as E
     cls = {"unet": E.UNet, "egm": E.GRFBUNet, "yuan": E.YuanGRFBUNet}[variant]
-    return cls(in_channels=3, num_classes=2, base_c=32)
+    return cls(in_channels=3, num_classes=2, base_c=32, **kw)
 
 
 @pytest.mark.parametrize("variant,tag", CASES)
@@ -28,7 +29,7 @@ def test_fp32_check_mode_matches_reference_fixture(variant, tag):
     import egm_unet_b200 as E
     fx = np.load(os.path.join(GOLD, tag + ".npz"))
     n, h, w = (int(v) for v in fx["shape"])
-    model = build(variant)
+    model = build(variant, **({"bilinear": False} if "deconv" in tag else {}))
     sd = synth.fill_state_dict(model.state_dict())
     model.load_state_dict(sd)
     model = model.cuda().train().set_check_mode(True)
