@@ -125,3 +125,63 @@ class Trainer:
             dist.all_reduce(self.store.grads, op=dist.ReduceOp.SUM, group=self.pg)
             call("sgd_step", self.store.params, self.store.grads, self.mom_buf, self.store.total, self.hp)
         return self._s_loss
+
+    # ------------------------------------------------------------------ host-fed loop (what train_one_epoch does, pipelined)
+    def run(self, host_batches):
+        """Train on an iterable of (image, target) HOST tensors (ideally pinned) and return the per-step losses as floats.
+
+        Equivalent to the reference loop `for image, target in loader: image.to(device) ...; loss.item()`
+        (train_utils/train_and_eval.py:55-73) but without its two serialisation points: the H2D copy of batch i+1 runs on a
+        copy stream while batch i computes (double-buffered device staging), and every loss is read back with an async D2H
+        into pinned memory that is only waited for one step later ("lazy metric read-back")."""
+        dev = self.dev
+        copy_stream = getattr(self, "_copy_stream", None) or torch.cuda.Stream(device=dev)
+        self._copy_stream = copy_stream
+        compute = torch.cuda.current_stream(dev)
+        it = iter(host_batches)
+        bufs, ready, freed = [None, None], [None, None], [None, None]
+
+        def prefetch(slot, batch):
+            img_h, tgt_h = batch
+            if bufs[slot] is None or bufs[slot][0].shape != img_h.shape:
+                bufs[slot] = (torch.empty(img_h.shape, dtype=torch.float32, device=dev), torch.empty(tgt_h.shape, dtype=torch.int64, device=dev))
+            if freed[slot] is not None:
+                copy_stream.wait_event(freed[slot])          # the step that last read this slot has consumed it
+            with torch.cuda.stream(copy_stream):
+                bufs[slot][0].copy_(img_h, non_blocking=True)
+                bufs[slot][1].copy_(tgt_h, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            ready[slot] = ev
+
+        losses, pending = [], []
+        nxt = next(it, None)
+        if nxt is None:
+            return losses
+        prefetch(0, nxt)
+        i = 0
+        while nxt is not None:
+            slot = i & 1
+            compute.wait_event(ready[slot])
+            loss = self.step(bufs[slot][0], bufs[slot][1])
+            ev = torch.cuda.Event()
+            ev.record(compute)
+            freed[slot] = ev
+            host = torch.empty(1, dtype=torch.float32).pin_memory() if len(pending) < 2 else pending[0][0]
+            if len(pending) >= 2:                            # wait for (and recycle the buffer of) the loss issued two steps ago
+                h, e = pending.pop(0)
+                e.synchronize()
+                losses.append(float(h[0]))
+                host = h
+            host.copy_(loss.detach().reshape(1), non_blocking=True)
+            e2 = torch.cuda.Event()
+            e2.record(compute)
+            pending.append((host, e2))
+            nxt = next(it, None)
+            if nxt is not None:
+                prefetch((i + 1) & 1, nxt)
+            i += 1
+        for h, e in pending:
+            e.synchronize()
+            losses.append(float(h[0]))
+        return losses

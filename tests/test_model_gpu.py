@@ -235,3 +235,21 @@ def test_cuda_graph_step_equals_eager_step():
     # bf16 + fp32 atomics (wgrad split-K) are not bit-deterministic: allow round-off level differences
     worst = max(rel_err(s1[k], s0[k]) for k in s0 if s0[k].numel() > 1)
     assert worst < 6e-2, worst
+
+
+def test_host_fed_pipelined_loop_equals_plain_steps():
+    """Trainer.run (double-buffered H2D prefetch + lagged loss read-back) gives the same losses as plain step() calls."""
+    from egm_unet_b200.trainer import Trainer
+    batches = [synth.make_inputs(2, 48, 48, seed=70 + i) for i in range(5)]
+    res = []
+    for mode in ("plain", "run"):
+        model = build("unet")
+        model.load_state_dict(synth.fill_state_dict(model.state_dict()))
+        model = model.cuda().train().set_check_mode(True)
+        tr = Trainer(model, use_graph=(mode == "run"))
+        if mode == "plain":
+            res.append([float(tr.step(i.cuda(), t.cuda())) for i, t in batches])
+        else:
+            res.append(tr.run((i.pin_memory(), t.pin_memory()) for i, t in batches))
+    assert len(res[1]) == 5
+    assert all(abs(a - b) <= 1e-3 * abs(a) for a, b in zip(*res)), res
