@@ -90,6 +90,12 @@ __device__ __forceinline__ void store16(__nv_bfloat16* yp, const uint32_t* v, co
   *reinterpret_cast<uint4*>(yp) = o[0];
   *reinterpret_cast<uint4*>(yp + 8) = o[1];
 }
+// one elected lane of a converged warp (keeps the surrounding control flow warp-uniform, so loop state lives in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version=1 <<46 | layout <<61
@@ -190,50 +196,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   const int tilesPerImg = p.tilesH * p.tilesW;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t bBytes = (uint32_t)(p.nChunk * p.bkc * 2);
-      if (p.wres) {
-        mbar_expect_tx(wfull, bBytes * (uint32_t)kIters);
-        for (int t = 0; t < taps; ++t)
-          for (int kc = 0; kc < p.kChunks; ++kc) tma_load_3d(sB + (size_t)(t * p.kChunks + kc) * p.bStride, &tmW, wfull, kc * p.bkc, 0, t);
-      }
-      const uint32_t txBytes = (uint32_t)p.aBytes + (p.wres ? 0u : bBytes);
-      int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
-        const int chunk = tile % p.coChunks, sp_t = tile / p.coChunks;
-        const int n = sp_t / tilesPerImg, r = sp_t - n * tilesPerImg;
-        const int h0 = (r / p.tilesW) * TILE_H, w0 = (r % p.tilesW) * TILE_W, co0 = chunk * p.nChunk;
-        for (int t = 0; t < taps; ++t) {
-          const int2 o = tapOff[t];
+    const bool leader = elect_one();
+    const uint32_t bBytes = (uint32_t)(p.nChunk * p.bkc * 2);
+    if (p.wres && leader) {
+      mbar_expect_tx(wfull, bBytes * (uint32_t)kIters);
+      for (int t = 0; t < taps; ++t)
+        for (int kc = 0; kc < p.kChunks; ++kc) tma_load_3d(sB + (size_t)(t * p.kChunks + kc) * p.bStride, &tmW, wfull, kc * p.bkc, 0, t);
+    }
+    const uint32_t txBytes = (uint32_t)p.aBytes + (p.wres ? 0u : bBytes);
+    int s = 0; uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+      const int chunk = tile % p.coChunks, sp_t = tile / p.coChunks;
+      const int n = sp_t / tilesPerImg, r = sp_t - n * tilesPerImg;
+      const int h0 = (r / p.tilesW) * TILE_H, w0 = (r % p.tilesW) * TILE_W, co0 = chunk * p.nChunk;
+      int dh = -p.pad, t = 0;
+      for (int kr = 0; kr < p.kh; ++kr, dh += p.dil) {
+        int dw = -p.pad;
+        for (int kc_ = 0; kc_ < p.kw; ++kc_, dw += p.dil, ++t) {
           for (int kc = 0; kc < p.kChunks; ++kc) {
             mbar_wait(&empty[s], ph ^ 1);
-            mbar_expect_tx(&full[s], txBytes);
-            tma_load_4d(sA + (size_t)s * p.aBytes, &tmX, &full[s], kc * p.bkc, w0 + o.x, h0 + o.y, n);
-            if (!p.wres) tma_load_3d(sB + (size_t)s * p.bStride, &tmW, &full[s], kc * p.bkc, co0, t);
+            if (leader) {
+              mbar_expect_tx(&full[s], txBytes);
+              tma_load_4d(sA + (size_t)s * p.aBytes, &tmX, &full[s], kc * p.bkc, w0 + dw, h0 + dh, n);
+              if (!p.wres) tma_load_3d(sB + (size_t)s * p.bStride, &tmW, &full[s], kc * p.bkc, co0, t);
+            }
             if (++s == p.stages) { s = 0; ph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(128, p.nChunk, 0, 0);
-      const int rowB = p.bkc * 2;                       // bytes per smem row == swizzle span
-      const uint32_t layout = rowB == 128 ? 2u : (rowB == 64 ? 4u : 6u);
-      const uint32_t sbo = 8u * rowB;                   // 8-row core-matrix group stride
-      const int ksteps = p.bkc / 16;
-      const uint64_t adBase = umma_desc(smem_u32(sA), 16, sbo, layout), bdBase = umma_desc(smem_u32(sB), 16, sbo, layout);
-      const uint32_t aStep = (uint32_t)p.aBytes >> 4, bStep = (uint32_t)p.bStride >> 4;
-      if (p.wres) mbar_wait(wfull, 0);
-      int s = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], aph ^ 1);
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc(128, p.nChunk, 0, 0);
+    const int rowB = p.bkc * 2;                       // bytes per smem row == swizzle span
+    const uint32_t layout = rowB == 128 ? 2u : (rowB == 64 ? 4u : 6u);
+    const uint32_t sbo = 8u * rowB;                   // 8-row core-matrix group stride
+    const int ksteps = p.bkc / 16;
+    const uint64_t adBase = umma_desc(smem_u32(sA), 16, sbo, layout), bdBase = umma_desc(smem_u32(sB), 16, sbo, layout);
+    const uint32_t aStep = (uint32_t)p.aBytes >> 4, bStep = (uint32_t)p.bStride >> 4;
+    if (p.wres) mbar_wait(wfull, 0);
+    int s = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)(acc * p.accCols);
+      uint32_t accf = 0;
+      for (int it = 0; it < kIters; ++it) {
+        mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(acc * p.accCols);
-        uint32_t accf = 0;
-        for (int it = 0; it < kIters; ++it) {
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
+        if (leader) {
           const uint64_t ad = adBase + (uint64_t)(s * aStep), bd = bdBase + (uint64_t)((p.wres ? it : s) * bStep);
           if (ksteps == 4) {
 #pragma unroll
@@ -241,13 +252,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
           } else if (ksteps == 2) {
 #pragma unroll
             for (int k = 0; k < 2; ++k) { umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, accf); accf = 1; }
-          } else { umma_bf16(d, ad, bd, idesc, accf); accf = 1; }
+          } else { umma_bf16(d, ad, bd, idesc, accf); }
           umma_commit(&empty[s]);
-          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[acc]);
-        if (++acc == 2) { acc = 0; aph ^= 1; }
+        accf = 1;
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
+      if (leader) umma_commit(&tfull[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; aph ^= 1; }
     }
   } else {
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
@@ -305,6 +319,7 @@ struct ConvHaloParams {
   int tilesH, tilesW, numTiles;
   int rowB, haloW, haloH, haloBytes, haloStride, wTapStride, stages, tmemCols, accCols;
   int nacc;                                          // TMEM accumulator buffers in flight (2..8)
+  int ksteps;                                        // MMAs (K=16) per tap = ceil(Cin/16); rowB may be wider than Cin*2 (zero-filled)
   int exp;                                           // timing experiments only (EGM_EXP): 1 = skip stores, 2 = rotate accumulators
 };
 constexpr int HT_H = 16, HT_W = 8;
@@ -345,52 +360,66 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // ---- TMA producer: all 32 lanes run the (uniform) loop, one elected lane issues
+    const bool leader = elect_one();
+    if (leader) {
       mbar_expect_tx(wfull, (uint32_t)(taps * p.Cout * p.rowB));
       for (int t = 0; t < taps; ++t) tma_load_3d(sW + (size_t)t * p.wTapStride, &tmW, wfull, 0, 0, t);
-      int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
-        int n = tile / (p.tilesH * p.tilesW); int r = tile - n * p.tilesH * p.tilesW;
-        int h0 = (r / p.tilesW) * HT_H, w0 = (r % p.tilesW) * HT_W;
-        mbar_wait(&empty[s], ph ^ 1);
-        if (p.exp & 8) { mbar_arrive(&full[s]); }
-        else {
-          mbar_expect_tx(&full[s], (uint32_t)p.haloBytes);
-          tma_load_4d(sA + (size_t)s * p.haloStride, &tmX, &full[s], 0, w0 - p.pad, h0 - p.pad, n);
-        }
-        if (++s == p.stages) { s = 0; ph ^= 1; }
+    }
+    const int tilesPerImg = p.tilesH * p.tilesW;
+    int s = 0; uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+      const int n = tile / tilesPerImg, r = tile - n * tilesPerImg;
+      const int h0 = (r / p.tilesW) * HT_H, w0 = (r % p.tilesW) * HT_W;
+      mbar_wait(&empty[s], ph ^ 1);
+      if (leader) {
+        mbar_expect_tx(&full[s], (uint32_t)p.haloBytes);
+        tma_load_4d(sA + (size_t)s * p.haloStride, &tmX, &full[s], 0, w0 - p.pad, h0 - p.pad, n);
       }
+      if (++s == p.stages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(128, p.Cout, 0, 0);
-      const uint32_t layout = p.rowB == 128 ? 2u : (p.rowB == 64 ? 4u : 6u);
-      const uint32_t sboA = (uint32_t)(p.haloW * p.rowB);
-      const int ksteps = p.rowB / 32;
-      mbar_wait(wfull, 0);
-      int s = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], aph ^ 1);
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(acc * p.accCols);
-        const uint64_t ad0 = umma_desc(smem_u32(sA + (size_t)s * p.haloStride), 16, sboA, layout);
+    // ---- MMA issuer: warp-uniform loops; descriptors are pure functions of uniform loop counters
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc(128, p.Cout, 0, 0);
+    const uint32_t layout = p.rowB == 128 ? 2u : (p.rowB == 64 ? 4u : 6u);
+    const uint32_t sboA = (uint32_t)(p.haloW * p.rowB);
+    const int ksteps = p.ksteps;
+    const uint64_t bd0 = umma_desc(smem_u32(sW), 16, 8u * p.rowB, layout);
+    const uint32_t bTap = (uint32_t)p.wTapStride >> 4;                  // B descriptor advance per tap
+    const uint32_t aCol = (uint32_t)(p.dil * p.rowB) >> 4;              // A advance per kernel column
+    const uint32_t aRow = (uint32_t)(p.dil * p.haloW * p.rowB) >> 4;    // A advance per kernel row
+    mbar_wait(wfull, 0);
+    int s = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], aph ^ 1);
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)(acc * p.accCols);
+      const uint64_t ad0 = umma_desc(smem_u32(sA + (size_t)s * p.haloStride), 16, sboA, layout);
+      if (leader) {
         uint32_t accf = 0;
-        for (int t = 0; t < ((p.exp & 4) ? 0 : taps); ++t) {   // per tap: one 64-bit LDS (B descriptor) + one 32-bit LDS (A row offset >> 4)
-          const uint64_t ad = ad0 + tapA[t], bd = tapB[t];
-          if (ksteps == 4) {
+        uint64_t bd = bd0, adr = ad0;
+        for (int r = 0; r < p.kh; ++r) {
+          uint64_t ad = adr;
+          for (int c = 0; c < p.kw; ++c) {
+            if (ksteps == 4) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, accf); accf = 1; }
-          } else if (ksteps == 2) {
+              for (int k = 0; k < 4; ++k) { umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, accf); accf = 1; }
+            } else if (ksteps == 2) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) { umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, accf); accf = 1; }
-          } else { umma_bf16(d, ad, bd, idesc, accf); accf = 1; }
+              for (int k = 0; k < 2; ++k) { umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, accf); accf = 1; }
+            } else { umma_bf16(d, ad, bd, idesc, accf); accf = 1; }
+            ad += aCol; bd += bTap;
+          }
+          adr += aRow;
         }
         umma_commit(&empty[s]);
         umma_commit(&tfull[acc]);
-        if (++s == p.stages) { s = 0; ph ^= 1; }
-        if (++acc == p.nacc) { acc = 0; aph ^= 1; }
       }
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1; }
+      if (++acc == p.nacc) { acc = 0; aph ^= 1; }
     }
   } else {
     const int q = warp & 3;
@@ -409,7 +438,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
           uint32_t v[32];
           tmem_ld32(t0 + c, v);
           tmem_ld_wait();
-          if (valid && !(p.exp & 1)) { store16(yp + c, v, bias ? bias + c : nullptr); store16(yp + c + 16, v + 16, bias ? bias + c + 16 : nullptr); }
+          if (valid) { store16(yp + c, v, bias ? bias + c : nullptr); store16(yp + c + 16, v + 16, bias ? bias + c + 16 : nullptr); }
         }
       } else {
         for (int c = 0; c < p.Cout; c += 16) {
@@ -444,7 +473,9 @@ static int launch_conv_halo(const void* x, const void* wpk, const float* bias, v
   ConvHaloParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
   p.tilesH = cdiv(H, HT_H); p.tilesW = cdiv(W, HT_W); p.numTiles = N * p.tilesH * p.tilesW;
-  p.rowB = Cin * 2; p.haloW = HT_W + 2 * p.pad; p.haloH = HT_H + 2 * p.pad;
+  p.rowB = Cin * 2; p.ksteps = Cin / 16;
+  { const char* pw = getenv("EGM_HALO_ROW128"); if (pw && pw[0] == '1') p.rowB = 128; }   // experiment: always 128-byte rows (TMA zero-fills)
+  p.haloW = HT_W + 2 * p.pad; p.haloH = HT_H + 2 * p.pad;
   p.haloBytes = p.haloW * p.haloH * p.rowB; p.haloStride = (p.haloBytes + 1023) / 1024 * 1024;
   p.wTapStride = (Cout * p.rowB + 1023) / 1024 * 1024;
   size_t wres = (size_t)kh * kw * p.wTapStride;
@@ -454,8 +485,8 @@ static int launch_conv_halo(const void* x, const void* wpk, const float* bias, v
   { const char* ev = getenv("EGM_EXP"); p.exp = ev ? atoi(ev) : 0; const char* na = getenv("EGM_NACC"); if (na) p.nacc = atoi(na); }
   p.tmemCols = pow2_cols(p.nacc * p.accCols);
   CUtensorMap tmX, tmW;
-  int e = make_map_nhwc(&tmX, x, N, H, W, Cin, Cin, p.haloW, p.haloH); if (e) return e;
-  e = make_map_w(&tmW, wpk, kh * kw, Cout, Cin, Cin, Cout); if (e) return e;
+  int e = make_map_nhwc(&tmX, x, N, H, W, Cin, p.rowB / 2, p.haloW, p.haloH); if (e) return e;
+  e = make_map_w(&tmW, wpk, kh * kw, Cout, Cin, p.rowB / 2, Cout); if (e) return e;
   size_t smem = wres + (size_t)p.stages * p.haloStride + 1024 + 1408;
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(k_conv_tc_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
@@ -677,31 +708,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      for (int tile = tileBeg; tile < tileEnd; ++tile) {
-        int n = tile / (p.tilesH * p.tilesW); int r = tile - n * p.tilesH * p.tilesW;
-        int h0 = (r / p.tilesW) * HT_H, w0 = (r % p.tilesW) * HT_W;
-        uint8_t* st = smem + (size_t)s * p.stageBytes;
-        mbar_wait(&empty[s], ph ^ 1);
+    const bool leader = elect_one();
+    const int tilesPerImg = p.tilesH * p.tilesW;
+    int s = 0; uint32_t ph = 0;
+    for (int tile = tileBeg; tile < tileEnd; ++tile) {
+      const int n = tile / tilesPerImg, r = tile - n * tilesPerImg;
+      const int h0 = (r / p.tilesW) * HT_H, w0 = (r % p.tilesW) * HT_W;
+      uint8_t* st = smem + (size_t)s * p.stageBytes;
+      mbar_wait(&empty[s], ph ^ 1);
+      if (leader) {
         mbar_expect_tx(&full[s], (uint32_t)(p.mAtoms * p.aAtomBytes + p.haloBytes));
         for (int a = 0; a < p.mAtoms; ++a)
           tma_load_4d(st + (size_t)a * p.aAtomBytes, &tmDY, &full[s], coc * p.mch + a * p.aAtomCh, w0, h0, n);
         tma_load_4d(st + p.aBytes, &tmX, &full[s], cic * p.nch, w0 - p.pad, h0 - p.pad, n);
-        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
+      if (++s == p.stages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(128, nN, 1, 1);
-      const uint32_t layA = p.rowA == 128 ? 2u : (p.rowA == 64 ? 4u : 6u), layB = p.rowB == 128 ? 2u : (p.rowB == 64 ? 4u : 6u);
-      const uint32_t kA = (uint32_t)(16 * p.rowA) >> 4;                 // A advance per 16-pixel K step (16-byte units)
-      const uint32_t kB = (uint32_t)(2 * p.haloW * p.rowB) >> 4;        // B advance per K step: two halo rows
-      const uint32_t rB = (uint32_t)(p.dil * p.haloW * p.rowB) >> 4;    // B advance per kernel row
-      int s = 0; uint32_t ph = 0; uint32_t accf = 0;
-      for (int tile = tileBeg; tile < tileEnd; ++tile) {
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc(128, nN, 1, 1);
+    const uint32_t layA = p.rowA == 128 ? 2u : (p.rowA == 64 ? 4u : 6u), layB = p.rowB == 128 ? 2u : (p.rowB == 64 ? 4u : 6u);
+    const uint32_t kA = (uint32_t)(16 * p.rowA) >> 4;                 // A advance per 16-pixel K step (16-byte units)
+    const uint32_t kB = (uint32_t)(2 * p.haloW * p.rowB) >> 4;        // B advance per K step: two halo rows
+    const uint32_t rB = (uint32_t)(p.dil * p.haloW * p.rowB) >> 4;    // B advance per kernel row
+    int s = 0; uint32_t ph = 0; uint32_t accf = 0;
+    for (int tile = tileBeg; tile < tileEnd; ++tile) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (leader) {
         const uint32_t a0 = smem_u32(smem + (size_t)s * p.stageBytes);
         const uint64_t ad0 = umma_desc(a0, (uint32_t)p.aAtomBytes, 8u * p.rowA, layA);
         const uint64_t bd0 = umma_desc(a0 + p.aBytes, (uint32_t)(p.dil * p.rowB), (uint32_t)(p.haloW * p.rowB), layB) + (uint64_t)(r0 * rB);
@@ -714,10 +748,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_co
           accf = 1;
         }
         umma_commit(&empty[s]);
-        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
-      umma_commit(tfull);
+      accf = 1;
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1; }
     }
+    if (leader) umma_commit(tfull);
+    __syncwarp();
   } else if (tileBeg < tileEnd) {
     const int q = warp & 3;
     const int co_local = q * 32 + lane;
