@@ -594,45 +594,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      for (int tile = tileBeg; tile < tileEnd; ++tile) {
-        int n = tile / (p.tilesH * p.tilesW); int r = tile - n * p.tilesH * p.tilesW;
-        int h0 = (r / p.tilesW) * TILE_H, w0 = (r % p.tilesW) * TILE_W;
-        uint8_t* st = smem + (size_t)s * p.stageBytes;
-        mbar_wait(&empty[s], ph ^ 1);
+    const bool leader = elect_one();
+    const int tilesPerImg = p.tilesH * p.tilesW;
+    int s = 0; uint32_t ph = 0;
+    for (int tile = tileBeg; tile < tileEnd; ++tile) {
+      const int n = tile / tilesPerImg, r = tile - n * tilesPerImg;
+      const int h0 = (r / p.tilesW) * TILE_H, w0 = (r % p.tilesW) * TILE_W;
+      uint8_t* st = smem + (size_t)s * p.stageBytes;
+      mbar_wait(&empty[s], ph ^ 1);
+      if (leader) {
         mbar_expect_tx(&full[s], (uint32_t)(p.mAtoms * p.aAtomBytes + nt * p.bTileBytes));
         for (int a = 0; a < p.mAtoms; ++a)
           tma_load_4d(st + (size_t)a * p.aAtomBytes, &tmDY, &full[s], coc * p.mch + a * 64, w0, h0, n);
         for (int j = 0; j < nt; ++j) {
-          int t = t0 + j; int dh = (t / p.kw) * p.dil - p.pad, dw = (t % p.kw) * p.dil - p.pad;
+          const int t = t0 + j, dh = (t / p.kw) * p.dil - p.pad, dw = (t % p.kw) * p.dil - p.pad;
           tma_load_4d(st + p.aBytes + (size_t)j * p.bTileBytes, &tmX, &full[s], cic * p.nch, w0 + dw, h0 + dh, n);
         }
-        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
+      if (++s == p.stages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(p.ummaM, p.nch, 1, 1);
-      const int rowA = (p.mch >= 64 ? 64 : p.mch) * 2, rowB = p.nch * 2;
-      const uint32_t layA = rowA == 128 ? 2u : (rowA == 64 ? 4u : 6u), layB = rowB == 128 ? 2u : (rowB == 64 ? 4u : 6u);
-      int s = 0; uint32_t ph = 0; bool first = true;
-      for (int tile = tileBeg; tile < tileEnd; ++tile) {
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc(p.ummaM, p.nch, 1, 1);
+    const int rowA = (p.mch >= 64 ? 64 : p.mch) * 2, rowB = p.nch * 2;
+    const uint32_t layA = rowA == 128 ? 2u : (rowA == 64 ? 4u : 6u), layB = rowB == 128 ? 2u : (rowB == 64 ? 4u : 6u);
+    const uint32_t kA = (uint32_t)(16 * rowA) >> 4, kB = (uint32_t)(16 * rowB) >> 4, jB = (uint32_t)p.bTileBytes >> 4;
+    int s = 0; uint32_t ph = 0; uint32_t accf = 0;
+    for (int tile = tileBeg; tile < tileEnd; ++tile) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (leader) {
         const uint32_t a0 = smem_u32(smem + (size_t)s * p.stageBytes);
+        const uint64_t ad0 = umma_desc(a0, (uint32_t)p.aAtomBytes, 8u * rowA, layA);
+        uint64_t bdj = umma_desc(a0 + p.aBytes, (uint32_t)p.bTileBytes, 8u * rowB, layB);
+        uint32_t dcol = tmem_base;
         for (int j = 0; j < nt; ++j) {
-          const uint32_t b0 = a0 + p.aBytes + j * p.bTileBytes;
-          for (int k = 0; k < TILE_PIX / 16; ++k)      // 16 pixels (= 2 groups of 8 K-rows) per MMA
-            umma_bf16(tmem_base + (uint32_t)(j * p.nch), umma_desc(a0 + k * 16 * rowA, (uint32_t)p.aAtomBytes, 8u * rowA, layA),
-                      umma_desc(b0 + k * 16 * rowB, (uint32_t)p.bTileBytes, 8u * rowB, layB), idesc, (first && k == 0) ? 0u : 1u);
+          uint32_t af = accf;
+#pragma unroll
+          for (int k = 0; k < TILE_PIX / 16; ++k) { umma_bf16(dcol, ad0 + k * kA, bdj + k * kB, idesc, af); af = 1; }   // 16 pixels per MMA
+          bdj += jB; dcol += (uint32_t)p.nch;
         }
-        first = false;
         umma_commit(&empty[s]);
-        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
-      umma_commit(tfull);
+      accf = 1;
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1; }
     }
+    if (leader) umma_commit(tfull);
+    __syncwarp();
   } else if (tileBeg < tileEnd) {
     const int q = warp & 3;
     const int co_local = q * 32 + lane;                  // TMEM lane = output channel inside the chunk
