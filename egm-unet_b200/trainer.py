@@ -139,7 +139,12 @@ class Trainer:
         self._copy_stream = copy_stream
         compute = torch.cuda.current_stream(dev)
         it = iter(host_batches)
-        bufs, ready, freed = [None, None], [None, None], [None, None]
+        # device staging buffers and pinned loss slots live on the trainer: allocating them (cudaMalloc / cudaHostAlloc) costs
+        # milliseconds and would otherwise be paid by every call
+        if not hasattr(self, "_stage"):
+            self._stage, self._loss_slots = [None, None], [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(3)]
+        bufs, ready, freed = self._stage, [None, None], [None, None]
+        free_hosts = list(self._loss_slots)
 
         def prefetch(slot, batch):
             img_h, tgt_h = batch
@@ -167,12 +172,12 @@ class Trainer:
             ev = torch.cuda.Event()
             ev.record(compute)
             freed[slot] = ev
-            host = torch.empty(1, dtype=torch.float32).pin_memory() if len(pending) < 2 else pending[0][0]
-            if len(pending) >= 2:                            # wait for (and recycle the buffer of) the loss issued two steps ago
+            if len(pending) >= 2:                            # wait for (and recycle the slot of) the loss issued two steps ago
                 h, e = pending.pop(0)
                 e.synchronize()
                 losses.append(float(h[0]))
-                host = h
+                free_hosts.append(h)
+            host = free_hosts.pop()
             host.copy_(loss.detach().reshape(1), non_blocking=True)
             e2 = torch.cuda.Event()
             e2.record(compute)
