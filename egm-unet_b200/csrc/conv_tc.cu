@@ -177,11 +177,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   uint64_t* tfull = empty + p.stages;
   uint64_t* tempty = tfull + 2;
   uint64_t* wfull = tempty + 2;
-  int2* tapOff = (int2*)(wfull + 1);                                    // [taps] (dw, dh) of each tap
-  uint32_t* tmem_slot = (uint32_t*)(tapOff + 64);
+  uint32_t* tmem_slot = (uint32_t*)(wfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x < taps) tapOff[threadIdx.x] = make_int2((threadIdx.x % p.kw) * p.dil - p.pad, (threadIdx.x / p.kw) * p.dil - p.pad);
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
@@ -320,7 +318,8 @@ struct ConvHaloParams {
   int rowB, haloW, haloH, haloBytes, haloStride, wTapStride, stages, tmemCols, accCols;
   int nacc;                                          // TMEM accumulator buffers in flight (2..8)
   int ksteps;                                        // MMAs (K=16) per tap = ceil(Cin/16); rowB may be wider than Cin*2 (zero-filled)
-  int exp;                                           // timing experiments only (EGM_EXP): 1 = skip stores, 2 = rotate accumulators
+  int exp;                                           // EGM_EXP diagnostic bit mask (timing ablations; results are wrong):
+                                                     // 1 = no global stores, 4 = no MMAs, 8 = no TMA loads
 };
 constexpr int HT_H = 16, HT_W = 8;
 
@@ -336,17 +335,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
   uint64_t* tfull = empty + p.stages;
   uint64_t* tempty = tfull + 8;
   uint64_t* wfull = tempty + 8;
-  uint64_t* tapB = wfull + 1;                          // [taps] UMMA descriptor of each tap's resident weight tile
-  uint32_t* tapA = (uint32_t*)(tapB + 64);             // [taps] (row offset of the tap inside the halo tile) >> 4
-  uint32_t* tmem_slot = tapA + 64;
+  uint32_t* tmem_slot = (uint32_t*)(wfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x < taps) {
-    const int t = threadIdx.x;
-    const uint32_t layout = p.rowB == 128 ? 2u : (p.rowB == 64 ? 4u : 6u);
-    tapB[t] = umma_desc(smem_u32(sW + (size_t)t * p.wTapStride), 16, 8u * p.rowB, layout);
-    tapA[t] = (uint32_t)(((t / p.kw) * p.dil * p.haloW + (t % p.kw) * p.dil) * p.rowB) >> 4;
-  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < p.nacc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
@@ -373,8 +364,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
       const int h0 = (r / p.tilesW) * HT_H, w0 = (r % p.tilesW) * HT_W;
       mbar_wait(&empty[s], ph ^ 1);
       if (leader) {
-        mbar_expect_tx(&full[s], (uint32_t)p.haloBytes);
-        tma_load_4d(sA + (size_t)s * p.haloStride, &tmX, &full[s], 0, w0 - p.pad, h0 - p.pad, n);
+        if (p.exp & 8) mbar_arrive(&full[s]);
+        else {
+          mbar_expect_tx(&full[s], (uint32_t)p.haloBytes);
+          tma_load_4d(sA + (size_t)s * p.haloStride, &tmX, &full[s], 0, w0 - p.pad, h0 - p.pad, n);
+        }
       }
       if (++s == p.stages) { s = 0; ph ^= 1; }
     }
@@ -400,7 +394,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
       if (leader) {
         uint32_t accf = 0;
         uint64_t bd = bd0, adr = ad0;
-        for (int r = 0; r < p.kh; ++r) {
+        for (int r = 0; r < ((p.exp & 4) ? 0 : p.kh); ++r) {
           uint64_t ad = adr;
           for (int c = 0; c < p.kw; ++c) {
             if (ksteps == 4) {
@@ -438,7 +432,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
           uint32_t v[32];
           tmem_ld32(t0 + c, v);
           tmem_ld_wait();
-          if (valid) { store16(yp + c, v, bias ? bias + c : nullptr); store16(yp + c + 16, v + 16, bias ? bias + c + 16 : nullptr); }
+          if (valid && !(p.exp & 1)) { store16(yp + c, v, bias ? bias + c : nullptr); store16(yp + c + 16, v + 16, bias ? bias + c + 16 : nullptr); }
         }
       } else {
         for (int c = 0; c < p.Cout; c += 16) {
@@ -474,7 +468,6 @@ static int launch_conv_halo(const void* x, const void* wpk, const float* bias, v
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
   p.tilesH = cdiv(H, HT_H); p.tilesW = cdiv(W, HT_W); p.numTiles = N * p.tilesH * p.tilesW;
   p.rowB = Cin * 2; p.ksteps = Cin / 16;
-  { const char* pw = getenv("EGM_HALO_ROW128"); if (pw && pw[0] == '1') p.rowB = 128; }   // experiment: always 128-byte rows (TMA zero-fills)
   p.haloW = HT_W + 2 * p.pad; p.haloH = HT_H + 2 * p.pad;
   p.haloBytes = p.haloW * p.haloH * p.rowB; p.haloStride = (p.haloBytes + 1023) / 1024 * 1024;
   p.wTapStride = (Cout * p.rowB + 1023) / 1024 * 1024;
@@ -482,7 +475,7 @@ static int launch_conv_halo(const void* x, const void* wpk, const float* bias, v
   p.stages = (int)((198 * 1024 - wres) / p.haloStride); if (p.stages > 8) p.stages = 8; if (p.stages < 2) p.stages = 2;
   p.accCols = (Cout + 31) / 32 * 32;
   p.nacc = 512 / p.accCols; if (p.nacc > 8) p.nacc = 8; if (p.nacc < 2) p.nacc = 2;
-  { const char* ev = getenv("EGM_EXP"); p.exp = ev ? atoi(ev) : 0; const char* na = getenv("EGM_NACC"); if (na) p.nacc = atoi(na); }
+  { const char* ev = getenv("EGM_EXP"); p.exp = ev ? atoi(ev) : 0; }
   p.tmemCols = pow2_cols(p.nacc * p.accCols);
   CUtensorMap tmX, tmW;
   int e = make_map_nhwc(&tmX, x, N, H, W, Cin, p.rowB / 2, p.haloW, p.haloH); if (e) return e;

@@ -74,6 +74,7 @@ class Ctx:
         self._grad_slot = grad_slot
         self.use_tc = use_tc and dtype == torch.bfloat16
         self.f32 = dict(dtype=torch.float32, device=device)
+        self.wplan: Optional["WeightPlan"] = None   # batched weight preparation (Trainer); None = per-conv pack kernels
 
     # ---- allocation helpers
     def empty(self, *shape, dtype=None):
@@ -130,6 +131,77 @@ def seed_grad_from_nchw(ctx: Ctx, x: Var, g_nchw: torch.Tensor):
 
 
 # =========================================================================== convolution
+class WSpec:
+    """Where a conv's weight comes from: kind 0 = the parameter itself (grouped / thin ones are zero-padded to a dense 16-aligned
+    weight), 1 = FusionConv.down on cat[x, x] (W[:, :C] + W[:, C:]), 2 = conv7x7 + conv5x5 + conv3x3 merged into one 7x7."""
+    __slots__ = ("kind", "srcs", "bsrcs", "shape", "groups")
+
+    def __init__(self, kind, srcs, bsrcs, shape, groups=1):
+        self.kind, self.srcs, self.bsrcs, self.shape, self.groups = kind, tuple(srcs), tuple(b for b in bsrcs if b is not None), tuple(shape), groups
+
+    @property
+    def key(self):
+        return tuple(id(p) for p in self.srcs)
+
+
+class WeightJob:
+    __slots__ = ("spec", "coutp", "cinp", "wf", "wd", "bpad", "dwp", "gdst")
+
+
+class WeightPlan:
+    """All tcgen05 convs of one model: persistent packed operands + ONE device job table (csrc/wbatch.cu: EgmWJob).
+    Step 1 runs the per-conv pack kernels and registers each conv; from step 2 on `prep()` / `unpack()` replace ~450 tiny
+    launches by two."""
+
+    def __init__(self):
+        self.jobs = {}
+        self.ready = False
+        self.table = None
+        self.prep_total = self.unpack_total = 0
+
+    def register(self, ctx: "Ctx", spec: WSpec, coutp: int, cinp: int):
+        if self.ready or spec.key in self.jobs:
+            return
+        j = WeightJob()
+        j.spec, j.coutp, j.cinp = spec, coutp, cinp
+        j.gdst = [ctx.grad_slot(p) for p in spec.srcs]
+        self.jobs[spec.key] = j
+
+    def finalize(self, device):
+        import numpy as np
+        assert abi.query("wjob_bytes") == 160
+        rows, pb, ub = [], 0, 0
+        for j in self.jobs.values():
+            co, cig, kh, kw = j.spec.shape
+            taps = kh * kw
+            n = taps * j.coutp * j.cinp
+            j.wf = torch.empty(n, dtype=torch.bfloat16, device=device)
+            j.wd = torch.empty(n, dtype=torch.bfloat16, device=device)
+            j.dwp = torch.empty(n, dtype=torch.float32, device=device)
+            need_b = len(j.spec.bsrcs) > 0 and (j.coutp != co or len(j.spec.bsrcs) > 1)
+            j.bpad = torch.empty(j.coutp, dtype=torch.float32, device=device) if need_b else None
+            src = [p.detach().data_ptr() for p in j.spec.srcs] + [0, 0]
+            bsrc = ([p.detach().data_ptr() for p in j.spec.bsrcs] if need_b else []) + [0, 0, 0]
+            g = [t.data_ptr() for t in j.gdst] + [0, 0]
+            pack = lambda lo, hi: (lo & 0xffffffff) | (hi << 32)
+            rows.append(src[:3] + bsrc[:3] + [j.wf.data_ptr(), j.wd.data_ptr(), j.bpad.data_ptr() if need_b else 0, j.dwp.data_ptr()] + g[:3]
+                        + [pack(j.spec.kind, co), pack(cig, j.spec.groups), pack(kh, kw), pack(j.coutp, j.cinp), pb, ub, 0])
+            pb += n
+            ub += co * cig * taps
+        self.prep_total, self.unpack_total = pb, ub
+        if rows:
+            self.table = torch.from_numpy(np.array(rows, dtype=np.uint64).view(np.int64)).to(device)
+        self.ready = True
+
+    def prep(self):
+        if self.table is not None:
+            call("weight_prep_batch", self.table, len(self.jobs), self.prep_total)
+
+    def unpack(self):
+        if self.table is not None:
+            call("wgrad_unpack_batch", self.table, len(self.jobs), self.unpack_total)
+
+
 class PackedConv:
     """Per-forward packed weights of one nn.Conv2d (+ optional weight override for folded / merged kernels)."""
 
@@ -160,18 +232,28 @@ def _conv_run(ctx, pk: PackedConv, x_t, x_cs, x_co, w, bias, y_t, y_cs, y_co, ac
 
 def conv2d(ctx: Ctx, x: Var, weight: torch.Tensor, bias: Optional[torch.Tensor], *, groups: int = 1, dilation: int = 1,
            x_coff: int = 0, x_cin: Optional[int] = None, wgrad_sink: Optional[Callable] = None,
-           bgrad_sink: Optional[Callable] = None, tc_ok: bool = True) -> Var:
+           bgrad_sink: Optional[Callable] = None, tc_ok: bool = True, wspec: Optional[WSpec] = None) -> Var:
     """y = conv2d(x[..., x_coff:x_coff+Cin], weight) + bias  (stride 1, "same" padding).  `weight` is the reference
     [Cout, Cin/groups, kh, kw] fp32 parameter (or a derived tensor; then `wgrad_sink(dw)` receives its gradient)."""
     n, h, w, ctot = x.shape
     wparam, bparam = weight, bias          # gradient slots are keyed by the nn.Parameter objects
     weight, bias = _p(weight), _p(bias)
-    co, cig, kh, kw = weight.shape
+    co, cig, kh, kw = wspec.shape if weight is None else weight.shape
     cin = cig * groups
-    assert (x_cin or ctot - x_coff) == cin, (x.shape, weight.shape, x_coff)
+    assert (x_cin or ctot - x_coff) == cin, (x.shape, (co, cig, kh, kw), x_coff)
     sliced = not (x_coff == 0 and cin == ctot)
     native_tc = ctx.use_tc and tc_ok and not sliced and abi.query("conv2d_tc_supported", cin, co, kh, kw, dilation, groups)
-    if ctx.use_tc and tc_ok and not native_tc and abi.query("conv2d_tc_supported", _pad16(cin), _pad16(co), kh, kw, dilation, 1):
+    lifted_tc = ctx.use_tc and tc_ok and not native_tc and abi.query("conv2d_tc_supported", _pad16(cin), _pad16(co), kh, kw, dilation, 1)
+    # derived weights without a WSpec (ConvTranspose2d repack) keep the per-conv path: their tensors are rebuilt every step
+    plan = ctx.wplan if (native_tc or lifted_tc) and ctx.record and (wspec is not None or wgrad_sink is None) else None
+    if plan is not None:
+        if wspec is None:
+            wspec = WSpec(0, (wparam,), (bparam,), (co, cig, kh, kw), groups)
+        if plan.ready:
+            return _conv2d_planned(ctx, x, plan.jobs[wspec.key], bias, bparam, dilation, x_coff, cin, bgrad_sink)
+        plan.register(ctx, wspec, co if native_tc else _pad16(co), cin if native_tc else _pad16(cin))
+    assert weight is not None, "a derived weight may only be omitted once the weight plan is ready"
+    if lifted_tc:
         return _conv2d_lifted(ctx, x, wparam, bparam, weight, bias, groups, dilation, x_coff, cin, wgrad_sink, bgrad_sink)
     pk = PackedConv(ctx, weight, groups, dilation, tc_ok and not sliced)
     y = ctx.empty(n, h, w, co)
@@ -282,6 +364,63 @@ def _conv2d_lifted(ctx, x, wparam, bparam, weight, bias, groups, dilation, x_cof
                 gx, acc = x.grad_target(partial=sliced)
                 call("copy_slice", gxp, gx, ctx.code, M, cin, cinp, 0, ctot, x_coff, acc)
         ctx.push(bwd)
+    return out
+
+
+def _conv2d_planned(ctx, x, job: WeightJob, bias, bparam, dilation, x_coff, cin, bgrad_sink) -> Var:
+    """tcgen05 conv whose packed operands come from the WeightPlan (filled by egm_weight_prep_batch at the start of the step);
+    its weight gradient stays packed in job.dwp until egm_wgrad_unpack_batch at the end of backward."""
+    n, h, w, ctot = x.shape
+    co, cig, kh, kw = job.spec.shape
+    M = n * h * w
+    cinp, cop = job.cinp, job.coutp
+    sliced = not (x_coff == 0 and cin == ctot)
+    if cinp == ctot and not sliced:
+        xp = x.t
+    else:
+        xp = ctx.empty(n, h, w, cinp)
+        if cinp != cin:
+            call("memset_zero", xp, xp.numel() * 2)
+        call("copy_slice", x.t, xp, ctx.code, M, cin, ctot, x_coff, cinp, 0, 0)
+    bp = job.bpad if job.bpad is not None else bias
+    yp = ctx.empty(n, h, w, cop)
+    call("conv2d_tc", xp, job.wf, bp, yp, n, h, w, cinp, cop, kh, kw, dilation)
+    if cop == co:
+        y = yp
+    else:
+        y = ctx.empty(n, h, w, co)
+        call("copy_slice", yp, y, ctx.code, M, co, cop, 0, co, 0, 0)
+    out = Var(y)
+
+    def bwd():
+        dy = out.grad
+        out.grad = None
+        if dy is None:
+            return
+        if cop == co:
+            dyp = dy
+        else:
+            dyp = ctx.empty(n, h, w, cop)
+            call("memset_zero", dyp, dyp.numel() * 2)
+            call("copy_slice", dy, dyp, ctx.code, M, co, co, 0, cop, 0, 0)
+        call("conv2d_wgrad_tc", xp, dyp, job.dwp, n, h, w, cinp, cop, kh, kw, dilation)
+        if bparam is not None or bgrad_sink is not None:
+            gb = torch.empty(co, **ctx.f32) if bgrad_sink is not None else ctx.grad_slot(bparam)
+            call("channel_sum", dy, ctx.code, M, co, co, 0, ctx.f64(co), gb)
+            if bgrad_sink is not None:
+                bgrad_sink(gb)
+        if x.needs_grad:
+            gx, acc = x.grad_target(partial=sliced)
+            if cinp == ctot and not sliced and not acc:
+                call("conv2d_tc", dyp, job.wd, None, gx, n, h, w, cop, cinp, kh, kw, dilation)
+            else:
+                gxp = ctx.empty(n, h, w, cinp)
+                call("conv2d_tc", dyp, job.wd, None, gxp, n, h, w, cop, cinp, kh, kw, dilation)
+                if cinp == ctot and not sliced:
+                    call("axpby", gx, gxp, ctx.code, gxp.numel(), 1.0, 1.0)
+                else:
+                    call("copy_slice", gxp, gx, ctx.code, M, cin, cinp, 0, ctot, x_coff, acc)
+    ctx.push(bwd)
     return out
 
 

@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import abi
 from .abi import call
-from .engine import (ACT_NONE, ACT_RELU, ACT_SIGMOID, MODE_PLAIN, MODE_RESIDUAL, Ctx, Var, _p, bn_act, conv2d, conv_module,
+from .engine import (ACT_NONE, ACT_RELU, ACT_SIGMOID, MODE_PLAIN, MODE_RESIDUAL, Ctx, Var, WSpec, _p, bn_act, conv2d, conv_module,
                      copy_into, deconv_concat, edge_enhancer, from_nchw, maxpool2, mca_layer, release_grad, slice_channels, to_nchw,
                      upsample_concat)
 
@@ -26,34 +26,42 @@ def fusion_conv(ctx: Ctx, cat: Var, m) -> Var:
     M, HW = n * h * w, h * w
     wdown = _p(m.down.weight)
     dim = wdown.shape[0]
-    wfold = torch.empty(dim, cc, 1, 1, **ctx.f32)
-    call("copy_slice", wdown, wfold, abi.F32, dim, cc, 2 * cc, 0, cc, 0, 0)
-    call("copy_slice", wdown, wfold, abi.F32, dim, cc, 2 * cc, cc, cc, 0, 1)
-
-    def sink_down(dw):
-        g = ctx.grad_slot(m.down.weight)
-        call("copy_slice", dw, g, abi.F32, dim, cc, cc, 0, 2 * cc, 0, 0)
-        call("copy_slice", dw, g, abi.F32, dim, cc, cc, 0, 2 * cc, cc, 0)
-    f = conv2d(ctx, cat, wfold, m.down.bias, wgrad_sink=sink_down)
-
-    w7 = torch.empty(dim, dim, 7, 7, **ctx.f32)
-    call("kernel_embed", w7, _p(m.conv_7x7.weight), dim * dim, 7, 7, 0, 0)
-    call("kernel_embed", w7, _p(m.conv_5x5.weight), dim * dim, 7, 5, 0, 1)
-    call("kernel_embed", w7, _p(m.conv_3x3.weight), dim * dim, 7, 3, 0, 1)
-    b7 = torch.empty(dim, **ctx.f32)
-    call("copy_slice", _p(m.conv_7x7.bias), b7, abi.F32, 1, dim, dim, 0, dim, 0, 0)
-    call("copy_slice", _p(m.conv_5x5.bias), b7, abi.F32, 1, dim, dim, 0, dim, 0, 1)
-    call("copy_slice", _p(m.conv_3x3.bias), b7, abi.F32, 1, dim, dim, 0, dim, 0, 1)
-
-    def sink_w7(dw):
-        call("kernel_embed", dw, ctx.grad_slot(m.conv_7x7.weight), dim * dim, 7, 7, 1, 0)
-        call("kernel_embed", dw, ctx.grad_slot(m.conv_5x5.weight), dim * dim, 7, 5, 1, 0)
-        call("kernel_embed", dw, ctx.grad_slot(m.conv_3x3.weight), dim * dim, 7, 3, 1, 0)
+    spec_down = WSpec(1, (m.down.weight,), (m.down.bias,), (dim, cc, 1, 1))
+    spec_w7 = WSpec(2, (m.conv_7x7.weight, m.conv_5x5.weight, m.conv_3x3.weight), (m.conv_7x7.bias, m.conv_5x5.bias, m.conv_3x3.bias), (dim, dim, 7, 7))
+    planned = ctx.wplan is not None and ctx.wplan.ready and ctx.record and spec_down.key in ctx.wplan.jobs and spec_w7.key in ctx.wplan.jobs
 
     def sink_b7(gb):
         for b in (m.conv_7x7.bias, m.conv_5x5.bias, m.conv_3x3.bias):
             call("copy_slice", gb, ctx.grad_slot(b), abi.F32, 1, dim, dim, 0, dim, 0, 0)
-    s = conv2d(ctx, f, w7, b7, wgrad_sink=sink_w7, bgrad_sink=sink_b7)
+
+    if planned:      # folded / merged weights come packed out of egm_weight_prep_batch; gradients leave through egm_wgrad_unpack_batch
+        f = conv2d(ctx, cat, None, m.down.bias, wspec=spec_down)
+        s = conv2d(ctx, f, None, None, bgrad_sink=sink_b7, wspec=spec_w7)
+    else:
+        wfold = torch.empty(dim, cc, 1, 1, **ctx.f32)
+        call("copy_slice", wdown, wfold, abi.F32, dim, cc, 2 * cc, 0, cc, 0, 0)
+        call("copy_slice", wdown, wfold, abi.F32, dim, cc, 2 * cc, cc, cc, 0, 1)
+
+        def sink_down(dw):
+            g = ctx.grad_slot(m.down.weight)
+            call("copy_slice", dw, g, abi.F32, dim, cc, cc, 0, 2 * cc, 0, 0)
+            call("copy_slice", dw, g, abi.F32, dim, cc, cc, 0, 2 * cc, cc, 0)
+        f = conv2d(ctx, cat, wfold, m.down.bias, wgrad_sink=sink_down, wspec=spec_down)
+
+        w7 = torch.empty(dim, dim, 7, 7, **ctx.f32)
+        call("kernel_embed", w7, _p(m.conv_7x7.weight), dim * dim, 7, 7, 0, 0)
+        call("kernel_embed", w7, _p(m.conv_5x5.weight), dim * dim, 7, 5, 0, 1)
+        call("kernel_embed", w7, _p(m.conv_3x3.weight), dim * dim, 7, 3, 0, 1)
+        b7 = torch.empty(dim, **ctx.f32)
+        call("copy_slice", _p(m.conv_7x7.bias), b7, abi.F32, 1, dim, dim, 0, dim, 0, 0)
+        call("copy_slice", _p(m.conv_5x5.bias), b7, abi.F32, 1, dim, dim, 0, dim, 0, 1)
+        call("copy_slice", _p(m.conv_3x3.bias), b7, abi.F32, 1, dim, dim, 0, dim, 0, 1)
+
+        def sink_w7(dw):
+            call("kernel_embed", dw, ctx.grad_slot(m.conv_7x7.weight), dim * dim, 7, 7, 1, 0)
+            call("kernel_embed", dw, ctx.grad_slot(m.conv_5x5.weight), dim * dim, 7, 5, 1, 0)
+            call("kernel_embed", dw, ctx.grad_slot(m.conv_3x3.weight), dim * dim, 7, 3, 1, 0)
+        s = conv2d(ctx, f, w7, b7, wgrad_sink=sink_w7, bgrad_sink=sink_b7, wspec=spec_w7)
 
     # spatial attention on s (SpatialAttentionModule :1189-1200)
     mm = torch.empty(M * 2, **ctx.f32)

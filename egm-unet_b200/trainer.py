@@ -6,6 +6,7 @@ by the fused SGD kernel, and the loss stays on the device (no per-step `.item()`
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -13,7 +14,7 @@ import torch.distributed as dist
 
 from . import abi
 from .abi import call
-from .engine import Ctx, seed_grad_from_nchw
+from .engine import Ctx, WeightPlan, seed_grad_from_nchw
 from .graph import net_forward
 from .models import _store_for
 from .ddp import BucketReducer
@@ -42,6 +43,8 @@ class Trainer:
         self.num_buckets = num_buckets
         self.use_graph = use_graph
         self._graph = None            # CUDA graph of forward + loss + backward (+ SGD when single-rank)
+        self._wplan, self._wplan_key = None, None
+        self.batch_weights = os.environ.get("EGM_NO_WEIGHT_PLAN", "0") != "1"
         self._gkey = None
         self._calls = 0
         self.reducer = None
@@ -64,6 +67,21 @@ class Trainer:
         if not st.valid():
             st = self.store = _store_for(m)
         ctx = Ctx(m.compute_dtype, self.dev, True, True, st.grad_slot, use_tc=m.use_tensor_cores)
+        # batched weight preparation: registered during the first (eager) step, two launches per step afterwards.  The eager
+        # multi-rank path keeps per-conv gradient unpacking because its bucket all-reduces start as soon as a bucket is complete.
+        plan = None
+        if (self.reducer is None or self.use_graph) and self.batch_weights:
+            key = (id(st), m.compute_dtype, m.use_tensor_cores)
+            if self._wplan is None or self._wplan_key != key:
+                self._wplan, self._wplan_key = WeightPlan(), key
+            plan = self._wplan
+            if self.reducer is not None and plan.ready:
+                plan = None                          # eager multi-rank step after the plan was built: overlap wins
+            elif not plan.ready and torch.cuda.is_current_stream_capturing():
+                plan = None                          # never build a plan (allocations, H2D table copy) inside a capture
+            ctx.wplan = plan
+            if plan is not None and plan.ready:
+                plan.prep()
         logits, lv = net_forward(ctx, m, image, m.variant)
         n, c, h, w = logits.shape
         ws_bytes = abi.query("loss_workspace_bytes", n, c, h, w)
@@ -81,6 +99,11 @@ class Trainer:
             self.reducer.finish()
         else:
             ctx.backward()
+        if plan is not None:
+            if plan.ready:
+                plan.unpack()
+            else:
+                plan.finalize(self.dev)
         self.loss_terms = out
         return out[0]
 

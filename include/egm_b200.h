@@ -42,6 +42,14 @@ int egm_pack_conv_weight(const float* w, float* wf, float* wd, int Cout, int Cin
 int egm_unpack_conv_wgrad(const float* dw_packed, float* dw, int Cout, int Cin_g, int kh, int kw, float beta, void* stream);
 int egm_conv_weight_lift(float* w, float* wp, int Cout, int Cin_g, int groups, int taps, int CoutP, int CinP, int mode, void* stream);
 int egm_kernel_embed(float* big, float* small_, long long CoCi, int kb, int ks, int mode, int accumulate, void* stream);
+/* Batched form of the per-conv weight preparation / gradient extraction above (csrc/wbatch.cu): `jobs` is a DEVICE array of
+ * n_jobs 160-byte EgmWJob records (layout documented in csrc/wbatch.cu and mirrored by engine.WeightPlan); one launch packs
+ * every tcgen05 conv's bf16 forward/dgrad operands (+ padded / summed bias) from the fp32 master parameters of
+ * nn.Conv2d.weight (src/EGM-UNet.py DoubleConv :44-55, BasicConv :958-975, FusionConv :1202-1236), one launch scatters every
+ * packed fp32 weight gradient back into the parameters' .grad layout.  total_elems = sum over jobs of the element space. */
+int egm_wjob_bytes(void);
+int egm_weight_prep_batch(const void* jobs, int n_jobs, long long total_elems, void* stream);
+int egm_wgrad_unpack_batch(const void* jobs, int n_jobs, long long total_elems, void* stream);
 int egm_conv2d_direct(const void* x, long long x_cstride, long long x_coff, const float* w_packed, const float* bias, void* y,
                       long long y_cstride, long long y_coff, int accumulate, int dtype, int N, int H, int W, int Cin, int Cout,
                       int kh, int kw, int dil, int groups, void* stream);

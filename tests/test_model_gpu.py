@@ -237,6 +237,33 @@ def test_cuda_graph_step_equals_eager_step():
     assert worst < 6e-2, worst
 
 
+@pytest.mark.parametrize("variant", ["unet", "egm", "yuan"])
+def test_batched_weight_plan_equals_per_conv_kernels(variant):
+    """Step 1 packs weights / unpacks gradients conv by conv and registers the WeightPlan; step 2 on the SAME parameters and
+    inputs goes through egm_weight_prep_batch / egm_wgrad_unpack_batch.  Loss and every gradient must agree (fp32 atomics in
+    the split-K wgrad are the only non-determinism)."""
+    from egm_unet_b200.trainer import Trainer
+    model = build(variant)
+    model.load_state_dict(synth.fill_state_dict(model.state_dict()))
+    model = model.cuda().train()
+    tr = Trainer(model, use_graph=False)
+    image, target = synth.make_inputs(2, 64, 48, seed=91)
+    image, target = image.cuda(), target.cuda()
+    l0 = float(tr.forward_backward(image, target))
+    assert tr._wplan is not None and tr._wplan.ready and len(tr._wplan.jobs) > 10
+    g0 = tr.store.grads.clone()
+    tr.store.grads.zero_()
+    l1 = float(tr.forward_backward(image, target))
+    g1 = tr.store.grads
+    assert abs(l0 - l1) <= 1e-5 * abs(l0), (l0, l1)
+    for name, p in model.named_parameters():
+        a, b = tr.store.grad_slot(p), None
+        lo = a.data_ptr() - tr.store.grads.data_ptr()
+        b = g0.view(-1)[lo // 4: lo // 4 + a.numel()].view_as(a)
+        scale = float(b.abs().max())
+        assert float((a - b).abs().max()) <= 2e-3 * scale + 1e-7, (name, float((a - b).abs().max()), scale)
+
+
 def test_host_fed_pipelined_loop_equals_plain_steps():
     """Trainer.run (double-buffered H2D prefetch + lagged loss read-back) gives the same losses as plain step() calls."""
     from egm_unet_b200.trainer import Trainer
