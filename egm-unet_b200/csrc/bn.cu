@@ -11,6 +11,49 @@ struct BnArgs {
   int act, mode; float alpha;
 };
 
+// Finalize fused into the reduction kernels: the LAST block to add its partial sums (ticket counter behind the sums) turns them
+// into scale/shift/mean/rstd + running statistics (forward) or the backward coefficients + dgamma/dbeta (backward).  Saves one
+// dependent ~3 us launch per BN layer and pass (148 per train step).
+struct BnTail {
+  unsigned int* counter;                 // nullptr: no fused finalize
+  int backward;
+  double M;
+  const float* gamma; const float* beta; float* rmean; float* rvar; long long* nbt; float momentum, eps;
+  float* scale; float* shift; float* mean; float* rstd;      // forward outputs (backward: rstd is an input)
+  float* coef; float* dgamma; float* dbeta;                  // backward outputs
+};
+__device__ __forceinline__ void bn_tail_run(const BnTail& tl, const double* sums, int C, int tid, int nthr, bool named) {
+  if (!tl.counter) return;
+  __shared__ int s_last;
+  __threadfence();                                           // my atomics are visible device-wide before the ticket is taken
+  if (named) asm volatile("bar.sync 1, %0;" ::"r"(nthr)); else __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(tl.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+  if (named) asm volatile("bar.sync 1, %0;" ::"r"(nthr)); else __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (!tl.backward && tid == 0 && tl.nbt) *tl.nbt += 1;
+  for (int c = tid; c < C; c += nthr) {
+    const double s0 = __ldcg(sums + c), s1 = __ldcg(sums + C + c);
+    if (!tl.backward) {                                      // == k_bn_finalize, training branch
+      const double mean = s0 / tl.M; double var = s1 / tl.M - mean * mean; if (var < 0) var = 0;
+      if (tl.rmean) {
+        const double unb = tl.M > 1 ? var * tl.M / (tl.M - 1) : var;
+        tl.rmean[c] = (float)((1.0 - tl.momentum) * tl.rmean[c] + tl.momentum * mean);
+        tl.rvar[c] = (float)((1.0 - tl.momentum) * tl.rvar[c] + tl.momentum * unb);
+      }
+      const double rstd = 1.0 / sqrt(var + (double)tl.eps);
+      tl.scale[c] = (float)(tl.gamma[c] * rstd); tl.shift[c] = (float)(tl.beta[c] - mean * tl.gamma[c] * rstd);
+      tl.mean[c] = (float)mean; tl.rstd[c] = (float)rstd;
+    } else {                                                 // == k_bn_bwd_finalize, training branch
+      tl.coef[c] = tl.gamma[c] * tl.rstd[c];
+      tl.coef[C + c] = (float)(s0 / tl.M);
+      tl.coef[2 * C + c] = (float)(s1 / tl.M);
+      if (tl.dgamma) tl.dgamma[c] = (float)s1;
+      if (tl.dbeta) tl.dbeta[c] = (float)s0;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- per-channel reduction skeleton
 // blockDim.x = CV * rpi (CV = C/V channel vectors, rpi rows per iteration). Each thread owns one
 // channel vector; partials are combined through shared memory, then one fp64 atomic per channel.
@@ -63,23 +106,37 @@ struct StatsF {
   }
 };
 template <typename T, int V>
-__global__ void k_bn_stats(StatsF<T, V> f, long long M, int C, double* out) {
+__global__ void k_bn_stats(StatsF<T, V> f, long long M, int C, double* out, BnTail tl) {
   extern __shared__ float smem[];
   chan_reduce<V, 2>(f, M, C, out, smem);
+  bn_tail_run(tl, out, C, threadIdx.x, blockDim.x, false);
 }
-static bool bn_stats_stream_launch(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, cudaStream_t st);
+static bool bn_stats_stream_launch(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, const BnTail& tl, cudaStream_t st);
 static bool bn_fwd_stream_launch(const void* z, long long zcs, long long zco, const BnArgs& a, void* y, long long ycs, long long yco, int dtype, long long M, int C, cudaStream_t st);
-extern "C" int egm_bn_stats(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, void* stream) {
+static int bn_stats_impl(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, BnTail tl, cudaStream_t st) {
   EGM_REQUIRE(C >= 1 && C <= 2048, EGM_E_SHAPE, "bn_stats: C=%d unsupported", C);
-  cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+  cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C + (tl.counter ? 1 : 0)), st);
   if (M == 0) return EGM_OK;
-  if (bn_stats_stream_launch(x, dtype, M, C, cstride, coff, sums, st)) { EGM_LAUNCH_CHECK("bn_stats(stream)"); return EGM_OK; }
+  if (bn_stats_stream_launch(x, dtype, M, C, cstride, coff, sums, tl, st)) { EGM_LAUNCH_CHECK("bn_stats(stream)"); return EGM_OK; }
   int v = egm_pick_vec(C, cstride, coff);
   int threads = reduce_threads(C, v); size_t sm = (size_t)(threads / (C / v)) * 2 * C * sizeof(float);
   EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_stats<T, V><<<reduce_blocks(M, threads, C, v), threads, sm, st>>>(
-      StatsF<T, V>{(const T*)x, cstride, coff}, M, C, sums))));
+      StatsF<T, V>{(const T*)x, cstride, coff}, M, C, sums, tl))));
   EGM_LAUNCH_CHECK("bn_stats"); return EGM_OK;
+}
+extern "C" int egm_bn_stats(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, void* stream) {
+  return bn_stats_impl(x, dtype, M, C, cstride, coff, sums, BnTail{}, (cudaStream_t)stream);
+}
+// training-mode statistics + finalize in one launch; `sums` holds 2*C + 1 doubles (the last one is the block ticket counter)
+extern "C" int egm_bn_stats_finalize(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, const float* gamma,
+                                     const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                                     float eps, float* scale, float* shift, float* mean, float* rstd, void* stream) {
+  EGM_REQUIRE(M > 0, EGM_E_SHAPE, "bn_stats_finalize: empty batch");
+  BnTail tl{};
+  tl.counter = (unsigned int*)(sums + 2 * C); tl.backward = 0; tl.M = (double)M;
+  tl.gamma = gamma; tl.beta = beta; tl.rmean = running_mean; tl.rvar = running_var; tl.nbt = num_batches_tracked; tl.momentum = momentum; tl.eps = eps;
+  tl.scale = scale; tl.shift = shift; tl.mean = mean; tl.rstd = rstd;
+  return bn_stats_impl(x, dtype, M, C, cstride, coff, sums, tl, (cudaStream_t)stream);
 }
 
 // sums [2][C] -> scale/shift/mean/rstd (+ running-stat update).  training=0: use the running stats.
@@ -185,15 +242,15 @@ struct BwdRedF {
   }
 };
 template <typename T, int V>
-__global__ void k_bn_bwd_reduce(BwdRedF<T, V> f, long long M, int C, double* out) {
+__global__ void k_bn_bwd_reduce(BwdRedF<T, V> f, long long M, int C, double* out, BnTail tl) {
   extern __shared__ float smem[];
   chan_reduce<V, 2>(f, M, C, out, smem);
+  bn_tail_run(tl, out, C, threadIdx.x, blockDim.x, false);
 }
-extern "C" int egm_bn_act_bwd_reduce(const void* dy, long long dy_cstride, long long dy_coff, const void* z, const float* scale, const float* shift,
-                                     const float* mean, const float* rstd, int act, int mode, const void* aux, float alpha, int dtype, long long M, int C,
-                                     double* sums, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+static int bn_bwd_reduce_impl(const void* dy, long long dy_cstride, long long dy_coff, const void* z, const float* scale, const float* shift,
+                              const float* mean, const float* rstd, int act, int mode, const void* aux, float alpha, int dtype, long long M, int C,
+                              double* sums, BnTail tl, cudaStream_t st) {
+  cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C + (tl.counter ? 1 : 0)), st);
   if (M == 0) return EGM_OK;
   BnArgs a{scale, shift, mean, rstd, nullptr, act, mode, alpha};
   if (bn_stream_eligible(mode, M, C, dy_cstride, dy_coff)) {
@@ -201,15 +258,31 @@ extern "C" int egm_bn_act_bwd_reduce(const void* dy, long long dy_cstride, long 
     EGM_DISPATCH_DTYPE(dtype, {
       static bool attr = false;
       if (!attr) { cudaFuncSetAttribute(k_bn_bwd_reduce_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
-      k_bn_bwd_reduce_stream<T><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st>>>((const T*)dy, (const T*)z, a, M * C, C, sums);
+      k_bn_bwd_reduce_stream<T><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st>>>((const T*)dy, (const T*)z, a, M * C, C, sums, tl);
     });
     EGM_LAUNCH_CHECK("bn_act_bwd_reduce(stream)"); return EGM_OK;
   }
   int v = egm_pick_vec(C, dy_cstride, dy_coff); if (v > 4) v = 4;      // 4-wide: fewer live registers -> more warps in flight
   int threads = reduce_threads(C, v); size_t sm = (size_t)(threads / (C / v)) * 2 * C * sizeof(float);
   EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_bwd_reduce<T, V><<<reduce_blocks(M, threads, C, v), threads, sm, st>>>(
-      BwdRedF<T, V>{(const T*)dy, dy_cstride, dy_coff, (const T*)z, (const T*)aux, a, C, {}, {}, {}, {}}, M, C, sums))));
+      BwdRedF<T, V>{(const T*)dy, dy_cstride, dy_coff, (const T*)z, (const T*)aux, a, C, {}, {}, {}, {}}, M, C, sums, tl))));
   EGM_LAUNCH_CHECK("bn_act_bwd_reduce"); return EGM_OK;
+}
+extern "C" int egm_bn_act_bwd_reduce(const void* dy, long long dy_cstride, long long dy_coff, const void* z, const float* scale, const float* shift,
+                                     const float* mean, const float* rstd, int act, int mode, const void* aux, float alpha, int dtype, long long M, int C,
+                                     double* sums, void* stream) {
+  return bn_bwd_reduce_impl(dy, dy_cstride, dy_coff, z, scale, shift, mean, rstd, act, mode, aux, alpha, dtype, M, C, sums, BnTail{}, (cudaStream_t)stream);
+}
+// training-mode backward reduction + finalize (coef[3][C], dgamma, dbeta) in one launch; `sums` holds 2*C + 1 doubles
+extern "C" int egm_bn_act_bwd_reduce_finalize(const void* dy, long long dy_cstride, long long dy_coff, const void* z, const float* scale, const float* shift,
+                                              const float* mean, const float* rstd, int act, int mode, const void* aux, float alpha, int dtype,
+                                              long long M, int C, double* sums, const float* gamma, float* coef, float* dgamma, float* dbeta,
+                                              void* stream) {
+  EGM_REQUIRE(M > 0, EGM_E_SHAPE, "bn_act_bwd_reduce_finalize: empty batch");
+  BnTail tl{};
+  tl.counter = (unsigned int*)(sums + 2 * C); tl.backward = 1; tl.M = (double)M;
+  tl.gamma = gamma; tl.rstd = const_cast<float*>(rstd); tl.coef = coef; tl.dgamma = dgamma; tl.dbeta = dbeta;
+  return bn_bwd_reduce_impl(dy, dy_cstride, dy_coff, z, scale, shift, mean, rstd, act, mode, aux, alpha, dtype, M, C, sums, tl, (cudaStream_t)stream);
 }
 
 // sums -> coef[0][c] = gamma*rstd, coef[1][c] = sum(g)/M, coef[2][c] = sum(g*xhat)/M ; dgamma, dbeta
@@ -305,15 +378,15 @@ extern "C" int egm_channel_sum(const void* x, int dtype, long long M, int C, lon
 }
 
 // ---------------------------------------------------------------- streaming launches declared above
-static bool bn_stats_stream_launch(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, cudaStream_t st) {
+static bool bn_stats_stream_launch(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, const BnTail& tl, cudaStream_t st) {
   if (!bn_stream_eligible(0, M, C, cstride, coff) || (dtype != EGM_F32 && dtype != EGM_BF16)) return false;
   const size_t smb = bs::ring_bytes<1>(2 * bs::CONSUMERS * bs::V * sizeof(float));
   if (dtype == EGM_F32) {
     static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_bn_stats_stream<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
-    k_bn_stats_stream<float><<<bn_stream_grid(M * C, 4), bs::THREADS, smb, st>>>((const float*)x, M * C, C, sums);
+    k_bn_stats_stream<float><<<bn_stream_grid(M * C, 4), bs::THREADS, smb, st>>>((const float*)x, M * C, C, sums, tl);
   } else {
     static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_bn_stats_stream<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
-    k_bn_stats_stream<__nv_bfloat16><<<bn_stream_grid(M * C, 2), bs::THREADS, smb, st>>>((const __nv_bfloat16*)x, M * C, C, sums);
+    k_bn_stats_stream<__nv_bfloat16><<<bn_stream_grid(M * C, 2), bs::THREADS, smb, st>>>((const __nv_bfloat16*)x, M * C, C, sums, tl);
   }
   return true;
 }

@@ -67,7 +67,7 @@ __device__ __forceinline__ void produce(const Ring& r, const T* const* src, long
 // ------------------------------------------------------------------ sum(g), sum(g*xhat) per channel   (mode 0 only)
 template <typename T>
 __global__ void __launch_bounds__(bs::THREADS, 1) k_bn_bwd_reduce_stream(const T* __restrict__ dy, const T* __restrict__ z, BnArgs a, long long total, int C,
-                                                                        double* __restrict__ out) {
+                                                                        double* __restrict__ out, BnTail tl) {
   using namespace bs;
   extern __shared__ uint8_t smem_raw[];
   float* red;
@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(bs::THREADS, 1) k_bn_bwd_reduce_stream(const T
     for (int tt = cc / V; tt < CONSUMERS; tt += CV) sum += red[k * CONSUMERS * V + tt * V + (cc % V)];
     atomicAdd(out + i, (double)sum);
   }
+  bn_tail_run(tl, out, C, t, CONSUMERS, true);
 }
 
 // ------------------------------------------------------------------ dz = k0 * (g - k1 - xhat*k2)   (mode 0 only)
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(bs::THREADS, 1) k_bn_bwd_apply_stream(const T*
 
 // ------------------------------------------------------------------ forward statistics sum(x), sum(x^2) per channel
 template <typename T>
-__global__ void __launch_bounds__(bs::THREADS, 1) k_bn_stats_stream(const T* __restrict__ x, long long total, int C, double* __restrict__ out) {
+__global__ void __launch_bounds__(bs::THREADS, 1) k_bn_stats_stream(const T* __restrict__ x, long long total, int C, double* __restrict__ out, BnTail tl) {
   using namespace bs;
   extern __shared__ uint8_t smem_raw[];
   float* red;
@@ -191,6 +192,7 @@ __global__ void __launch_bounds__(bs::THREADS, 1) k_bn_stats_stream(const T* __r
     for (int tt = cc / V; tt < CONSUMERS; tt += CV) sum += red[k * CONSUMERS * V + tt * V + (cc % V)];
     atomicAdd(out + i, (double)sum);
   }
+  bn_tail_run(tl, out, C, t, CONSUMERS, true);
 }
 
 // ------------------------------------------------------------------ y = act(z*scale + shift)   (mode 0, dense in and out)

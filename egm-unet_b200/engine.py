@@ -8,6 +8,7 @@ straight into the fp32 gradient slots handed out by `Ctx.grad_slot`.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -440,12 +441,16 @@ def bn_act(ctx: Ctx, z: Var, bn: nn.BatchNorm2d, act: int, mode: int = MODE_PLAI
     gamma, beta = _p(bn.weight), _p(bn.bias)
     scale, shift, mean, rstd = (torch.empty(c, **ctx.f32) for _ in range(4))
     training = ctx.training or bn.running_mean is None
-    sums = ctx.f64(2 * c)
-    if training:
-        call("bn_stats", z.t, ctx.code, M, c, c, 0, sums)
     mom = 0.1 if bn.momentum is None else bn.momentum
-    call("bn_finalize", sums, M, gamma, beta, bn.running_mean, bn.running_var, bn.num_batches_tracked if training else None,
-         float(mom), float(bn.eps), int(training), c, scale, shift, mean, rstd)
+    if training and M > 0:      # statistics + finalize (scale/shift/mean/rstd, running stats) in one launch
+        call("bn_stats_finalize", z.t, ctx.code, M, c, c, 0, ctx.f64(2 * c + 1), gamma, beta, bn.running_mean, bn.running_var,
+             bn.num_batches_tracked, float(mom), float(bn.eps), scale, shift, mean, rstd)
+    else:
+        sums = ctx.f64(2 * c)
+        if training:
+            call("bn_stats", z.t, ctx.code, M, c, c, 0, sums)
+        call("bn_finalize", sums, M, gamma, beta, bn.running_mean, bn.running_var, bn.num_batches_tracked if training else None,
+             float(mom), float(bn.eps), int(training), c, scale, shift, mean, rstd)
     if out is None:
         y = Var(ctx.empty(n, h, w, c))
         ycs, yco = c, 0
@@ -459,11 +464,15 @@ def bn_act(ctx: Ctx, z: Var, bn: nn.BatchNorm2d, act: int, mode: int = MODE_PLAI
                 return
             if out is None:
                 y.grad = None
-            s2 = ctx.f64(2 * c)
             auxt = aux.t if aux is not None else None
-            call("bn_act_bwd_reduce", dy, ycs, yco, z.t, scale, shift, mean, rstd, act, mode, auxt, float(alpha), ctx.code, M, c, s2)
             coef = torch.empty(3 * c, **ctx.f32)
-            call("bn_bwd_finalize", s2, M, gamma, rstd, c, coef, ctx.grad_slot(bn.weight), ctx.grad_slot(bn.bias), int(training))
+            if training and M > 0:
+                call("bn_act_bwd_reduce_finalize", dy, ycs, yco, z.t, scale, shift, mean, rstd, act, mode, auxt, float(alpha), ctx.code, M, c,
+                     ctx.f64(2 * c + 1), gamma, coef, ctx.grad_slot(bn.weight), ctx.grad_slot(bn.bias))
+            else:
+                s2 = ctx.f64(2 * c)
+                call("bn_act_bwd_reduce", dy, ycs, yco, z.t, scale, shift, mean, rstd, act, mode, auxt, float(alpha), ctx.code, M, c, s2)
+                call("bn_bwd_finalize", s2, M, gamma, rstd, c, coef, ctx.grad_slot(bn.weight), ctx.grad_slot(bn.bias), int(training))
             dz, _ = z.grad_target()
             daux, dacc = (None, 0)
             if aux is not None and aux.needs_grad:

@@ -68,6 +68,16 @@ int egm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_packed, int N, 
 
 /* ---- BatchNorm2d (+ReLU / sigmoid gate / residual) (nn.BatchNorm2d: src/EGM-UNet.py:50,53,879,966; ATen native_batch_norm today) ---- */
 int egm_bn_stats(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, void* stream);
+/* bn_stats + bn_finalize (training) in one launch: the last block to finish turns the sums into scale/shift/mean/rstd and
+ * updates the running statistics.  `sums` must hold 2*C + 1 doubles (sums, sums of squares, block ticket counter). */
+int egm_bn_stats_finalize(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, const float* gamma,
+                          const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                          float eps, float* scale, float* shift, float* mean, float* rstd, void* stream);
+/* bn_act_bwd_reduce + bn_bwd_finalize (training) in one launch; `sums` holds 2*C + 1 doubles. */
+int egm_bn_act_bwd_reduce_finalize(const void* dy, long long dy_cstride, long long dy_coff, const void* z, const float* scale, const float* shift,
+                                   const float* mean, const float* rstd, int act, int mode, const void* aux, float alpha, int dtype,
+                                   long long M, int C, double* sums, const float* gamma, float* coef, float* dgamma, float* dbeta,
+                                   void* stream);
 int egm_bn_finalize(const double* sums, long long M, const float* gamma, const float* beta, float* running_mean, float* running_var,
                     long long* num_batches_tracked, float momentum, float eps, int training, int C,
                     float* scale, float* shift, float* mean, float* rstd, void* stream);
