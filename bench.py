@@ -202,9 +202,9 @@ def main():
     def is_doubleconv(key):
         """DoubleConv 3x3 launches (fwd / dgrad / wgrad): k=3, dilation 1, >= 32 channels on both sides (in_conv.0 runs as 16->32)."""
         name, _, shape = key.partition(":")
-        if name not in ("conv2d_tc", "conv2d_wgrad_tc") or not shape:
+        if name not in ("conv2d_tc", "conv2d_wgrad_tc", "conv2d_tc_view", "conv2d_wgrad_tc_view") or not shape:
             return False
-        n_, h_, w_, ci, co, kh, kw, dil = [int(v) for v in shape.split(",")][:8]
+        n_, h_, w_, ci, co, kh, kw, dil = [int(v) for v in shape.split(",")][-8:]     # the view forms put their stride/offset ints first
         return kh == 3 and dil == 1 and ((min(ci, co) >= 32) or (h_ == H and {ci, co} == {16, 32}))
 
     step_sum = sum(v["ms"] for v in prof.values())
@@ -224,7 +224,7 @@ def main():
         best = 0.0
         for k, v in prof.items():
             if is_doubleconv(k):
-                n_, h_, w_, ci, co = [int(x) for x in k.split(":")[1].split(",")][:5]
+                n_, h_, w_, ci, co = [int(x) for x in k.split(":")[1].split(",")][-8:-3]
                 best = max(best, 2.0 * n_ * h_ * w_ * ci * co * 9 * v["calls"] / (v["ms"] * 1e-3) / 1e12)
         roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
                 "kernel": "tcgen05 implicit-GEMM convs of the 18 DoubleConv layers (k_conv_tc / k_conv_tc_halo fwd+dgrad, k_wgrad_tc_halo)",

@@ -90,6 +90,38 @@ __device__ __forceinline__ void store16(__nv_bfloat16* yp, const uint32_t* v, co
   *reinterpret_cast<uint4*>(yp) = o[0];
   *reinterpret_cast<uint4*>(yp + 8) = o[1];
 }
+// Output side of a conv: row pointer = y + pixel*cs + coff; only channels < valid are written; acc: y += result.
+struct OutView { long long cs, coff; int valid, acc, vec, dense; };  // vec: every row start is 16-byte aligned; dense: all padded channels exist, plain overwrite
+// 16 accumulator columns starting at channel c of the row `yp` (already offset by c): fast path = two 16-byte stores
+__device__ __forceinline__ void store16v(__nv_bfloat16* yp, const uint32_t* v, const float* bp, int nvalid, const OutView& o) {
+  if (nvalid >= 16 && o.vec && !o.acc) { store16(yp, v, bp); return; }
+  if (nvalid <= 0) return;
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[hf * 8 + j]) + (bp ? bp[hf * 8 + j] : 0.f);
+    if (nvalid >= hf * 8 + 8 && o.vec) {
+      uint4 q; __nv_bfloat162* qb = reinterpret_cast<__nv_bfloat162*>(&q);
+      if (o.acc) {
+        q = *reinterpret_cast<const uint4*>(yp + hf * 8);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float2 old = __bfloat1622float2(qb[j]); f[2 * j] += old.x; f[2 * j + 1] += old.y; }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) qb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+      *reinterpret_cast<uint4*>(yp + hf * 8) = q;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (hf * 8 + j < nvalid) {
+          float t = f[j];
+          if (o.acc) t += __bfloat162float(yp[hf * 8 + j]);
+          yp[hf * 8 + j] = __float2bfloat16_rn(t);
+        }
+    }
+  }
+}
 // one elected lane of a converged warp (keeps the surrounding control flow warp-uniform, so loop state lives in uniform registers)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -124,12 +156,21 @@ static PFN_encodeTiled get_encode() {
 static CUtensorMapSwizzle swz_enum(int row_bytes) {
   return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
-// NHWC bf16 tensor [N,H,W,C] -> 4-D map (C, W, H, N), box (bc, bw, bh, 1)
-static int make_map_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, int C, int bc, int bw, int bh) {
+// Channel-strided view of an NHWC bf16 tensor: channel c (< valid) of pixel p lives at ptr[p*cs + coff + c].  A conv reads such
+// a view directly: the TMA box may be wider than `valid` (out-of-bounds channels are zero-filled), which is how thin and
+// channel-sliced inputs are padded to the 16-channel MMA granularity without a staging copy.
+struct NhwcView { const void* ptr; long long cs, coff; int valid; };
+static inline NhwcView dense_view(const void* ptr, int C) { return NhwcView{ptr, C, 0, C}; }
+static inline bool view_tma_ok(const NhwcView& v) { return v.cs % 8 == 0 && v.coff % 8 == 0 && (((uintptr_t)v.ptr) & 15) == 0; }
+// view [N,H,W,valid] -> 4-D map (C, W, H, N), box (bc, bw, bh, 1)
+static int make_map_nhwc(CUtensorMap* tm, const NhwcView& v, int N, int H, int W, int bc, int bw, int bh) {
   PFN_encodeTiled enc = get_encode();
   EGM_REQUIRE(enc, EGM_E_ARCH, "cuTensorMapEncodeTiled unavailable");
+  EGM_REQUIRE(view_tma_ok(v), EGM_E_ALIGN, "tcgen05 conv: a TMA operand needs a 16-byte aligned base and channel stride/offset that are multiples of 8");
+  const void* ptr = (const __nv_bfloat16*)v.ptr + v.coff;
+  const int C = v.valid;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+  cuuint64_t strides[3] = {(cuuint64_t)v.cs * 2, (cuuint64_t)v.cs * 2 * W, (cuuint64_t)v.cs * 2 * W * H};
   cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -161,6 +202,7 @@ struct ConvTcParams {
   int stages, aBytes, bStride, tmemCols, accCols;
   int nChunk, coChunks;                               // Cout is processed in coChunks slices of nChunk (<= 256) channels
   int wres;                                           // 1: the whole packed weight tensor stays resident in smem (single Cout slice)
+  OutView out;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
@@ -270,24 +312,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       const int n = sp_t / tilesPerImg, r = sp_t - n * tilesPerImg;
       const int h = (r / p.tilesW) * TILE_H + row / TILE_W, w = (r % p.tilesW) * TILE_W + row % TILE_W;
       const bool valid = h < p.H && w < p.W;
-      __nv_bfloat16* yp = y + (((long long)n * p.H + h) * p.W + w) * p.Cout + chunk * p.nChunk;
+      __nv_bfloat16* yp = y + (((long long)n * p.H + h) * p.W + w) * p.out.cs + p.out.coff + chunk * p.nChunk;
       const float* bp = bias ? bias + chunk * p.nChunk : nullptr;
+      const int nv = p.out.valid - chunk * p.nChunk;                 // channels of this slice that exist in y
+      const int cend = nv < p.nChunk ? nv : p.nChunk;
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.accCols);
-      if ((p.nChunk & 31) == 0) {
+      if (p.out.dense && (p.nChunk & 31) == 0) {                      // hot path of the DoubleConv layers: no per-store decisions
         for (int c = 0; c < p.nChunk; c += 32) {
           uint32_t v[32];
           tmem_ld32(t0 + c, v);
           tmem_ld_wait();
           if (valid) { store16(yp + c, v, bp ? bp + c : nullptr); store16(yp + c + 16, v + 16, bp ? bp + c + 16 : nullptr); }
         }
-      } else {
+      } else if (p.out.dense) {
         for (int c = 0; c < p.nChunk; c += 16) {
           uint32_t v[16];
           tmem_ld16(t0 + c, v);
           tmem_ld_wait();
           if (valid) store16(yp + c, v, bp ? bp + c : nullptr);
+        }
+      } else {
+        for (int c = 0; c < cend; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(t0 + c, v);
+          tmem_ld_wait();
+          if (valid) store16v(yp + c, v, bp ? bp + c : nullptr, nv - c, p.out);
         }
       }
       tc_fence_before();
@@ -320,6 +371,7 @@ struct ConvHaloParams {
   int ksteps;                                        // MMAs (K=16) per tap = ceil(Cin/16); rowB may be wider than Cin*2 (zero-filled)
   int exp;                                           // EGM_EXP diagnostic bit mask (timing ablations; results are wrong):
                                                      // 1 = no global stores, 4 = no MMAs, 8 = no TMA loads
+  OutView out;
 };
 constexpr int HT_H = 16, HT_W = 8;
 
@@ -423,23 +475,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
       int n = tile / (p.tilesH * p.tilesW); int r = tile - n * p.tilesH * p.tilesW;
       int h = (r / p.tilesW) * HT_H + row / HT_W, w = (r % p.tilesW) * HT_W + row % HT_W;
       const bool valid = h < p.H && w < p.W;
-      __nv_bfloat16* yp = y + (((long long)n * p.H + h) * p.W + w) * p.Cout;
+      __nv_bfloat16* yp = y + (((long long)n * p.H + h) * p.W + w) * p.out.cs + p.out.coff;
+      const int nv = p.out.valid, cend = nv < p.Cout ? nv : p.Cout;
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.accCols);
-      if ((p.Cout & 31) == 0) {
+      if (p.out.dense && (p.Cout & 31) == 0) {
         for (int c = 0; c < p.Cout; c += 32) {
           uint32_t v[32];
           tmem_ld32(t0 + c, v);
           tmem_ld_wait();
           if (valid && !(p.exp & 1)) { store16(yp + c, v, bias ? bias + c : nullptr); store16(yp + c + 16, v + 16, bias ? bias + c + 16 : nullptr); }
         }
-      } else {
+      } else if (p.out.dense) {
         for (int c = 0; c < p.Cout; c += 16) {
           uint32_t v[16];
           tmem_ld16(t0 + c, v);
           tmem_ld_wait();
           if (valid) store16(yp + c, v, bias ? bias + c : nullptr);
+        }
+      } else {
+        for (int c = 0; c < cend; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(t0 + c, v);
+          tmem_ld_wait();
+          if (valid) store16v(yp + c, v, bias ? bias + c : nullptr, nv - c, p.out);
         }
       }
       tc_fence_before();
@@ -462,8 +522,8 @@ static bool halo_eligible(int Cin, int Cout, int kh, int dil) {
   long long wbytes = (long long)kh * kh * ((Cout * Cin * 2 + 1023) / 1024 * 1024);
   return wbytes <= 100 * 1024;
 }
-static int launch_conv_halo(const void* x, const void* wpk, const float* bias, void* y, int N, int H, int W, int Cin, int Cout, int kh, int kw, int dil,
-                            cudaStream_t st) {
+static int launch_conv_halo(const NhwcView& xv, const void* wpk, const float* bias, void* y, const OutView& ov, int N, int H, int W, int Cin, int Cout, int kh,
+                            int kw, int dil, cudaStream_t st) {
   ConvHaloParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
   p.tilesH = cdiv(H, HT_H); p.tilesW = cdiv(W, HT_W); p.numTiles = N * p.tilesH * p.tilesW;
@@ -478,7 +538,8 @@ static int launch_conv_halo(const void* x, const void* wpk, const float* bias, v
   { const char* ev = getenv("EGM_EXP"); p.exp = ev ? atoi(ev) : 0; }
   p.tmemCols = pow2_cols(p.nacc * p.accCols);
   CUtensorMap tmX, tmW;
-  int e = make_map_nhwc(&tmX, x, N, H, W, Cin, p.rowB / 2, p.haloW, p.haloH); if (e) return e;
+  p.out = ov;
+  int e = make_map_nhwc(&tmX, xv, N, H, W, p.rowB / 2, p.haloW, p.haloH); if (e) return e;
   e = make_map_w(&tmW, wpk, kh * kw, Cout, Cin, p.rowB / 2, Cout); if (e) return e;
   size_t smem = wres + (size_t)p.stages * p.haloStride + 1024 + 1408;
   static bool attr_set = false;
@@ -497,12 +558,20 @@ extern "C" int egm_conv2d_tc_supported(int Cin, int Cout, int kh, int kw, int di
 }
 extern "C" long long egm_conv2d_tc_workspace_bytes(int, int, int, int, int, int, int) { return 0; }
 
-extern "C" int egm_conv2d_tc(const void* x, const void* w_packed_bf16, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
-                             int kh, int kw, int dil, void* stream) {
+// General form: x and y are channel-strided views (egm_copy_slice semantics).  Cin / Cout are the PADDED channel counts of the
+// packed weight [taps][Cout][Cin] (multiples of 16); channels >= cin_valid read as zero (TMA out-of-bounds fill) and channels
+// >= cout_valid are not written.  accumulate != 0: y += conv (dgrad into a gradient that already holds other contributions).
+extern "C" int egm_conv2d_tc_view(const void* x, long long x_cstride, long long x_coff, int cin_valid, const void* w_packed_bf16, const float* bias,
+                                  void* y, long long y_cstride, long long y_coff, int cout_valid, int accumulate, int N, int H, int W, int Cin,
+                                  int Cout, int kh, int kw, int dil, void* stream) {
   EGM_REQUIRE(egm_conv2d_tc_supported(Cin, Cout, kh, kw, dil, 1), EGM_E_SHAPE, "conv2d_tc: unsupported shape %d->%d k%d", Cin, Cout, kh);
-  EGM_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)w_packed_bf16 & 15) == 0, EGM_E_ALIGN, "conv2d_tc: pointers must be 16-byte aligned");
+  EGM_REQUIRE(cin_valid >= 1 && cin_valid <= Cin && cout_valid >= 1 && cout_valid <= Cout, EGM_E_SHAPE, "conv2d_tc: valid channels out of range");
+  EGM_REQUIRE(((uintptr_t)w_packed_bf16 & 15) == 0, EGM_E_ALIGN, "conv2d_tc: weights must be 16-byte aligned");
   if ((long long)N * H * W == 0) return EGM_OK;
-  if (halo_eligible(Cin, Cout, kh, dil)) return launch_conv_halo(x, w_packed_bf16, bias, y, N, H, W, Cin, Cout, kh, kw, dil, (cudaStream_t)stream);
+  const NhwcView xv{x, x_cstride, x_coff, cin_valid};
+  OutView ov{y_cstride, y_coff, cout_valid, accumulate ? 1 : 0, (y_cstride % 8 == 0 && y_coff % 8 == 0 && ((uintptr_t)y & 15) == 0) ? 1 : 0, 0};
+  ov.dense = (ov.vec && !ov.acc && cout_valid == Cout) ? 1 : 0;
+  if (halo_eligible(Cin, Cout, kh, dil)) return launch_conv_halo(xv, w_packed_bf16, bias, y, ov, N, H, W, Cin, Cout, kh, kw, dil, (cudaStream_t)stream);
   ConvTcParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
   p.coChunks = (Cout + 255) / 256; p.nChunk = Cout / p.coChunks;
@@ -516,7 +585,8 @@ extern "C" int egm_conv2d_tc(const void* x, const void* w_packed_bf16, const flo
   p.stages = (int)((198 * 1024 - (p.wres ? wresBytes : 0)) / per); if (p.stages > 8) p.stages = 8; if (p.stages < 2) p.stages = 2;
   p.accCols = (p.nChunk + 31) / 32 * 32; p.tmemCols = pow2_cols(2 * p.accCols);
   CUtensorMap tmX, tmW;
-  int e = make_map_nhwc(&tmX, x, N, H, W, Cin, p.bkc, TILE_W, TILE_H); if (e) return e;
+  p.out = ov;
+  int e = make_map_nhwc(&tmX, xv, N, H, W, p.bkc, TILE_W, TILE_H); if (e) return e;
   e = make_map_w(&tmW, w_packed_bf16, kh * kw, Cout, Cin, p.bkc, p.nChunk); if (e) return e;
   size_t smem = (size_t)p.stages * per + (p.wres ? (size_t)wresBytes : 0) + 1024 + 1024;
   static bool attr_set = false;
@@ -524,6 +594,10 @@ extern "C" int egm_conv2d_tc(const void* x, const void* w_packed_bf16, const flo
   int grid = p.numTiles < egm_num_sms() ? p.numTiles : egm_num_sms();
   k_conv_tc<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmX, tmW, (__nv_bfloat16*)y, bias, p);
   EGM_LAUNCH_CHECK("conv2d_tc"); return EGM_OK;
+}
+extern "C" int egm_conv2d_tc(const void* x, const void* w_packed_bf16, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
+                             int kh, int kw, int dil, void* stream) {
+  return egm_conv2d_tc_view(x, Cin, 0, Cin, w_packed_bf16, bias, y, Cout, 0, Cout, 0, N, H, W, Cin, Cout, kh, kw, dil, stream);
 }
 
 // weights fp32 [Cout][Cin][kh][kw] -> bf16 wf [taps][Cout][Cin] (forward) and wd [taps_flipped][Cin][Cout] (dgrad: roles swapped)
@@ -794,7 +868,7 @@ static bool wgrad_halo_eligible(int Cin, int Cout, int kh, int kw, int dil) {
   int nch = pick_bkc(Cin);
   return kw * nch <= 256;
 }
-static int launch_wgrad_halo(const void* x, const void* dy, float* dwp, int N, int H, int W, int Cin, int Cout, int kh, int kw, int dil, cudaStream_t st) {
+static int launch_wgrad_halo(const NhwcView& xv, const NhwcView& dyv, float* dwp, int N, int H, int W, int Cin, int Cout, int kh, int kw, int dil, cudaStream_t st) {
   WgradHaloParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
   p.tilesH = cdiv(H, HT_H); p.tilesW = cdiv(W, HT_W); p.numTiles = N * p.tilesH * p.tilesW;
@@ -817,8 +891,8 @@ static int launch_wgrad_halo(const void* x, const void* dy, float* dwp, int N, i
   if (want > p.numTiles) want = p.numTiles; if (want < 1) want = 1;
   p.tilesPerSplit = cdiv(p.numTiles, want); p.splits = cdiv(p.numTiles, p.tilesPerSplit);
   CUtensorMap tmDY, tmX;
-  int e = make_map_nhwc(&tmDY, dy, N, H, W, Cout, p.aAtomCh, HT_W, HT_H); if (e) return e;
-  e = make_map_nhwc(&tmX, x, N, H, W, Cin, p.nch, p.haloW, p.haloH); if (e) return e;
+  int e = make_map_nhwc(&tmDY, dyv, N, H, W, p.aAtomCh, HT_W, HT_H); if (e) return e;
+  e = make_map_nhwc(&tmX, xv, N, H, W, p.nch, p.haloW, p.haloH); if (e) return e;
   size_t smem = (size_t)p.stages * p.stageBytes + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(k_wgrad_tc_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
@@ -829,13 +903,17 @@ static int launch_wgrad_halo(const void* x, const void* dy, float* dwp, int N, i
 }
 
 // dw_packed fp32 [taps][Cin][Cout] (same layout as the direct path; zeroed here)
-extern "C" int egm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_packed, int N, int H, int W, int Cin, int Cout, int kh, int kw, int dil,
-                                   void* stream) {
+// General form: x and dy are channel-strided views; Cin / Cout are the padded channel counts of dw_packed.
+extern "C" int egm_conv2d_wgrad_tc_view(const void* x, long long x_cstride, long long x_coff, int cin_valid, const void* dy, long long dy_cstride,
+                                        long long dy_coff, int cout_valid, float* dw_packed, int N, int H, int W, int Cin, int Cout, int kh, int kw,
+                                        int dil, void* stream) {
   EGM_REQUIRE(egm_conv2d_tc_supported(Cin, Cout, kh, kw, dil, 1), EGM_E_SHAPE, "wgrad_tc: unsupported shape %d->%d", Cin, Cout);
+  EGM_REQUIRE(cin_valid >= 1 && cin_valid <= Cin && cout_valid >= 1 && cout_valid <= Cout, EGM_E_SHAPE, "wgrad_tc: valid channels out of range");
+  const NhwcView xv{x, x_cstride, x_coff, cin_valid}, dyv{dy, dy_cstride, dy_coff, cout_valid};
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(dw_packed, 0, sizeof(float) * (size_t)kh * kw * Cin * Cout, st);
   if ((long long)N * H * W == 0) return EGM_OK;
-  if (wgrad_halo_eligible(Cin, Cout, kh, kw, dil)) return launch_wgrad_halo(x, dy, dw_packed, N, H, W, Cin, Cout, kh, kw, dil, st);
+  if (wgrad_halo_eligible(Cin, Cout, kh, kw, dil)) return launch_wgrad_halo(xv, dyv, dw_packed, N, H, W, Cin, Cout, kh, kw, dil, st);
   WgradParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
   p.tilesH = cdiv(H, TILE_H); p.tilesW = cdiv(W, TILE_W); p.numTiles = N * p.tilesH * p.tilesW;
@@ -857,8 +935,8 @@ extern "C" int egm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_pack
   if (want > p.numTiles) want = p.numTiles; if (want < 1) want = 1;
   p.tilesPerSplit = cdiv(p.numTiles, want); p.splits = cdiv(p.numTiles, p.tilesPerSplit);
   CUtensorMap tmDY, tmX;
-  int e = make_map_nhwc(&tmDY, dy, N, H, W, Cout, aAtomCh, TILE_W, TILE_H); if (e) return e;
-  e = make_map_nhwc(&tmX, x, N, H, W, Cin, p.nch, TILE_W, TILE_H); if (e) return e;
+  int e = make_map_nhwc(&tmDY, dyv, N, H, W, aAtomCh, TILE_W, TILE_H); if (e) return e;
+  e = make_map_nhwc(&tmX, xv, N, H, W, p.nch, TILE_W, TILE_H); if (e) return e;
   size_t smem = (size_t)p.stages * p.stageBytes + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
@@ -866,4 +944,8 @@ extern "C" int egm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_pack
   EGM_REQUIRE(grid < (1ll << 31), EGM_E_SHAPE, "wgrad_tc: grid too large");
   k_wgrad_tc<<<(unsigned)grid, TC_THREADS, smem, st>>>(tmDY, tmX, dw_packed, p);
   EGM_LAUNCH_CHECK("conv2d_wgrad_tc"); return EGM_OK;
+}
+extern "C" int egm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_packed, int N, int H, int W, int Cin, int Cout, int kh, int kw, int dil,
+                                   void* stream) {
+  return egm_conv2d_wgrad_tc_view(x, Cin, 0, Cin, dy, Cout, 0, Cout, dw_packed, N, H, W, Cin, Cout, kh, kw, dil, stream);
 }

@@ -301,22 +301,66 @@ def _pad16(c: int) -> int:
     return (c + 15) // 16 * 16
 
 
-def _conv2d_lifted(ctx, x, wparam, bparam, weight, bias, groups, dilation, x_coff, cin, wgrad_sink, bgrad_sink) -> Var:
-    """Thin (C < 16 or C % 16 != 0), grouped or channel-sliced conv on the tcgen05 path: activations are copied into
-    zero-padded 16-channel-aligned scratch tensors and the weight is lifted to a dense zero-padded (block-diagonal) one;
-    outputs / gradients are sliced back.  MMA work on the padding is irrelevant -- these layers are bandwidth-bound."""
+def _tc_read_view(ctx, t, n, h, w, ctot, coff, c, cp):
+    """(tensor, cstride, coff, valid) of a channel slice as a TMA-readable operand of a tcgen05 conv with `cp` padded channels.
+    egm_conv2d_tc_view zero-fills the channels >= valid, so no staging copy is needed unless the slice is not 16-byte aligned."""
+    if ctot % 8 == 0 and coff % 8 == 0:
+        return t, ctot, coff, c
+    tp = ctx.empty(n, h, w, cp)
+    if cp != c:
+        call("memset_zero", tp, tp.numel() * 2)
+    call("copy_slice", t, tp, ctx.code, n * h * w, c, ctot, coff, cp, 0, 0)
+    return tp, cp, 0, cp
+
+
+def _conv_tc_fwd_bwd(ctx, x, x_coff, cin, cinp, co, cop, kh, kw, dilation, wf, wd, bp, bias_present, bparam, bgrad_sink, wgrad_to):
+    """Forward + tape entry of one tcgen05 conv on channel-strided views.  wgrad_to(dwp) receives / names the packed fp32
+    gradient buffer: it returns the tensor egm_conv2d_wgrad_tc_view writes and is called again (post=True) afterwards."""
     n, h, w, ctot = x.shape
-    co, cig, kh, kw = weight.shape
-    M, taps = n * h * w, kh * kw
-    cinp, cop = _pad16(cin), _pad16(co)
+    M = n * h * w
     sliced = not (x_coff == 0 and cin == ctot)
-    if cinp == ctot and not sliced:
-        xp = x.t
-    else:
-        xp = ctx.empty(n, h, w, cinp)
-        if cinp != cin:
-            call("memset_zero", xp, xp.numel() * 2)
-        call("copy_slice", x.t, xp, ctx.code, M, cin, ctot, x_coff, cinp, 0, 0)
+    xt, xcs, xco, xv = _tc_read_view(ctx, x.t, n, h, w, ctot, x_coff, cin, cinp)
+    y = ctx.empty(n, h, w, co)
+    call("conv2d_tc_view", xt, xcs, xco, xv, wf, bp, y, co, 0, co, 0, n, h, w, cinp, cop, kh, kw, dilation)
+    out = Var(y)
+    if ctx.record:
+        def bwd():
+            dy = out.grad
+            out.grad = None
+            if dy is None:
+                return
+            dyt, dcs, dco, dv = _tc_read_view(ctx, dy, n, h, w, co, 0, co, cop)
+            dwp = wgrad_to(False)
+            call("conv2d_wgrad_tc_view", xt, xcs, xco, xv, dyt, dcs, dco, dv, dwp, n, h, w, cinp, cop, kh, kw, dilation)
+            wgrad_to(True)
+            if bias_present:
+                gb = torch.empty(co, **ctx.f32) if bgrad_sink is not None else ctx.grad_slot(bparam)
+                call("channel_sum", dy, ctx.code, M, co, co, 0, ctx.f64(co), gb)
+                if bgrad_sink is not None:
+                    bgrad_sink(gb)
+            if x.needs_grad:
+                fresh = x.grad is None
+                gx, acc = x.grad_target(partial=sliced)
+                if fresh:             # first contribution: dgrad lands directly in (the channel slice of) x's gradient
+                    call("conv2d_tc_view", dyt, dcs, dco, dv, wd, None, gx, ctot, x_coff, cin, 0, n, h, w, cop, cinp, kh, kw, dilation)
+                else:                 # a read-modify-write epilogue is latency-bound (measured 2.4x slower): add in a streaming pass
+                    tmp = ctx.empty(n, h, w, cin)
+                    call("conv2d_tc_view", dyt, dcs, dco, dv, wd, None, tmp, cin, 0, cin, 0, n, h, w, cop, cinp, kh, kw, dilation)
+                    if sliced:
+                        call("copy_slice", tmp, gx, ctx.code, M, cin, cin, 0, ctot, x_coff, 1)
+                    else:
+                        call("axpby", gx, tmp, ctx.code, tmp.numel(), 1.0, 1.0)
+        ctx.push(bwd)
+    return out
+
+
+def _conv2d_lifted(ctx, x, wparam, bparam, weight, bias, groups, dilation, x_coff, cin, wgrad_sink, bgrad_sink) -> Var:
+    """Thin (C < 16 or C % 16 != 0), grouped or channel-sliced conv on the tcgen05 path: the weight is lifted to a dense
+    zero-padded (block-diagonal) 16-aligned one; activations are read / written in place through channel-strided views (TMA
+    zero-fills the padding channels).  MMA work on the padding is irrelevant -- these layers are bandwidth-bound."""
+    co, cig, kh, kw = weight.shape
+    taps = kh * kw
+    cinp, cop = _pad16(cin), _pad16(co)
     wpd = torch.empty(cop, cinp, kh, kw, **ctx.f32)
     call("conv_weight_lift", weight, wpd, co, cig, groups, taps, cop, cinp, 0)
     bp = None
@@ -326,103 +370,28 @@ def _conv2d_lifted(ctx, x, wparam, bparam, weight, bias, groups, dilation, x_cof
     wf = torch.empty(wpd.numel(), dtype=torch.bfloat16, device=ctx.device)
     wd = torch.empty(wpd.numel(), dtype=torch.bfloat16, device=ctx.device) if ctx.record else None
     call("pack_conv_weight_tc", wpd, wf, wd, cop, cinp, kh, kw)
-    yp = ctx.empty(n, h, w, cop)
-    call("conv2d_tc", xp, wf, bp, yp, n, h, w, cinp, cop, kh, kw, dilation)
-    if cop == co:
-        y = yp
-    else:
-        y = ctx.empty(n, h, w, co)
-        call("copy_slice", yp, y, ctx.code, M, co, cop, 0, co, 0, 0)
-    out = Var(y)
-    if ctx.record:
-        def bwd():
-            dy = out.grad
-            out.grad = None
-            if dy is None:
-                return
-            if cop == co:
-                dyp = dy
-            else:
-                dyp = ctx.empty(n, h, w, cop)
-                call("memset_zero", dyp, dyp.numel() * 2)
-                call("copy_slice", dy, dyp, ctx.code, M, co, co, 0, cop, 0, 0)
-            dwpk = torch.empty(wpd.numel(), **ctx.f32)
-            call("conv2d_wgrad_tc", xp, dyp, dwpk, n, h, w, cinp, cop, kh, kw, dilation)
-            dwd = torch.empty_like(wpd)
-            call("unpack_conv_wgrad", dwpk, dwd, cop, cinp, kh, kw, 0.0)
-            dw = torch.empty_like(weight) if wgrad_sink is not None else ctx.grad_slot(wparam)
-            call("conv_weight_lift", dw, dwd, co, cig, groups, taps, cop, cinp, 1)
-            if wgrad_sink is not None:
-                wgrad_sink(dw)
-            if bias is not None:
-                gb = torch.empty(co, **ctx.f32) if bgrad_sink is not None else ctx.grad_slot(bparam)
-                call("channel_sum", dy, ctx.code, M, co, co, 0, ctx.f64(co), gb)
-                if bgrad_sink is not None:
-                    bgrad_sink(gb)
-            if x.needs_grad:
-                gxp = ctx.empty(n, h, w, cinp)
-                call("conv2d_tc", dyp, wd, None, gxp, n, h, w, cop, cinp, kh, kw, dilation)
-                gx, acc = x.grad_target(partial=sliced)
-                call("copy_slice", gxp, gx, ctx.code, M, cin, cinp, 0, ctot, x_coff, acc)
-        ctx.push(bwd)
-    return out
+    hold = {}
+
+    def wgrad_to(post):
+        if not post:
+            hold["dwp"] = torch.empty(wpd.numel(), **ctx.f32)
+            return hold["dwp"]
+        dwd = torch.empty_like(wpd)
+        call("unpack_conv_wgrad", hold.pop("dwp"), dwd, cop, cinp, kh, kw, 0.0)
+        dw = torch.empty_like(weight) if wgrad_sink is not None else ctx.grad_slot(wparam)
+        call("conv_weight_lift", dw, dwd, co, cig, groups, taps, cop, cinp, 1)
+        if wgrad_sink is not None:
+            wgrad_sink(dw)
+    return _conv_tc_fwd_bwd(ctx, x, x_coff, cin, cinp, co, cop, kh, kw, dilation, wf, wd, bp, bias is not None, bparam, bgrad_sink, wgrad_to)
 
 
 def _conv2d_planned(ctx, x, job: WeightJob, bias, bparam, dilation, x_coff, cin, bgrad_sink) -> Var:
     """tcgen05 conv whose packed operands come from the WeightPlan (filled by egm_weight_prep_batch at the start of the step);
     its weight gradient stays packed in job.dwp until egm_wgrad_unpack_batch at the end of backward."""
-    n, h, w, ctot = x.shape
     co, cig, kh, kw = job.spec.shape
-    M = n * h * w
-    cinp, cop = job.cinp, job.coutp
-    sliced = not (x_coff == 0 and cin == ctot)
-    if cinp == ctot and not sliced:
-        xp = x.t
-    else:
-        xp = ctx.empty(n, h, w, cinp)
-        if cinp != cin:
-            call("memset_zero", xp, xp.numel() * 2)
-        call("copy_slice", x.t, xp, ctx.code, M, cin, ctot, x_coff, cinp, 0, 0)
     bp = job.bpad if job.bpad is not None else bias
-    yp = ctx.empty(n, h, w, cop)
-    call("conv2d_tc", xp, job.wf, bp, yp, n, h, w, cinp, cop, kh, kw, dilation)
-    if cop == co:
-        y = yp
-    else:
-        y = ctx.empty(n, h, w, co)
-        call("copy_slice", yp, y, ctx.code, M, co, cop, 0, co, 0, 0)
-    out = Var(y)
-
-    def bwd():
-        dy = out.grad
-        out.grad = None
-        if dy is None:
-            return
-        if cop == co:
-            dyp = dy
-        else:
-            dyp = ctx.empty(n, h, w, cop)
-            call("memset_zero", dyp, dyp.numel() * 2)
-            call("copy_slice", dy, dyp, ctx.code, M, co, co, 0, cop, 0, 0)
-        call("conv2d_wgrad_tc", xp, dyp, job.dwp, n, h, w, cinp, cop, kh, kw, dilation)
-        if bparam is not None or bgrad_sink is not None:
-            gb = torch.empty(co, **ctx.f32) if bgrad_sink is not None else ctx.grad_slot(bparam)
-            call("channel_sum", dy, ctx.code, M, co, co, 0, ctx.f64(co), gb)
-            if bgrad_sink is not None:
-                bgrad_sink(gb)
-        if x.needs_grad:
-            gx, acc = x.grad_target(partial=sliced)
-            if cinp == ctot and not sliced and not acc:
-                call("conv2d_tc", dyp, job.wd, None, gx, n, h, w, cop, cinp, kh, kw, dilation)
-            else:
-                gxp = ctx.empty(n, h, w, cinp)
-                call("conv2d_tc", dyp, job.wd, None, gxp, n, h, w, cop, cinp, kh, kw, dilation)
-                if cinp == ctot and not sliced:
-                    call("axpby", gx, gxp, ctx.code, gxp.numel(), 1.0, 1.0)
-                else:
-                    call("copy_slice", gxp, gx, ctx.code, M, cin, cinp, 0, ctot, x_coff, acc)
-    ctx.push(bwd)
-    return out
+    return _conv_tc_fwd_bwd(ctx, x, x_coff, cin, job.cinp, co, job.coutp, kh, kw, dilation, job.wf, job.wd, bp,
+                            bparam is not None or bgrad_sink is not None, bparam, bgrad_sink, lambda post: job.dwp)
 
 
 def conv_module(ctx: Ctx, x: Var, m: nn.Conv2d, **kw) -> Var:

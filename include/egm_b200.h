@@ -65,6 +65,18 @@ int egm_conv2d_tc(const void* x, const void* w_packed_bf16, const float* bias, v
                   int kh, int kw, int dil, void* stream);
 int egm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_packed, int N, int H, int W, int Cin, int Cout, int kh, int kw, int dil,
                         void* stream);
+/* General forms: operands are channel-strided views (element (pixel p, channel c < valid) at ptr[p*cstride + coff + c], as in
+ * egm_copy_slice).  Cin / Cout are the padded (multiple-of-16) channel counts of the packed weight; channels >= *_valid read
+ * as zero through TMA out-of-bounds fill and are never written, so thin (C < 16), odd and channel-sliced tensors -- GRFB branch
+ * convs on slices of cat(x, dir, edge, ctx), RGA split, 1/2/3-channel heads -- need no staging copies.  TMA-read views need
+ * cstride % 8 == 0 and coff % 8 == 0; the output view may be arbitrary (unaligned rows fall back to 2-byte stores).
+ * accumulate != 0: y += conv. */
+int egm_conv2d_tc_view(const void* x, long long x_cstride, long long x_coff, int cin_valid, const void* w_packed_bf16, const float* bias,
+                       void* y, long long y_cstride, long long y_coff, int cout_valid, int accumulate, int N, int H, int W, int Cin,
+                       int Cout, int kh, int kw, int dil, void* stream);
+int egm_conv2d_wgrad_tc_view(const void* x, long long x_cstride, long long x_coff, int cin_valid, const void* dy, long long dy_cstride,
+                             long long dy_coff, int cout_valid, float* dw_packed, int N, int H, int W, int Cin, int Cout, int kh, int kw,
+                             int dil, void* stream);
 
 /* ---- BatchNorm2d (+ReLU / sigmoid gate / residual) (nn.BatchNorm2d: src/EGM-UNet.py:50,53,879,966; ATen native_batch_norm today) ---- */
 int egm_bn_stats(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, void* stream);
