@@ -16,10 +16,10 @@ for n, a in sorted(agg.items(), key=lambda x: -x[1][0])[:top]:
     print(f"{n:26s} {a[0]:7.2f} ms {a[1]:4d}")
 rows = []
 for k, v in d["kernels"].items():
-    if k.startswith("conv2d_tc:") or k.startswith("conv2d_wgrad_tc:"):
+    if k.startswith("conv2d_tc") or k.startswith("conv2d_wgrad_tc"):
         a = [int(x) for x in k.split(":")[1].split(",")]
-        n, h, w, ci, co, kh, kw, dil = a[:8]
-        rows.append((v["ms"], k.split(":")[0][7:], h, ci, co, kh, dil, v["calls"], 2.0 * n * h * w * ci * co * kh * kw * v["calls"] / v["ms"] / 1e9))
+        n, h, w, ci, co, kh, kw, dil = a[-8:]          # the *_view entry points put their stride / offset ints first
+        rows.append((v["ms"], k.split(":")[0][7:].replace("_view", ""), h, ci, co, kh, dil, v["calls"], 2.0 * n * h * w * ci * co * kh * kw * v["calls"] / v["ms"] / 1e9))
 rows.sort(reverse=True)
 for r in rows[:top]:
     print(f"  {r[1]:9s} {r[3]:4d}->{r[4]:4d} @{r[2]:3d} k{r[5]} d{r[6]:2d} x{r[7]}  {r[0]:.3f} ms  {r[8]:7.1f} TF/s")
