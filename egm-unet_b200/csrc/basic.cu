@@ -61,8 +61,9 @@ template <typename T, int V>
 __global__ void k_copy_slice(const T* __restrict__ src, T* __restrict__ dst, long long M, int CV, long long scs, long long sco,
                              long long dcs, long long dco, int accumulate) {
   long long total = M * CV;
+  const RowIndexer rix(CV, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long m = i / CV; int c = (int)(i - m * CV) * V;
+    long long m; int c; rix(i, m, c); c *= V;
     FVec<V> a = ldv<V>(src + m * scs + sco + c);
     T* dp = dst + m * dcs + dco + c;
     if (accumulate) { FVec<V> b = ldv<V>(dp);

@@ -9,8 +9,9 @@
 template <typename T, int V>
 __global__ void k_highpass3(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int CV, int accumulate) {
   const int C = CV * V; long long total = (long long)N * H * W * CV;
+  const NhwcIndexer ix(CV, W, H, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % CV) * V; long long p = i / CV; int w = (int)(p % W); long long q = p / W; int h = (int)(q % H);
+    const Nhwc4 e = ix(i); const int c = e.cv * V, w = e.w, h = e.h; const long long p = e.p;
     FVec<V> s, ctr;
 #pragma unroll
     for (int j = 0; j < V; ++j) s.v[j] = 0.f;
@@ -125,8 +126,9 @@ __device__ __forceinline__ float pixel_phi(const T* g, long long m, int Gc, int 
 template <typename T, int V>
 __global__ void k_mul_pixel_gate(const T* __restrict__ a, const T* __restrict__ g, T* __restrict__ y, long long M, int CV, int Gc, int mode) {
   const int C = CV * V; long long total = M * CV;
+  const RowIndexer rix(CV, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long m = i / CV; int c = (int)(i - m * CV) * V;
+    long long m; int c; rix(i, m, c); c *= V;
     float f = pixel_phi(g, m, Gc, mode);
     FVec<V> x = ldv<V>(a + m * C + c);
 #pragma unroll
@@ -388,8 +390,9 @@ template <typename T, int V>
 __global__ void k_fuse_mix_fwd(const T* __restrict__ f, const T* __restrict__ s, const float* __restrict__ sa, const float* __restrict__ ca, T* __restrict__ t,
                                long long M, long long HW, int CV) {
   const int C = CV * V; long long total = M * CV;
+  const RowIndexer rix(CV, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long m = i / CV; int c = (int)(i - m * CV) * V;
+    long long m; int c; rix(i, m, c); c *= V;
     FVec<V> a = ldv<V>(f + m * C + c), b = ldv<V>(s + m * C + c), cc = ldv<V>(ca + (m / HW) * C + c);
     float g = sa[m];
 #pragma unroll
@@ -408,8 +411,9 @@ template <typename T, int V>
 __global__ void k_fuse_mix_bwd_s(const T* __restrict__ dt, const float* __restrict__ sa, const float* __restrict__ ca, const float* __restrict__ dmm,
                                  const unsigned char* __restrict__ amax, T* __restrict__ ds, long long M, long long HW, int CV) {
   const int C = CV * V; long long total = M * CV;
+  const RowIndexer rix(CV, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long m = i / CV; int c = (int)(i - m * CV) * V;
+    long long m; int c; rix(i, m, c); c *= V;
     FVec<V> a = ldv<V>(dt + m * C + c), cc = ldv<V>(ca + (m / HW) * C + c);
     float g = sa[m], d0 = dmm[m * 2] / (float)C, d1 = dmm[m * 2 + 1]; int am = amax[m];
 #pragma unroll
@@ -429,8 +433,9 @@ template <typename T, int V>
 __global__ void k_fuse_df_finish(T* __restrict__ df, const T* __restrict__ dt, const float* __restrict__ davg, const float* __restrict__ dmx,
                                  const int* __restrict__ arg, int accumulate, long long M, long long HW, int CV) {
   const int C = CV * V; long long total = M * CV; const float ih = 1.f / (float)HW;
+  const RowIndexer rix(CV, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long m = i / CV; int c = (int)(i - m * CV) * V; long long n = m / HW; int p = (int)(m - n * HW);
+    long long m; int c; rix(i, m, c); c *= V; long long n = m / HW; int p = (int)(m - n * HW);
     FVec<V> a, b = ldv<V>(dt + m * C + c), da = ldv<V>(davg + n * C + c), dm = ldv<V>(dmx + n * C + c);
     if (accumulate) a = ldv<V>(df + m * C + c);
 #pragma unroll

@@ -170,8 +170,9 @@ template <typename T, int V>
 __global__ void k_mca_u(const T* __restrict__ x, T* __restrict__ u, McaGeom g) {
   const int CV = g.C / V;
   long long total = (long long)g.N * g.H * g.W * CV;
+  const NhwcIndexer ix(CV, g.W, g.H, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % CV) * V; long long p = i / CV; int w = (int)(p % g.W); long long q = p / g.W; int h = (int)(q % g.H); int n = (int)(q / g.H);
+    const Nhwc4 e = ix(i); const int c = e.cv * V, w = e.w, h = e.h, n = e.n; const long long p = e.p;
     FVec<V> gcv = ldv<V>(g.gc + n * g.C + c);
     FVec<V> o = mca_u<T, V>(x, g, n, h, w, c, gcv);
     stv<V>(u + p * g.C + c, o);
@@ -180,8 +181,9 @@ __global__ void k_mca_u(const T* __restrict__ x, T* __restrict__ u, McaGeom g) {
 template <typename T, int V>
 __global__ void k_mca_d2(const T* __restrict__ u, T* __restrict__ d2, int N, int H, int W, int CV) {
   const int C = CV * V; long long total = (long long)N * H * W * CV;
+  const NhwcIndexer ix(CV, W, H, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % CV) * V; long long p = i / CV; int w = (int)(p % W); long long q = p / W; int h = (int)(q % H);
+    const Nhwc4 e = ix(i); const int c = e.cv * V, w = e.w, h = e.h; const long long p = e.p;
     FVec<V> s, ctr;
 #pragma unroll
     for (int j = 0; j < V; ++j) { s.v[j] = 0.f; ctr.v[j] = 0.f; }
@@ -205,8 +207,9 @@ __global__ void k_mca_d2(const T* __restrict__ u, T* __restrict__ d2, int N, int
 template <typename T, int V>
 __global__ void k_mca_out(const T* __restrict__ u, const T* __restrict__ d2, T* __restrict__ y, unsigned char* __restrict__ idx, int N, int H, int W, int CV) {
   const int C = CV * V; long long total = (long long)N * H * W * CV;
+  const NhwcIndexer ix(CV, W, H, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % CV) * V; long long p = i / CV; int w = (int)(p % W); long long q = p / W; int h = (int)(q % H);
+    const Nhwc4 e = ix(i); const int c = e.cv * V, w = e.w, h = e.h; const long long p = e.p;
     float mx[V], mn[V], var[V], uc[V]; int amx[V], amn[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) { mx[j] = -INFINITY; mn[j] = INFINITY; var[j] = 0.f; uc[j] = 0.f; amx[j] = 4; amn[j] = 4; }
@@ -272,8 +275,9 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256) k_mca_bwd_e(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ E, McaGeom g) {
   const int CV = g.C / V;
   long long total = (long long)g.N * g.H * g.W * CV;
+  const NhwcIndexer ix(CV, g.W, g.H, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % CV) * V; long long p = i / CV; int w = (int)(p % g.W); long long q = p / g.W; int h = (int)(q % g.H); int n = (int)(q / g.H);
+    const Nhwc4 e = ix(i); const int c = e.cv * V, w = e.w, h = e.h, n = e.n; const long long p = e.p;
     FVec<V> gcv = ldv<V>(g.gc + n * g.C + c), su, sd, uc;
 #pragma unroll
     for (int j = 0; j < V; ++j) { su.v[j] = 0.f; sd.v[j] = 0.f; uc.v[j] = 0.f; }
@@ -300,8 +304,9 @@ __global__ void __launch_bounds__(256) k_mca_bwd_du(const T* __restrict__ dy, co
                                                     T* __restrict__ du, McaGeom g) {
   const int CV = g.C / V;
   long long total = (long long)g.N * g.H * g.W * CV;
+  const NhwcIndexer ix(CV, g.W, g.H, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % CV) * V; long long p = i / CV; int w = (int)(p % g.W); long long q = p / g.W; int h = (int)(q % g.H); int n = (int)(q / g.H);
+    const Nhwc4 e = ix(i); const int c = e.cv * V, w = e.w, h = e.h, n = e.n; const long long p = e.p;
     FVec<V> o, se;
 #pragma unroll
     for (int j = 0; j < V; ++j) { o.v[j] = 0.f; se.v[j] = 0.f; }
@@ -411,8 +416,9 @@ template <typename T, int V>
 __global__ void k_mca_bwd_dx(const T* __restrict__ du, const T* __restrict__ x, const float* __restrict__ gates, const float* __restrict__ ca,
                              const float* __restrict__ cb, T* __restrict__ dx, int N, int H, int W, int CV, long long ow, long long oc) {
   const int C = CV * V; long long total = (long long)N * H * W * CV;
+  const NhwcIndexer ix(CV, W, H, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % CV) * V; long long p = i / CV; int w = (int)(p % W); long long q = p / W; int h = (int)(q % H); int n = (int)(q / H);
+    const Nhwc4 e = ix(i); const int c = e.cv * V, w = e.w, h = e.h, n = e.n; const long long p = e.p;
     FVec<V> d = ldv<V>(du + p * C + c), xv = ldv<V>(x + p * C + c), gc = ldv<V>(gates + oc + n * C + c), ac = ldv<V>(ca + oc + n * C + c),
             bc = ldv<V>(cb + oc + n * C + c), o;
     float gs = gates[n * H + h] + gates[ow + n * W + w], as = ca[n * H + h] + ca[ow + n * W + w], bs = cb[n * H + h] + cb[ow + n * W + w];

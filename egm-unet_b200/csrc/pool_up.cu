@@ -9,8 +9,9 @@ template <typename T, int V>
 __global__ void k_maxpool2_fwd(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int CV) {
   const int Ho = H / 2, Wo = W / 2, C = CV * V;
   long long total = (long long)N * Ho * Wo * CV;
+  const NhwcIndexer ix(CV, Wo, Ho, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int cv = (int)(i % CV); long long p = i / CV; int wo = (int)(p % Wo); long long q = p / Wo; int ho = (int)(q % Ho); int n = (int)(q / Ho);
+    const Nhwc4 e = ix(i); const int cv = e.cv, wo = e.w, ho = e.h, n = e.n; const long long p = e.p;
     const T* b = x + (((long long)n * H + 2 * ho) * W + 2 * wo) * C + cv * V;
     FVec<V> a = ldv<V>(b), c1 = ldv<V>(b + C), c2 = ldv<V>(b + (long long)W * C), c3 = ldv<V>(b + (long long)W * C + C), o;
 #pragma unroll
@@ -23,8 +24,9 @@ template <typename T, int V>
 __global__ void k_maxpool2_bwd(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W, int CV, int accumulate) {
   const int Ho = H / 2, Wo = W / 2, C = CV * V;
   long long total = (long long)N * Ho * Wo * CV;
+  const NhwcIndexer ix(CV, Wo, Ho, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int cv = (int)(i % CV); long long p = i / CV; int wo = (int)(p % Wo); long long q = p / Wo; int ho = (int)(q % Ho); int n = (int)(q / Ho);
+    const Nhwc4 e = ix(i); const int cv = e.cv, wo = e.w, ho = e.h, n = e.n; const long long p = e.p;
     long long base = (((long long)n * H + 2 * ho) * W + 2 * wo) * C + cv * V;
     long long off[4] = {0, C, (long long)W * C, (long long)W * C + C};
     FVec<V> v[4], g = ldv<V>(dy + p * C + cv * V);
@@ -77,8 +79,9 @@ template <typename T, int V>
 __global__ void k_upcat_fwd(const T* __restrict__ skip, const T* __restrict__ low, T* __restrict__ out, UpGeom g) {
   const int C = g.Cs + g.Cu, CV = C / V;
   long long total = (long long)g.N * g.H * g.W * CV;
+  const NhwcIndexer ix(CV, g.W, g.H, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % CV) * V; long long p = i / CV; int w = (int)(p % g.W); long long q = p / g.W; int h = (int)(q % g.H); int n = (int)(q / g.H);
+    const Nhwc4 e = ix(i); const int c = e.cv * V, w = e.w, h = e.h, n = e.n; const long long p = e.p;
     FVec<V> o;
     if (c < g.Cs) o = ldv<V>(skip + p * g.Cs + c);
     else {
@@ -104,8 +107,9 @@ template <typename T, int V>
 __global__ void k_upcat_bwd_low(const T* __restrict__ dcat, T* __restrict__ dlow, UpGeom g) {
   const int C = g.Cs + g.Cu, CV = g.Cu / V;
   long long total = (long long)g.N * g.Hl * g.Wl * CV;
+  const NhwcIndexer ix(CV, g.Wl, g.Hl, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int cu = (int)(i % CV) * V; long long p = i / CV; int wl = (int)(p % g.Wl); long long q = p / g.Wl; int hl = (int)(q % g.Hl); int n = (int)(q / g.Hl);
+    const Nhwc4 e = ix(i); const int cu = e.cv * V, wl = e.w, hl = e.h, n = e.n; const long long p = e.p;
     float wh[6], ww[6];
 #pragma unroll
     for (int t = 0; t < 6; ++t) {
@@ -180,8 +184,9 @@ template <typename T, int V>
 __global__ void k_shufcat_fwd(const T* __restrict__ skip, const T* __restrict__ z, T* __restrict__ out, UpGeom g) {
   const int C = g.Cs + g.Cu, CV = C / V;
   long long total = (long long)g.N * g.H * g.W * CV;
+  const NhwcIndexer ix(CV, g.W, g.H, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % CV) * V; long long p = i / CV; int w = (int)(p % g.W); long long q = p / g.W; int h = (int)(q % g.H); int n = (int)(q / g.H);
+    const Nhwc4 e = ix(i); const int c = e.cv * V, w = e.w, h = e.h, n = e.n; const long long p = e.p;
     FVec<V> o;
     if (c < g.Cs) o = ldv<V>(skip + p * g.Cs + c);
     else {
