@@ -112,7 +112,8 @@ __global__ void k_bn_stats(StatsF<T, V> f, long long M, int C, double* out, BnTa
   bn_tail_run(tl, out, C, threadIdx.x, blockDim.x, false);
 }
 static bool bn_stats_stream_launch(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, const BnTail& tl, cudaStream_t st);
-static bool bn_fwd_stream_launch(const void* z, long long zcs, long long zco, const BnArgs& a, void* y, long long ycs, long long yco, int dtype, long long M, int C, cudaStream_t st);
+static bool bn_fwd_stream_launch(const void* z, long long zcs, long long zco, const BnArgs& a, const void* aux, void* y, long long ycs, long long yco, int dtype,
+                                 long long M, int C, cudaStream_t st);
 static int bn_stats_impl(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, BnTail tl, cudaStream_t st) {
   EGM_REQUIRE(C >= 1 && C <= 2048, EGM_E_SHAPE, "bn_stats: C=%d unsupported", C);
   cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C + (tl.counter ? 1 : 0)), st);
@@ -202,7 +203,7 @@ extern "C" int egm_bn_act_fwd(const void* z, long long z_cstride, long long z_co
   EGM_REQUIRE(mode == 0 || aux, EGM_E_BADARG, "bn_act_fwd: mode %d needs aux", mode);
   int v = egm_pick_vec(C, z_cstride, z_coff), v2 = egm_pick_vec(C, y_cstride, y_coff); if (v2 < v) v = v2;
   BnArgs a{scale, shift, nullptr, nullptr, nullptr, act, mode, alpha};
-  if (bn_fwd_stream_launch(z, z_cstride, z_coff, a, y, y_cstride, y_coff, dtype, M, C, (cudaStream_t)stream)) { EGM_LAUNCH_CHECK("bn_act_fwd(stream)"); return EGM_OK; }
+  if (bn_fwd_stream_launch(z, z_cstride, z_coff, a, aux, y, y_cstride, y_coff, dtype, M, C, (cudaStream_t)stream)) { EGM_LAUNCH_CHECK("bn_act_fwd(stream)"); return EGM_OK; }
   const int threads = reduce_threads(C, v);
   EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_act_fwd<T, V><<<ew_blocks(M, threads, C, V), threads, 0, (cudaStream_t)stream>>>(
       (const T*)z, z_cstride, z_coff, a, (const T*)aux, (T*)y, y_cstride, y_coff, M, C / V))));
@@ -254,11 +255,19 @@ static int bn_bwd_reduce_impl(const void* dy, long long dy_cstride, long long dy
   if (M == 0) return EGM_OK;
   BnArgs a{scale, shift, mean, rstd, nullptr, act, mode, alpha};
   if (bn_stream_eligible(mode, M, C, dy_cstride, dy_coff)) {
-    const size_t smb = bs::ring_bytes<2>(2 * bs::CONSUMERS * bs::V * sizeof(float));
+    const size_t tail = 2 * bs::CONSUMERS * bs::V * sizeof(float);
     EGM_DISPATCH_DTYPE(dtype, {
-      static bool attr = false;
-      if (!attr) { cudaFuncSetAttribute(k_bn_bwd_reduce_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
-      k_bn_bwd_reduce_stream<T><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st>>>((const T*)dy, (const T*)z, a, M * C, C, sums, tl);
+      if (mode == 0) {
+        const size_t smb = bs::ring_bytes<2>(tail);
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(k_bn_bwd_reduce_stream<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+        k_bn_bwd_reduce_stream<T, false><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st>>>((const T*)dy, (const T*)z, nullptr, a, M * C, C, sums, tl);
+      } else {
+        const size_t smb = bs::ring_bytes<3>(tail);
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(k_bn_bwd_reduce_stream<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+        k_bn_bwd_reduce_stream<T, true><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st>>>((const T*)dy, (const T*)z, (const T*)aux, a, M * C, C, sums, tl);
+      }
     });
     EGM_LAUNCH_CHECK("bn_act_bwd_reduce(stream)"); return EGM_OK;
   }
@@ -331,12 +340,21 @@ extern "C" int egm_bn_act_bwd_apply(const void* dy, long long dy_cstride, long l
                                     void* dz, void* daux, int daux_accumulate, int dtype, long long M, int C, void* stream) {
   if (M * C == 0) return EGM_OK;
   BnArgs a{scale, shift, mean, rstd, coef, act, mode, alpha};
-  if (bn_stream_eligible(mode, M, C, dy_cstride, dy_coff)) {
-    const size_t smb = bs::ring_bytes<2>(0);
+  if (mode == 0 && bn_stream_eligible(mode, M, C, dy_cstride, dy_coff)) {   // the aux modes are ALU-bound on 8 consumer warps (measured slower)
     EGM_DISPATCH_DTYPE(dtype, {
-      static bool attr = false;
-      if (!attr) { cudaFuncSetAttribute(k_bn_bwd_apply_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
-      k_bn_bwd_apply_stream<T><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, (cudaStream_t)stream>>>((const T*)dy, (const T*)z, a, (T*)dz, M * C, C);
+      if (mode == 0) {
+        const size_t smb = bs::ring_bytes<2>(0);
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(k_bn_bwd_apply_stream<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+        k_bn_bwd_apply_stream<T, false><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, (cudaStream_t)stream>>>(
+            (const T*)dy, (const T*)z, nullptr, a, (T*)dz, nullptr, 0, M * C, C);
+      } else {
+        const size_t smb = bs::ring_bytes<3>(0);
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(k_bn_bwd_apply_stream<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+        k_bn_bwd_apply_stream<T, true><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, (cudaStream_t)stream>>>(
+            (const T*)dy, (const T*)z, (const T*)aux, a, (T*)dz, (T*)daux, daux_accumulate, M * C, C);
+      }
     });
     EGM_LAUNCH_CHECK("bn_act_bwd_apply(stream)"); return EGM_OK;
   }
@@ -390,16 +408,22 @@ static bool bn_stats_stream_launch(const void* x, int dtype, long long M, int C,
   }
   return true;
 }
-static bool bn_fwd_stream_launch(const void* z, long long zcs, long long zco, const BnArgs& a, void* y, long long ycs, long long yco, int dtype, long long M, int C,
-                                 cudaStream_t st) {
+static bool bn_fwd_stream_launch(const void* z, long long zcs, long long zco, const BnArgs& a, const void* aux, void* y, long long ycs, long long yco, int dtype,
+                                 long long M, int C, cudaStream_t st) {
   if (!bn_stream_eligible(a.mode, M, C, zcs, zco) || ycs != C || yco != 0 || (dtype != EGM_F32 && dtype != EGM_BF16)) return false;
-  const size_t smb = bs::ring_bytes<1>(0);
-  if (dtype == EGM_F32) {
-    static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_bn_act_fwd_stream<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
-    k_bn_act_fwd_stream<float><<<bn_stream_grid(M * C, 4), bs::THREADS, smb, st>>>((const float*)z, a, (float*)y, M * C, C);
-  } else {
-    static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_bn_act_fwd_stream<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
-    k_bn_act_fwd_stream<__nv_bfloat16><<<bn_stream_grid(M * C, 2), bs::THREADS, smb, st>>>((const __nv_bfloat16*)z, a, (__nv_bfloat16*)y, M * C, C);
-  }
+  if (a.mode == 1) return false;        // sigmoid gate: ALU-bound on 8 consumer warps, the grid-stride kernel is faster (measured)
+  EGM_DISPATCH_DTYPE(dtype, {
+    if (a.mode == 0) {
+      const size_t smb = bs::ring_bytes<1>(0);
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(k_bn_act_fwd_stream<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+      k_bn_act_fwd_stream<T, false><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st>>>((const T*)z, nullptr, a, (T*)y, M * C, C);
+    } else {
+      const size_t smb = bs::ring_bytes<2>(0);
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(k_bn_act_fwd_stream<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+      k_bn_act_fwd_stream<T, true><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st>>>((const T*)z, (const T*)aux, a, (T*)y, M * C, C);
+    }
+  });
   return true;
 }

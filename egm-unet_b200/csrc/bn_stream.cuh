@@ -64,18 +64,19 @@ __device__ __forceinline__ void produce(const Ring& r, const T* const* src, long
 }
 }  // namespace bs
 
-// ------------------------------------------------------------------ sum(g), sum(g*xhat) per channel   (mode 0 only)
-template <typename T>
-__global__ void __launch_bounds__(bs::THREADS, 1) k_bn_bwd_reduce_stream(const T* __restrict__ dy, const T* __restrict__ z, BnArgs a, long long total, int C,
-                                                                        double* __restrict__ out, BnTail tl) {
+// ------------------------------------------------------------------ sum(g), sum(g*xhat) per channel   (AUX: gate / residual modes read `aux` too)
+template <typename T, bool AUX>
+__global__ void __launch_bounds__(bs::THREADS, 1) k_bn_bwd_reduce_stream(const T* __restrict__ dy, const T* __restrict__ z, const T* __restrict__ aux, BnArgs a,
+                                                                        long long total, int C, double* __restrict__ out, BnTail tl) {
   using namespace bs;
+  constexpr int NT = AUX ? 3 : 2;
   extern __shared__ uint8_t smem_raw[];
   float* red;
-  Ring r = make_ring<2>(smem_raw, &red);
+  Ring r = make_ring<NT>(smem_raw, &red);
   constexpr long long EPC = CHUNK_BYTES / sizeof(T);
   const long long nChunks = (total + EPC - 1) / EPC;
   if (threadIdx.x >= CONSUMERS) {
-    if (threadIdx.x == CONSUMERS) { const T* src[2] = {dy, z}; produce<T, 2>(r, src, total, nChunks); }
+    if (threadIdx.x == CONSUMERS) { const T* src[3] = {dy, z, aux}; produce<T, NT>(r, src, total, nChunks); }
     return;
   }
   const int t = threadIdx.x, c = (t * V) % C;                 // fixed channel vector: (CONSUMERS*V) % C == 0 and EPC % C == 0
@@ -86,15 +87,17 @@ __global__ void __launch_bounds__(bs::THREADS, 1) k_bn_bwd_reduce_stream(const T
   int s = 0; uint32_t ph = 0;
   for (long long ch = blockIdx.x; ch < nChunks; ch += gridDim.x) {
     const long long e0 = ch * EPC; const int n = (int)(total - e0 < EPC ? total - e0 : EPC);
-    const T* sd = (const T*)(r.buf + ((size_t)s * 2 + 0) * CHUNK_BYTES);
-    const T* sz = (const T*)(r.buf + ((size_t)s * 2 + 1) * CHUNK_BYTES);
+    const T* sd = (const T*)(r.buf + ((size_t)s * NT + 0) * CHUNK_BYTES);
+    const T* sz = (const T*)(r.buf + ((size_t)s * NT + 1) * CHUNK_BYTES);
+    const T* sx = (const T*)(r.buf + ((size_t)s * NT + (NT - 1)) * CHUNK_BYTES);
     bar_wait(&r.full[s], ph);
 #pragma unroll 4
     for (int e = t * V; e < n; e += CONSUMERS * V) {
-      FVec<V> d = ldv<V>(sd + e), zv = ldv<V>(sz + e);
+      FVec<V> d = ldv<V>(sd + e), zv = ldv<V>(sz + e), xv;
+      if constexpr (AUX) xv = ldv<V>(sx + e);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        float g, da; bn_local_grad(a, d.v[j], zv.v[j], sc.v[j], sh.v[j], 0.f, g, da);
+        float g, da; bn_local_grad(a, d.v[j], zv.v[j], sc.v[j], sh.v[j], AUX ? xv.v[j] : 0.f, g, da);
         acc0[j] += g; acc1[j] += g * (zv.v[j] - mu.v[j]) * rs.v[j];
       }
     }
@@ -114,18 +117,19 @@ __global__ void __launch_bounds__(bs::THREADS, 1) k_bn_bwd_reduce_stream(const T
   bn_tail_run(tl, out, C, t, CONSUMERS, true);
 }
 
-// ------------------------------------------------------------------ dz = k0 * (g - k1 - xhat*k2)   (mode 0 only)
-template <typename T>
-__global__ void __launch_bounds__(bs::THREADS, 1) k_bn_bwd_apply_stream(const T* __restrict__ dy, const T* __restrict__ z, BnArgs a, T* __restrict__ dz,
-                                                                       long long total, int C) {
+// ------------------------------------------------------------------ dz = k0 * (g - k1 - xhat*k2)   (AUX: also daux (+)= the gate / residual branch)
+template <typename T, bool AUX>
+__global__ void __launch_bounds__(bs::THREADS, 1) k_bn_bwd_apply_stream(const T* __restrict__ dy, const T* __restrict__ z, const T* __restrict__ aux, BnArgs a,
+                                                                       T* __restrict__ dz, T* __restrict__ daux, int daux_acc, long long total, int C) {
   using namespace bs;
+  constexpr int NT = AUX ? 3 : 2;
   extern __shared__ uint8_t smem_raw[];
   float* tail;
-  Ring r = make_ring<2>(smem_raw, &tail);
+  Ring r = make_ring<NT>(smem_raw, &tail);
   constexpr long long EPC = CHUNK_BYTES / sizeof(T);
   const long long nChunks = (total + EPC - 1) / EPC;
   if (threadIdx.x >= CONSUMERS) {
-    if (threadIdx.x == CONSUMERS) { const T* src[2] = {dy, z}; produce<T, 2>(r, src, total, nChunks); }
+    if (threadIdx.x == CONSUMERS) { const T* src[3] = {dy, z, aux}; produce<T, NT>(r, src, total, nChunks); }
     return;
   }
   const int t = threadIdx.x, c = (t * V) % C;
@@ -134,18 +138,25 @@ __global__ void __launch_bounds__(bs::THREADS, 1) k_bn_bwd_apply_stream(const T*
   int s = 0; uint32_t ph = 0;
   for (long long ch = blockIdx.x; ch < nChunks; ch += gridDim.x) {
     const long long e0 = ch * EPC; const int n = (int)(total - e0 < EPC ? total - e0 : EPC);
-    const T* sd = (const T*)(r.buf + ((size_t)s * 2 + 0) * CHUNK_BYTES);
-    const T* sz = (const T*)(r.buf + ((size_t)s * 2 + 1) * CHUNK_BYTES);
+    const T* sd = (const T*)(r.buf + ((size_t)s * NT + 0) * CHUNK_BYTES);
+    const T* sz = (const T*)(r.buf + ((size_t)s * NT + 1) * CHUNK_BYTES);
+    const T* sx = (const T*)(r.buf + ((size_t)s * NT + (NT - 1)) * CHUNK_BYTES);
     bar_wait(&r.full[s], ph);
 #pragma unroll 4
     for (int e = t * V; e < n; e += CONSUMERS * V) {
-      FVec<V> d = ldv<V>(sd + e), zv = ldv<V>(sz + e), o;
+      FVec<V> d = ldv<V>(sd + e), zv = ldv<V>(sz + e), o, xv, oa;
+      if constexpr (AUX) {
+        xv = ldv<V>(sx + e);
+        if (daux && daux_acc) oa = ldv<V>(daux + e0 + e);
+      }
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        float g, da; bn_local_grad(a, d.v[j], zv.v[j], sc.v[j], sh.v[j], 0.f, g, da);
+        float g, da; bn_local_grad(a, d.v[j], zv.v[j], sc.v[j], sh.v[j], AUX ? xv.v[j] : 0.f, g, da);
         o.v[j] = k0.v[j] * (g - k1.v[j] - (zv.v[j] - mu.v[j]) * rs.v[j] * k2.v[j]);
+        if constexpr (AUX) oa.v[j] = (daux_acc ? oa.v[j] : 0.f) + da;
       }
       stv<V>(dz + e0 + e, o);
+      if constexpr (AUX) { if (daux) stv<V>(daux + e0 + e, oa); }
     }
     bar_arrive(&r.empty[s]);
     if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -195,17 +206,19 @@ __global__ void __launch_bounds__(bs::THREADS, 1) k_bn_stats_stream(const T* __r
   bn_tail_run(tl, out, C, t, CONSUMERS, true);
 }
 
-// ------------------------------------------------------------------ y = act(z*scale + shift)   (mode 0, dense in and out)
-template <typename T>
-__global__ void __launch_bounds__(bs::THREADS, 1) k_bn_act_fwd_stream(const T* __restrict__ z, BnArgs a, T* __restrict__ y, long long total, int C) {
+// ------------------------------------------------------------------ y = act(z*scale + shift) | gate | residual   (dense in and out)
+template <typename T, bool AUX>
+__global__ void __launch_bounds__(bs::THREADS, 1) k_bn_act_fwd_stream(const T* __restrict__ z, const T* __restrict__ aux, BnArgs a, T* __restrict__ y,
+                                                                     long long total, int C) {
   using namespace bs;
+  constexpr int NT = AUX ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   float* tail;
-  Ring r = make_ring<1>(smem_raw, &tail);
+  Ring r = make_ring<NT>(smem_raw, &tail);
   constexpr long long EPC = CHUNK_BYTES / sizeof(T);
   const long long nChunks = (total + EPC - 1) / EPC;
   if (threadIdx.x >= CONSUMERS) {
-    if (threadIdx.x == CONSUMERS) { const T* src[1] = {z}; produce<T, 1>(r, src, total, nChunks); }
+    if (threadIdx.x == CONSUMERS) { const T* src[2] = {z, aux}; produce<T, NT>(r, src, total, nChunks); }
     return;
   }
   const int t = threadIdx.x, c = (t * V) % C;
@@ -213,15 +226,19 @@ __global__ void __launch_bounds__(bs::THREADS, 1) k_bn_act_fwd_stream(const T* _
   int s = 0; uint32_t ph = 0;
   for (long long ch = blockIdx.x; ch < nChunks; ch += gridDim.x) {
     const long long e0 = ch * EPC; const int n = (int)(total - e0 < EPC ? total - e0 : EPC);
-    const T* sz = (const T*)(r.buf + (size_t)s * CHUNK_BYTES);
+    const T* sz = (const T*)(r.buf + ((size_t)s * NT + 0) * CHUNK_BYTES);
+    const T* sx = (const T*)(r.buf + ((size_t)s * NT + (NT - 1)) * CHUNK_BYTES);
     bar_wait(&r.full[s], ph);
 #pragma unroll 4
     for (int e = t * V; e < n; e += CONSUMERS * V) {
-      FVec<V> zv = ldv<V>(sz + e), o;
+      FVec<V> zv = ldv<V>(sz + e), o, xv;
+      if constexpr (AUX) xv = ldv<V>(sx + e);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
         float q = fmaf(zv.v[j], sc.v[j], sh.v[j]);
-        o.v[j] = a.act == 1 ? fmaxf(q, 0.f) : (a.act == 2 ? sigmoidf_(q) : q);
+        if constexpr (!AUX) o.v[j] = a.act == 1 ? fmaxf(q, 0.f) : (a.act == 2 ? sigmoidf_(q) : q);
+        else if (a.mode == 1) { float sg = sigmoidf_(q); o.v[j] = fmaf(sg, xv.v[j], xv.v[j]); }
+        else o.v[j] = fmaxf(fmaf(a.alpha, xv.v[j], q), 0.f);
       }
       stv<V>(y + e0 + e, o);
     }
@@ -234,7 +251,8 @@ static inline bool bn_stream_eligible(int mode, long long M, int C, long long cs
   static int off = -1;
   if (off < 0) { const char* e = getenv("EGM_NO_BN_STREAM"); off = (e && e[0] == '1') ? 1 : 0; }
   if (off) return false;
-  return mode == 0 && cstride == C && coff == 0 && C >= 8 && C <= 2048 && (C & (C - 1)) == 0 && M * (long long)C >= 4 * 8192;
+  (void)mode;    // the gate / residual modes stream their dense `aux` tensor as one more input
+  return cstride == C && coff == 0 && C >= 8 && C <= 2048 && (C & (C - 1)) == 0 && M * (long long)C >= 4 * 8192;
 }
 static inline int bn_stream_grid(long long total, size_t elem) {
   long long nChunks = (total * (long long)elem + bs::CHUNK_BYTES - 1) / bs::CHUNK_BYTES;

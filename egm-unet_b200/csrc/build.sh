@@ -10,7 +10,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 pids=()
 for f in "$HERE"/*.cu; do
   o="$OBJ/$(basename "${f%.cu}").o"
-  if [[ ! -f "$o" || "$f" -nt "$o" || "$HERE/common.cuh" -nt "$o" || "$HERE/../../include/egm_b200.h" -nt "$o" ]]; then
+  if [[ ! -f "$o" || "$f" -nt "$o" || "$HERE/common.cuh" -nt "$o" || -n "$(find "$HERE" -name "*.cuh" -newer "$o" -print -quit)" || "$HERE/../../include/egm_b200.h" -nt "$o" ]]; then
     ( "$NVCC" "${FLAGS[@]}" -c "$f" -o "$o" > "$o.log" 2>&1 || { cat "$o.log"; exit 1; } ) &
     pids+=($!)
   fi
