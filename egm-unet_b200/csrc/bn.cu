@@ -340,7 +340,7 @@ extern "C" int egm_bn_act_bwd_apply(const void* dy, long long dy_cstride, long l
                                     void* dz, void* daux, int daux_accumulate, int dtype, long long M, int C, void* stream) {
   if (M * C == 0) return EGM_OK;
   BnArgs a{scale, shift, mean, rstd, coef, act, mode, alpha};
-  if (mode == 0 && bn_stream_eligible(mode, M, C, dy_cstride, dy_coff)) {   // the aux modes are ALU-bound on 8 consumer warps (measured slower)
+  if (mode == 0 && bn_stream_eligible(mode, M, C, dy_cstride, dy_coff)) {   // the aux modes are ALU-bound in the consumer warps (measured slower)
     EGM_DISPATCH_DTYPE(dtype, {
       if (mode == 0) {
         const size_t smb = bs::ring_bytes<2>(0);
@@ -411,7 +411,7 @@ static bool bn_stats_stream_launch(const void* x, int dtype, long long M, int C,
 static bool bn_fwd_stream_launch(const void* z, long long zcs, long long zco, const BnArgs& a, const void* aux, void* y, long long ycs, long long yco, int dtype,
                                  long long M, int C, cudaStream_t st) {
   if (!bn_stream_eligible(a.mode, M, C, zcs, zco) || ycs != C || yco != 0 || (dtype != EGM_F32 && dtype != EGM_BF16)) return false;
-  if (a.mode == 1) return false;        // sigmoid gate: ALU-bound on 8 consumer warps, the grid-stride kernel is faster (measured)
+  if (a.mode == 1) return false;        // sigmoid gate: ALU-bound in the consumer warps, the grid-stride kernel is faster (measured)
   EGM_DISPATCH_DTYPE(dtype, {
     if (a.mode == 0) {
       const size_t smb = bs::ring_bytes<1>(0);

@@ -1,12 +1,12 @@
 // Streaming variants of the BatchNorm backward kernels for dense, power-of-two-channel tensors (the DoubleConv / BasicConv
 // majority).  A register-staged grid-stride loop cannot keep enough bytes in flight to cover HBM latency (ncu: 64 regs ->
 // 48 % occupancy, 35 % DRAM throughput, stalls = long_scoreboard).  Here a producer warp streams 16 KB chunks of every input
-// tensor into a 4-stage shared-memory ring with cp.async.bulk (1-D TMA) + mbarriers -- 128 KB in flight per SM -- and 256
-// consumer threads read them back with 16-byte LDS.  Included by bn.cu (shares BnArgs / bn_local_grad).
+// tensor into a 4-stage shared-memory ring with cp.async.bulk (1-D TMA) + mbarriers -- 128 KB in flight per SM -- and 512
+// consumer threads (16 warps: with 8 the kernels turn ALU-bound) read them back with 16-byte LDS.  Included by bn.cu (shares BnArgs / bn_local_grad).
 #pragma once
 
 namespace bs {
-constexpr int STAGES = 4, CHUNK_BYTES = 16384, CONSUMERS = 256, THREADS = CONSUMERS + 32, V = 8;
+constexpr int STAGES = 4, CHUNK_BYTES = 16384, CONSUMERS = 512, THREADS = CONSUMERS + 32, V = 8;
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_init(uint64_t* b, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n)); }
