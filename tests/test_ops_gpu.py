@@ -345,3 +345,23 @@ def test_conv_lifted_to_tc(case):
     assert rel_err(hs.pgrad(mc.weight), m.weight.grad) < 1e-2, "wgrad"
     if bias:
         assert rel_err(hs.pgrad(mc.bias), m.bias.grad) < 1e-2
+
+
+@pytest.mark.parametrize("shape", [(2, 80, 80, 32), (3, 37, 41, 16), (1, 120, 120, 64)])
+def test_gap_gmp_against_torch(shape):
+    """ChannelAttentionModule pooling (src/EGM-UNet.py:1183-1187): global average / max per (n, c) with the FIRST arg-max pixel."""
+    from egm_unet_b200 import abi
+    n, h, w, c = shape
+    torch.manual_seed(5)
+    x = torch.randn(n, h, w, c).to(torch.bfloat16)
+    x[:, ::7, ::5] = x.amax()                      # exact ties: the first pixel in scan order must win
+    xg = x.cuda()
+    avg, mx = torch.empty(n * c, device="cuda"), torch.empty(n * c, device="cuda")
+    arg = torch.empty(n * c, dtype=torch.int32, device="cuda")
+    scratch = torch.empty(n * c * 12 + 16, dtype=torch.uint8, device="cuda")
+    abi.call("gap_gmp", xg, avg, mx, arg, scratch, abi.DTYPE_CODE[torch.bfloat16], n, h * w, c)
+    xf = x.float().reshape(n, h * w, c)
+    assert torch.allclose(avg.cpu().reshape(n, c), xf.mean(1), rtol=1e-4, atol=1e-5)
+    assert torch.equal(mx.cpu().reshape(n, c), xf.amax(1))
+    first = (xf == xf.amax(1, keepdim=True)).float().argmax(1)          # first index of the maximum
+    assert torch.equal(arg.cpu().reshape(n, c).long(), first)
