@@ -384,8 +384,10 @@ __global__ void k_chan_sum(SumF<T, V> f, long long M, int C, double* out) {
 __global__ void k_d2f(const double* s, float* d, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) d[i] = (float)s[i]; }
 extern "C" int egm_channel_sum(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* scratch, float* out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(scratch, 0, sizeof(double) * C, st);
-  if (M > 0) {
+  cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st);
+  if (M > 0 && bn_stats_stream_launch(x, dtype, M, C, cstride, coff, scratch, BnTail{}, st)) {
+    // dense power-of-two tensors: the streaming statistics kernel (its sum-of-squares half of `scratch` is simply unused)
+  } else if (M > 0) {
     int v = egm_pick_vec(C, cstride, coff);
     int threads = reduce_threads(C, v); size_t sm = (size_t)(threads / (C / v)) * C * sizeof(float);
     EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_chan_sum<T, V><<<reduce_blocks(M, threads, C, v), threads, sm, st>>>(

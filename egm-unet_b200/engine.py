@@ -280,7 +280,7 @@ def conv2d(ctx: Ctx, x: Var, weight: torch.Tensor, bias: Optional[torch.Tensor],
                 call("unpack_conv_wgrad", dwp, ctx.grad_slot(wparam), co, cig, kh, kw, 0.0)
             if bias is not None:
                 gb = torch.empty(co, **ctx.f32) if bgrad_sink is not None else ctx.grad_slot(bparam)
-                call("channel_sum", dy, ctx.code, n * h * w, co, co, 0, ctx.f64(co), gb)
+                call("channel_sum", dy, ctx.code, n * h * w, co, co, 0, ctx.f64(2 * co), gb)
                 if bgrad_sink is not None:
                     bgrad_sink(gb)
             if x.needs_grad:
@@ -335,7 +335,7 @@ def _conv_tc_fwd_bwd(ctx, x, x_coff, cin, cinp, co, cop, kh, kw, dilation, wf, w
             wgrad_to(True)
             if bias_present:
                 gb = torch.empty(co, **ctx.f32) if bgrad_sink is not None else ctx.grad_slot(bparam)
-                call("channel_sum", dy, ctx.code, M, co, co, 0, ctx.f64(co), gb)
+                call("channel_sum", dy, ctx.code, M, co, co, 0, ctx.f64(2 * co), gb)
                 if bgrad_sink is not None:
                     bgrad_sink(gb)
             if x.needs_grad:

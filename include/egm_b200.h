@@ -103,6 +103,7 @@ int egm_bn_bwd_finalize(const double* sums, long long M, const float* gamma, con
 int egm_bn_act_bwd_apply(const void* dy, long long dy_cstride, long long dy_coff, const void* z, const float* scale, const float* shift,
                          const float* mean, const float* rstd, const float* coef, int act, int mode, const void* aux, float alpha,
                          void* dz, void* daux, int daux_accumulate, int dtype, long long M, int C, void* stream);
+/* out[c] = sum over pixels of x[., c] (conv bias gradient).  scratch: 2*C doubles. */
 int egm_channel_sum(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* scratch, float* out, void* stream);
 
 /* ---- down / up sampling (nn.MaxPool2d :908, nn.Upsample+F.pad+cat :931-947) ---- */
