@@ -162,6 +162,19 @@ int egm_sgd_step(float* params, const float* grads, float* momentum_buf, long lo
 int egm_eval_metrics(const float* logits, const long long* target, int N, int C, int H, int W, int ignore_index, long long* confmat,
                      double* dice_acc, void* stream);
 
+/* ---- CLIPSeg-ensemble fusion downstream of the UNet logits (csrc/ensemble.cu) -----------------------------
+ * Replaces, per validation image and alpha: F.interpolate(clip_logits, bilinear, align_corners=False) (eval_CLIPseg.py:885-888),
+ * fused = clip + alpha*unet, torch.argmax, cv2.resize(INTER_NEAREST) and ConfusionMatrix.update/compute inside
+ * search_best_alpha (eval_CLIPseg.py:656-748), and the final mask of eval_CLIPseg.py:901-912 / predict_CLIPseg.py:519-526.
+ * clip_logits [C,hc,wc] and unet_logits [C,H,W] are fp32 NCHW planes of ONE image, label is uint8 [Hl,Wl] (values >= C are
+ * ignored), confusion is [n_alpha][C][C] uint64 and is ACCUMULATED (zero it once, call per image); best = {alpha, mIoU}. */
+int egm_ensemble_confusion(const float* clip_logits, int hc, int wc, const float* unet_logits, int H, int W, const unsigned char* label, int Hl,
+                           int Wl, int num_classes, const double* alphas, int n_alpha, unsigned long long* confusion, void* stream);
+int egm_ensemble_best_alpha(const unsigned long long* confusion, const double* alphas, int n_alpha, int num_classes, float* miou, double* best,
+                            void* stream);
+int egm_ensemble_predict(const float* clip_logits, int hc, int wc, const float* unet_logits, int H, int W, int num_classes, float alpha,
+                         unsigned char* mask, int Ho, int Wo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
