@@ -175,6 +175,19 @@ int egm_ensemble_best_alpha(const unsigned long long* confusion, const double* a
 int egm_ensemble_predict(const float* clip_logits, int hc, int wc, const float* unet_logits, int H, int W, int num_classes, float alpha,
                          unsigned char* mask, int Ho, int Wo, void* stream);
 
+/* ---- input pipeline on the device (csrc/pipeline.cu) ------------------------------------------------------
+ * One decoded image -> one entry of the model-input batch: replaces transforms.py:30-110 (RandomResize [Pillow bilinear /
+ * nearest], flips, RandomCrop + pad_if_smaller, ToTensor, Normalize) and my_dataset.py:106-133 (mask / 255, collate_fn padding).
+ * img [H,W,3] / mask [H,W] are uint8 DEVICE buffers; the resample tables are DEVICE int32 arrays computed by the host exactly as
+ * Pillow's precompute_coeffs / ImagingScaleAffine do (egm_unet_b200.data): hmin/hcnt [rw], hk [rw][hks] (null when rw == W),
+ * vmin/vcnt [rh], vk [rh][vks] (null when rh == H), nnx [rw] / nny [rh] (null = identity).  The valid_h x valid_w region (the
+ * crop, or the resized image in eval mode) starts at (top, left) of the zero-padded resized image; the rest of the out_h x out_w
+ * plane gets the collate padding (0.0 / 255).  mean_std_host: 6 HOST floats.  out_img fp32 [3][out_h][out_w], out_tgt int64. */
+int egm_input_transform(const unsigned char* img, const unsigned char* mask, int H, int W, int rh, int rw, const int* hmin, const int* hcnt,
+                        const int* hk, int hks, const int* vmin, const int* vcnt, const int* vk, int vks, const int* nnx, const int* nny,
+                        int hflip, int vflip, int top, int left, int valid_h, int valid_w, int out_h, int out_w, const float* mean_std_host,
+                        float* out_img, long long* out_tgt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
