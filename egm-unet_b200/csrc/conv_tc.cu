@@ -745,11 +745,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
 // halo tile are fetched; one MMA per (16-pixel K-step, kernel row) covers the kw taps of that row at once: the B operand is
 // MN-major with N = kw*nch, whose N-atoms (one per tap) are the halo tile shifted by `dil` rows (LBO = dil*rowB) -- legal
 // because the swizzle is a function of the absolute smem address.  8*R MMAs and 2-3 TMA loads per tile instead of 72 / 12.
+// Row stacking (Cout chunk * kh <= 128, i.e. the 16/32-channel layers): an M=128 MMA costs the same whether 32 or 128 of its rows
+// are useful (its time is the (M+N) operand fetch), so the kh kernel rows share ONE MMA per K-step: with q = p + r*dil,
+//   dW[r][s] = sum_p dY[p] x[p + (r*dil - pad, s*dil - pad)] = sum_q dY[q - r*dil rows] x[q + (-pad, s*dil - pad)],
+// i.e. the B operand is the same X window for every r and the A operand gets one atom per r holding the dY tile fetched r*dil rows
+// higher (TMA zero-fills rows outside the image; the tile range is extended by (kh-1)*dil rows so every dY row meets every r).
 struct WgradHaloParams {
   int N, H, W, Cin, Cout, kh, kw, dil, pad;
   int tilesH, tilesW, numTiles;
   int coChunks, ciChunks, rowGroups, rowsPerGroup, splits, tilesPerSplit;
   int mch, nch, mAtoms, aAtomCh, aAtomBytes, aBytes, rowA, rowB, haloW, haloH, haloBytes, haloStride, stageBytes, stages, tmemCols;
+  int stack;   // 1: the kh kernel rows are stacked along M (narrow Cout): atom j of the A operand = dY shifted up by j*dil rows
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
@@ -793,9 +799,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_co
       uint8_t* st = smem + (size_t)s * p.stageBytes;
       mbar_wait(&empty[s], ph ^ 1);
       if (leader) {
-        mbar_expect_tx(&full[s], (uint32_t)(p.mAtoms * p.aAtomBytes + p.haloBytes));
-        for (int a = 0; a < p.mAtoms; ++a)
-          tma_load_4d(st + (size_t)a * p.aAtomBytes, &tmDY, &full[s], coc * p.mch + a * p.aAtomCh, w0, h0, n);
+        if (p.stack) {
+          mbar_expect_tx(&full[s], (uint32_t)(p.kh * p.aAtomBytes + p.haloBytes));
+          for (int j = 0; j < p.kh; ++j) tma_load_4d(st + (size_t)j * p.aAtomBytes, &tmDY, &full[s], coc * p.mch, w0, h0 - j * p.dil, n);
+        } else {
+          mbar_expect_tx(&full[s], (uint32_t)(p.mAtoms * p.aAtomBytes + p.haloBytes));
+          for (int a = 0; a < p.mAtoms; ++a)
+            tma_load_4d(st + (size_t)a * p.aAtomBytes, &tmDY, &full[s], coc * p.mch + a * p.aAtomCh, w0, h0, n);
+        }
         tma_load_4d(st + p.aBytes, &tmX, &full[s], cic * p.nch, w0 - p.pad, h0 - p.pad, n);
       }
       if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -820,7 +831,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_co
           const uint64_t ad = ad0 + k * kA;
           uint64_t bd = bd0 + k * kB;
           uint32_t dcol = tmem_base;
-          for (int r = 0; r < R; ++r) { umma_bf16(dcol, ad, bd, idesc, accf); bd += rB; dcol += (uint32_t)nN; }
+          if (p.stack) umma_bf16(dcol, ad, bd, idesc, accf);            // all kernel rows at once (stacked along M)
+          else for (int r = 0; r < R; ++r) { umma_bf16(dcol, ad, bd, idesc, accf); bd += rB; dcol += (uint32_t)nN; }
           accf = 1;
         }
         umma_commit(&empty[s]);
@@ -833,16 +845,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_co
     __syncwarp();
   } else if (tileBeg < tileEnd) {
     const int q = warp & 3;
-    const int co_local = q * 32 + lane;
+    const int m = q * 32 + lane;                          // accumulator row (TMEM lane)
     mbar_wait(tfull, 0);
     tc_fence_after();
-    const int co = coc * p.mch + co_local;
-    const bool valid = co_local < p.mch && co < p.Cout;
-    if (q * 32 < p.mch) {
-      for (int r = 0; r < R; ++r)
+    if (p.stack) {
+      // rows m = j*mch + co: kernel row j, output channel co; columns = (s, ci) of the single accumulator
+      const int j = m / p.mch, co = coc * p.mch + (m - j * p.mch);
+      const bool valid = j < p.kh && co < p.Cout;
+      if (q * 32 < p.kh * p.mch) {
         for (int sidx = 0; sidx < p.kw; ++sidx) {
-          const int tap = (r0 + r) * p.kw + sidx;
-          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * nN + sidx * p.nch);
+          const int tap = j * p.kw + sidx;
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sidx * p.nch);
           for (int c = 0; c < p.nch; c += 16) {
             uint32_t v[16];
             tmem_ld16(ta + c, v);
@@ -854,6 +867,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_co
             }
           }
         }
+      }
+    } else {
+      const int co_local = m;
+      const int co = coc * p.mch + co_local;
+      const bool valid = co_local < p.mch && co < p.Cout;
+      if (q * 32 < p.mch) {
+        for (int r = 0; r < R; ++r)
+          for (int sidx = 0; sidx < p.kw; ++sidx) {
+            const int tap = (r0 + r) * p.kw + sidx;
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * nN + sidx * p.nch);
+            for (int c = 0; c < p.nch; c += 16) {
+              uint32_t v[16];
+              tmem_ld16(ta + c, v);
+              tmem_ld_wait();
+              if (valid) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (cic * p.nch + c + i < p.Cin) atomicAdd(dwp + ((long long)tap * p.Cin + cic * p.nch + c + i) * p.Cout + co, __uint_as_float(v[i]));
+              }
+            }
+          }
+      }
     }
   }
   tc_fence_before();
@@ -861,6 +896,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_co
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmemCols); }
 }
 
+static bool wgrad_stack_disabled() { static int v = -1; if (v < 0) { const char* e = getenv("EGM_NO_WGRAD_STACK"); v = (e && e[0] == '1') ? 1 : 0; } return v == 1; }
 static bool wgrad_halo_eligible(int Cin, int Cout, int kh, int kw, int dil) {
   if (halo_disabled()) return false;
   int pad = dil * (kh - 1) / 2;
@@ -885,6 +921,11 @@ static int launch_wgrad_halo(const NhwcView& xv, const NhwcView& dyv, float* dwp
   p.rowsPerGroup = 512 / perRow; if (p.rowsPerGroup > kh) p.rowsPerGroup = kh;
   p.rowGroups = cdiv(kh, p.rowsPerGroup);
   p.tmemCols = pow2_cols(p.rowsPerGroup * perRow);
+  p.stack = (kh > 1 && p.mAtoms == 1 && p.mch * kh <= 128 && !wgrad_stack_disabled()) ? 1 : 0;
+  if (p.stack) {                                         // one accumulator; q rows cover [0, H + (kh-1)*dil)
+    p.rowsPerGroup = kh; p.rowGroups = 1; p.tmemCols = pow2_cols(perRow);
+    p.tilesH = cdiv(H + (kh - 1) * dil, HT_H); p.numTiles = N * p.tilesH * p.tilesW;
+  }
   p.coChunks = cdiv(Cout, p.mch); p.ciChunks = cdiv(Cin, p.nch);
   long long units = (long long)p.rowGroups * p.coChunks * p.ciChunks;
   long long want = ((long long)egm_num_sms() * 2 + units - 1) / units;
