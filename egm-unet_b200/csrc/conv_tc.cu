@@ -281,24 +281,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       tc_fence_after();
       const uint32_t d = tmem_base + (uint32_t)(acc * p.accCols);
       uint32_t accf = 0;
-      for (int it = 0; it < kIters; ++it) {
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        if (leader) {
-          const uint64_t ad = adBase + (uint64_t)(s * aStep), bd = bdBase + (uint64_t)((p.wres ? it : s) * bStep);
-          if (ksteps == 4) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, accf); accf = 1; }
-          } else if (ksteps == 2) {
-#pragma unroll
-            for (int k = 0; k < 2; ++k) { umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, accf); accf = 1; }
-          } else { umma_bf16(d, ad, bd, idesc, accf); }
-          umma_commit(&empty[s]);
-        }
-        accf = 1;
-        __syncwarp();
-        if (++s == p.stages) { s = 0; ph ^= 1; }
+      // one copy of the K loop per K-steps-per-chunk value: no data-dependent branch between two MMAs of the issuing thread
+#define EGM_V1_KLOOP(KS)                                                                                              \
+      for (int it = 0; it < kIters; ++it) {                                                                            \
+        mbar_wait(&full[s], ph);                                                                                       \
+        tc_fence_after();                                                                                              \
+        if (leader) {                                                                                                  \
+          const uint64_t ad = adBase + (uint64_t)(s * aStep), bd = bdBase + (uint64_t)((p.wres ? it : s) * bStep);    \
+          _Pragma("unroll") for (int k = 0; k < KS; ++k) { umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, accf); accf = 1; } \
+          umma_commit(&empty[s]);                                                                                      \
+        }                                                                                                              \
+        accf = 1;                                                                                                      \
+        __syncwarp();                                                                                                  \
+        if (++s == p.stages) { s = 0; ph ^= 1; }                                                                       \
       }
+      if (ksteps == 4) { EGM_V1_KLOOP(4) } else if (ksteps == 2) { EGM_V1_KLOOP(2) } else { EGM_V1_KLOOP(1) }
+#undef EGM_V1_KLOOP
       if (leader) umma_commit(&tfull[acc]);
       __syncwarp();
       if (++acc == 2) { acc = 0; aph ^= 1; }
@@ -446,6 +444,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
       if (leader) {
         uint32_t accf = 0;
         uint64_t bd = bd0, adr = ad0;
+        // 3x3 kernels (the DoubleConv layers): mode decided once per tile, the 9 taps are straight-line code -- every branch in this
+        // single-thread issue path costs about as much as an MMA
+        if (p.kh == 1 && !(p.exp & 4)) {
+          if (ksteps == 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d, ad0 + 2 * k, bd0 + 2 * k, idesc, k ? 1u : 0u);
+          } else if (ksteps == 2) { umma_bf16(d, ad0, bd0, idesc, 0u); umma_bf16(d, ad0 + 2, bd0 + 2, idesc, 1u); }
+          else umma_bf16(d, ad0, bd0, idesc, 0u);
+        } else if (p.kh == 3 && p.kw == 3 && !(p.exp & 4)) {
+          if (ksteps == 2) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              uint64_t ad = adr;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                umma_bf16(d, ad, bd, idesc, (r | c) ? 1u : 0u); umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+                ad += aCol; bd += bTap;
+              }
+              adr += aRow;
+            }
+          } else if (ksteps == 4) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              uint64_t ad = adr;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                umma_bf16(d, ad, bd, idesc, (r | c) ? 1u : 0u);
+#pragma unroll
+                for (int k = 1; k < 4; ++k) umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, 1u);
+                ad += aCol; bd += bTap;
+              }
+              adr += aRow;
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              uint64_t ad = adr;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) { umma_bf16(d, ad, bd, idesc, (r | c) ? 1u : 0u); ad += aCol; bd += bTap; }
+              adr += aRow;
+            }
+          }
+        } else
         for (int r = 0; r < ((p.exp & 4) ? 0 : p.kh); ++r) {
           uint64_t ad = adr;
           for (int c = 0; c < p.kw; ++c) {
@@ -755,7 +796,8 @@ struct WgradHaloParams {
   int tilesH, tilesW, numTiles;
   int coChunks, ciChunks, rowGroups, rowsPerGroup, splits, tilesPerSplit;
   int mch, nch, mAtoms, aAtomCh, aAtomBytes, aBytes, rowA, rowB, haloW, haloH, haloBytes, haloStride, stageBytes, stages, tmemCols;
-  int stack;   // 1: the kh kernel rows are stacked along M (narrow Cout): atom j of the A operand = dY shifted up by j*dil rows
+  int stack;   // 1: kernel rows are stacked along M (Cout chunk <= 64): atom j of the A operand = dY shifted up by j*dil rows
+  int rpm, nGroups;   // stacked mode: kernel rows per MMA (128 / mch) and MMAs per K-step (ceil(kh / rpm)), one accumulator each
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
@@ -818,6 +860,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_co
     const uint32_t kA = (uint32_t)(16 * p.rowA) >> 4;                 // A advance per 16-pixel K step (16-byte units)
     const uint32_t kB = (uint32_t)(2 * p.haloW * p.rowB) >> 4;        // B advance per K step: two halo rows
     const uint32_t rB = (uint32_t)(p.dil * p.haloW * p.rowB) >> 4;    // B advance per kernel row
+    const uint32_t gA = (uint32_t)(p.rpm * p.aAtomBytes) >> 4;         // stacked mode: A advance per group of rpm kernel rows
     int s = 0; uint32_t ph = 0; uint32_t accf = 0;
     for (int tile = tileBeg; tile < tileEnd; ++tile) {
       mbar_wait(&full[s], ph);
@@ -826,14 +869,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_co
         const uint32_t a0 = smem_u32(smem + (size_t)s * p.stageBytes);
         const uint64_t ad0 = umma_desc(a0, (uint32_t)p.aAtomBytes, 8u * p.rowA, layA);
         const uint64_t bd0 = umma_desc(a0 + p.aBytes, (uint32_t)(p.dil * p.rowB), (uint32_t)(p.haloW * p.rowB), layB) + (uint64_t)(r0 * rB);
+        // Every branch inside this single-thread issue loop costs about as much as an MMA (measured: +30..45 % on 32->32@480^2),
+        // so the mode is decided once per tile and the stacked cases are straight-line code.
+        if (p.stack && p.nGroups == 1) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { umma_bf16(tmem_base, ad0 + k * kA, bd0 + k * kB, idesc, accf); accf = 1; }
+        } else if (p.stack && p.nGroups == 2) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            umma_bf16(tmem_base, ad0 + k * kA, bd0 + k * kB, idesc, accf);
+            umma_bf16(tmem_base + (uint32_t)nN, ad0 + k * kA + gA, bd0 + k * kB, idesc, accf);
+            accf = 1;
+          }
+        } else if (p.stack) {
 #pragma unroll 1
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t ad = ad0 + k * kA;
-          uint64_t bd = bd0 + k * kB;
-          uint32_t dcol = tmem_base;
-          if (p.stack) umma_bf16(dcol, ad, bd, idesc, accf);            // all kernel rows at once (stacked along M)
-          else for (int r = 0; r < R; ++r) { umma_bf16(dcol, ad, bd, idesc, accf); bd += rB; dcol += (uint32_t)nN; }
-          accf = 1;
+          for (int k = 0; k < 8; ++k) {
+            for (int g = 0; g < p.nGroups; ++g) umma_bf16(tmem_base + (uint32_t)(g * nN), ad0 + k * kA + (uint64_t)g * gA, bd0 + k * kB, idesc, accf);
+            accf = 1;
+          }
+        } else if (R == 3) {                                             // 3x3 kernels, wide Cout: 24 MMAs, straight-line
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) umma_bf16(tmem_base + (uint32_t)(r * nN), ad0 + k * kA, bd0 + k * kB + (uint64_t)r * rB, idesc, accf);
+            accf = 1;
+          }
+        } else {
+#pragma unroll 1
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t ad = ad0 + k * kA;
+            uint64_t bd = bd0 + k * kB;
+            uint32_t dcol = tmem_base;
+            for (int r = 0; r < R; ++r) { umma_bf16(dcol, ad, bd, idesc, accf); bd += rB; dcol += (uint32_t)nN; }
+            accf = 1;
+          }
         }
         umma_commit(&empty[s]);
       }
@@ -849,21 +918,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_co
     mbar_wait(tfull, 0);
     tc_fence_after();
     if (p.stack) {
-      // rows m = j*mch + co: kernel row j, output channel co; columns = (s, ci) of the single accumulator
-      const int j = m / p.mch, co = coc * p.mch + (m - j * p.mch);
-      const bool valid = j < p.kh && co < p.Cout;
-      if (q * 32 < p.kh * p.mch) {
-        for (int sidx = 0; sidx < p.kw; ++sidx) {
-          const int tap = j * p.kw + sidx;
-          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sidx * p.nch);
-          for (int c = 0; c < p.nch; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(ta + c, v);
-            tmem_ld_wait();
-            if (valid) {
+      // accumulator g, row m = jl*mch + co: kernel row j = g*rpm + jl, output channel co; columns = (s, ci)
+      const int jl = m / p.mch, co = coc * p.mch + (m - jl * p.mch);
+      if (q * 32 < p.rpm * p.mch) {
+        for (int g = 0; g < p.nGroups; ++g) {
+          const int j = g * p.rpm + jl;
+          const bool valid = jl < p.rpm && j < p.kh && co < p.Cout;
+          for (int sidx = 0; sidx < p.kw; ++sidx) {
+            const int tap = j * p.kw + sidx;
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * nN + sidx * p.nch);
+            for (int c = 0; c < p.nch; c += 16) {
+              uint32_t v[16];
+              tmem_ld16(ta + c, v);
+              tmem_ld_wait();
+              if (valid) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (cic * p.nch + c + i < p.Cin) atomicAdd(dwp + ((long long)tap * p.Cin + cic * p.nch + c + i) * p.Cout + co, __uint_as_float(v[i]));
+                for (int i = 0; i < 16; ++i)
+                  if (cic * p.nch + c + i < p.Cin) atomicAdd(dwp + ((long long)tap * p.Cin + cic * p.nch + c + i) * p.Cout + co, __uint_as_float(v[i]));
+              }
             }
           }
         }
@@ -921,10 +993,16 @@ static int launch_wgrad_halo(const NhwcView& xv, const NhwcView& dyv, float* dwp
   p.rowsPerGroup = 512 / perRow; if (p.rowsPerGroup > kh) p.rowsPerGroup = kh;
   p.rowGroups = cdiv(kh, p.rowsPerGroup);
   p.tmemCols = pow2_cols(p.rowsPerGroup * perRow);
-  p.stack = (kh > 1 && p.mAtoms == 1 && p.mch * kh <= 128 && !wgrad_stack_disabled()) ? 1 : 0;
-  if (p.stack) {                                         // one accumulator; q rows cover [0, H + (kh-1)*dil)
-    p.rowsPerGroup = kh; p.rowGroups = 1; p.tmemCols = pow2_cols(perRow);
+  p.rpm = 128 / p.mch; if (p.rpm > kh) p.rpm = kh;
+  p.nGroups = cdiv(kh, p.rpm);
+  p.stack = (kh > 1 && p.mAtoms == 1 && p.rpm >= 2 && p.nGroups * perRow <= 512 && !wgrad_stack_disabled()) ? 1 : 0;
+  if (p.stack) {                                         // nGroups accumulators; q rows cover [0, H + (kh-1)*dil)
+    p.rowsPerGroup = kh; p.rowGroups = 1; p.tmemCols = pow2_cols(p.nGroups * perRow);
     p.tilesH = cdiv(H + (kh - 1) * dil, HT_H); p.numTiles = N * p.tilesH * p.tilesW;
+    const int atoms = p.nGroups * (128 / p.aAtomCh);    // every MMA addresses 128/aAtomCh atoms from its first one
+    p.aBytes = atoms * p.aAtomBytes;
+    p.stageBytes = p.aBytes + p.haloStride;
+    p.stages = (200 * 1024) / p.stageBytes; if (p.stages > 6) p.stages = 6; if (p.stages < 2) p.stages = 2;
   }
   p.coChunks = cdiv(Cout, p.mch); p.ciChunks = cdiv(Cin, p.nch);
   long long units = (long long)p.rowGroups * p.coChunks * p.ciChunks;
