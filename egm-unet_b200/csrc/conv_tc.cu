@@ -452,6 +452,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
             for (int k = 0; k < 4; ++k) umma_bf16(d, ad0 + 2 * k, bd0 + 2 * k, idesc, k ? 1u : 0u);
           } else if (ksteps == 2) { umma_bf16(d, ad0, bd0, idesc, 0u); umma_bf16(d, ad0 + 2, bd0 + 2, idesc, 1u); }
           else umma_bf16(d, ad0, bd0, idesc, 0u);
+        } else if (p.kh == 7 && p.kw == 7 && ksteps <= 2 && !(p.exp & 4)) {          // merged FusionConv 7x7 (16 / 32 channels)
+          if (ksteps == 1) {
+#pragma unroll
+            for (int r = 0; r < 7; ++r) {
+              uint64_t ad = adr;
+#pragma unroll
+              for (int c = 0; c < 7; ++c) { umma_bf16(d, ad, bd, idesc, (r | c) ? 1u : 0u); ad += aCol; bd += bTap; }
+              adr += aRow;
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < 7; ++r) {
+              uint64_t ad = adr;
+#pragma unroll
+              for (int c = 0; c < 7; ++c) {
+                umma_bf16(d, ad, bd, idesc, (r | c) ? 1u : 0u); umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+                ad += aCol; bd += bTap;
+              }
+              adr += aRow;
+            }
+          }
         } else if (p.kh == 3 && p.kw == 3 && !(p.exp & 4)) {
           if (ksteps == 2) {
 #pragma unroll
@@ -736,6 +757,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
         const uint64_t ad0 = umma_desc(a0, (uint32_t)p.aAtomBytes, 8u * rowA, layA);
         uint64_t bdj = umma_desc(a0 + p.aBytes, (uint32_t)p.bTileBytes, 8u * rowB, layB);
         uint32_t dcol = tmem_base;
+        if (nt == WG_TAPS) {                               // the common case as straight-line code (no branch between MMAs)
+#pragma unroll
+          for (int j = 0; j < WG_TAPS; ++j) {
+#pragma unroll
+            for (int k = 0; k < TILE_PIX / 16; ++k)
+              umma_bf16(tmem_base + (uint32_t)(j * p.nch), ad0 + k * kA, bdj + (uint64_t)j * jB + k * kB, idesc, k ? 1u : accf);   // 16 pixels per MMA
+          }
+        } else
         for (int j = 0; j < nt; ++j) {
           uint32_t af = accf;
 #pragma unroll
