@@ -916,6 +916,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_co
             for (int g = 0; g < p.nGroups; ++g) umma_bf16(tmem_base + (uint32_t)(g * nN), ad0 + k * kA + (uint64_t)g * gA, bd0 + k * kB, idesc, accf);
             accf = 1;
           }
+        } else if (R == 1) {                                             // 1x1 kernels (or one kernel row per unit)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { umma_bf16(tmem_base, ad0 + k * kA, bd0 + k * kB, idesc, accf); accf = 1; }
         } else if (R == 3) {                                             // 3x3 kernels, wide Cout: 24 MMAs, straight-line
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
