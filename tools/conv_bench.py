@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--kind", default="both")
     ap.add_argument("--n", type=int, default=16)
     ap.add_argument("--k", type=int, default=3)
+    ap.add_argument("--dil", type=int, default=1)
     a = ap.parse_args()
     shapes = [tuple(int(v) for v in s.split(",")) for s in a.shapes] if a.shapes else LAYERS
     dev = torch.device("cuda")
@@ -44,9 +45,9 @@ def main():
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 if kind == "fwd":
-                    call("conv2d_tc", x, wf, None, y, n, hw, hw, cin, cout, k, k, 1)
+                    call("conv2d_tc", x, wf, None, y, n, hw, hw, cin, cout, k, k, a.dil)
                 else:
-                    call("conv2d_wgrad_tc", x, dy, dw, n, hw, hw, cin, cout, k, k, 1)
+                    call("conv2d_wgrad_tc", x, dy, dw, n, hw, hw, cin, cout, k, k, a.dil)
                 e1.record()
                 torch.cuda.synchronize()
                 if it:
