@@ -12,19 +12,25 @@ __global__ void k_highpass3(const T* __restrict__ in, T* __restrict__ out, int N
   const NhwcIndexer ix(CV, W, H, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const Nhwc4 e = ix(i); const int c = e.cv * V, w = e.w, h = e.h; const long long p = e.p;
-    FVec<V> s, ctr;
+    // all 9 neighbour loads are issued unconditionally (out-of-image neighbours are clamped onto the centre row / column and
+    // masked afterwards): predicated loads were consumed one by one -- ncu showed 9 separate long-scoreboard stalls per vector
+    const bool vr[3] = {h > 0, true, h < H - 1}, vc[3] = {w > 0, true, w < W - 1};
+    const long long ro[3] = {vr[0] ? -(long long)W : 0, 0, vr[2] ? (long long)W : 0}, cofs[3] = {vc[0] ? -1 : 0, 0, vc[2] ? 1 : 0};
+    FVec<V> t[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) t[a][b] = ldv<V>(in + (p + ro[a] + cofs[b]) * C + c);
+    FVec<V> s, ctr = t[1][1];
 #pragma unroll
     for (int j = 0; j < V; ++j) s.v[j] = 0.f;
 #pragma unroll
-    for (int a = -1; a <= 1; ++a)
+    for (int a = 0; a < 3; ++a)
 #pragma unroll
-      for (int b = -1; b <= 1; ++b) {
-        int hh = h + a, ww = w + b;
-        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-        FVec<V> t = ldv<V>(in + (p + (long long)a * W + b) * C + c);
+      for (int b = 0; b < 3; ++b) {
+        const float m = (vr[a] && vc[b]) ? 1.f : 0.f;
 #pragma unroll
-        for (int j = 0; j < V; ++j) s.v[j] += t.v[j];
-        if (a == 0 && b == 0) ctr = t;
+        for (int j = 0; j < V; ++j) s.v[j] += m * t[a][b].v[j];
       }
     FVec<V> o;
     if (accumulate) o = ldv<V>(out + p * C + c);

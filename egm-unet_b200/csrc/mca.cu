@@ -184,19 +184,24 @@ __global__ void k_mca_d2(const T* __restrict__ u, T* __restrict__ d2, int N, int
   const NhwcIndexer ix(CV, W, H, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const Nhwc4 e = ix(i); const int c = e.cv * V, w = e.w, h = e.h; const long long p = e.p;
-    FVec<V> s, ctr;
+    // unconditional neighbour loads (clamped + masked): all 9 in flight at once instead of 9 dependent round trips
+    const bool vr[3] = {h > 0, true, h < H - 1}, vc[3] = {w > 0, true, w < W - 1};
+    const long long ro[3] = {vr[0] ? -(long long)W : 0, 0, vr[2] ? (long long)W : 0}, cofs[3] = {vc[0] ? -1 : 0, 0, vc[2] ? 1 : 0};
+    FVec<V> t[3][3];
 #pragma unroll
-    for (int j = 0; j < V; ++j) { s.v[j] = 0.f; ctr.v[j] = 0.f; }
+    for (int a = 0; a < 3; ++a)
 #pragma unroll
-    for (int a = -1; a <= 1; ++a)
+      for (int b = 0; b < 3; ++b) t[a][b] = ldv<V>(u + (p + ro[a] + cofs[b]) * C + c);
+    FVec<V> s, ctr = t[1][1];
 #pragma unroll
-      for (int b = -1; b <= 1; ++b) {
-        int hh = h + a, ww = w + b;
-        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-        FVec<V> t = ldv<V>(u + (p + (long long)a * W + b) * C + c);
+    for (int j = 0; j < V; ++j) s.v[j] = 0.f;
 #pragma unroll
-        for (int j = 0; j < V; ++j) s.v[j] += t.v[j];
-        if (a == 0 && b == 0) ctr = t;
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const float m = (vr[a] && vc[b]) ? 1.f : 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) s.v[j] += m * t[a][b].v[j];
       }
     FVec<V> o;
 #pragma unroll
@@ -213,22 +218,25 @@ __global__ void k_mca_out(const T* __restrict__ u, const T* __restrict__ d2, T* 
     float mx[V], mn[V], var[V], uc[V]; int amx[V], amn[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) { mx[j] = -INFINITY; mn[j] = INFINITY; var[j] = 0.f; uc[j] = 0.f; amx[j] = 4; amn[j] = 4; }
+    const bool vr[3] = {h > 0, true, h < H - 1}, vc[3] = {w > 0, true, w < W - 1};
+    const long long ro[3] = {vr[0] ? -(long long)W : 0, 0, vr[2] ? (long long)W : 0}, cofs[3] = {vc[0] ? -1 : 0, 0, vc[2] ? 1 : 0};
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
+    for (int a = 0; a < 3; ++a) {
+      FVec<V> tu[3], td[3];                              // one row of neighbours at a time: 6 unconditional loads in flight
+#pragma unroll
+      for (int b = 0; b < 3; ++b) { const long long off = (p + ro[a] + cofs[b]) * C + c; tu[b] = ldv<V>(u + off); td[b] = ldv<V>(d2 + off); }
 #pragma unroll
       for (int b = 0; b < 3; ++b) {
-        int hh = h + a - 1, ww = w + b - 1;
-        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-        long long off = (p + (long long)(a - 1) * W + (b - 1)) * C + c;
-        FVec<V> t = ldv<V>(u + off), d = ldv<V>(d2 + off);
+        if (!(vr[a] && vc[b])) continue;
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-          if (t.v[j] > mx[j]) { mx[j] = t.v[j]; amx[j] = a * 3 + b; }
-          if (t.v[j] < mn[j]) { mn[j] = t.v[j]; amn[j] = a * 3 + b; }
-          var[j] += d.v[j];
-          if (a == 1 && b == 1) uc[j] = t.v[j];
+          if (tu[b].v[j] > mx[j]) { mx[j] = tu[b].v[j]; amx[j] = a * 3 + b; }
+          if (tu[b].v[j] < mn[j]) { mn[j] = tu[b].v[j]; amn[j] = a * 3 + b; }
+          var[j] += td[b].v[j];
+          if (a == 1 && b == 1) uc[j] = tu[b].v[j];
         }
       }
+    }
     FVec<V> o;
     const T* up = u + p * C;
 #pragma unroll
@@ -281,17 +289,28 @@ __global__ void __launch_bounds__(256) k_mca_bwd_e(const T* __restrict__ x, cons
     FVec<V> gcv = ldv<V>(g.gc + n * g.C + c), su, sd, uc;
 #pragma unroll
     for (int j = 0; j < V; ++j) { su.v[j] = 0.f; sd.v[j] = 0.f; uc.v[j] = 0.f; }
+    const bool vr[3] = {h > 0, true, h < g.H - 1}, vc[3] = {w > 0, true, w < g.W - 1};
+    const int hr[3] = {vr[0] ? h - 1 : h, h, vr[2] ? h + 1 : h}, wc[3] = {vc[0] ? w - 1 : w, w, vc[2] ? w + 1 : w};
 #pragma unroll
-    for (int a = -1; a <= 1; ++a)
+    for (int a = 0; a < 3; ++a) {
+      FVec<V> tx[3], td[3];                              // one row of neighbours at a time, loads unconditional (clamped + masked)
+      const float gh = g.gh[n * g.H + hr[a]];
 #pragma unroll
-      for (int b = -1; b <= 1; ++b) {
-        int hh = h + a, ww = w + b;
-        if (hh < 0 || hh >= g.H || ww < 0 || ww >= g.W) continue;
-        FVec<V> t = mca_u<T, V>(x, g, n, hh, ww, c, gcv);
-        FVec<V> d = ldv<V>(dy + (((long long)n * g.H + hh) * g.W + ww) * g.C + c);
-#pragma unroll
-        for (int j = 0; j < V; ++j) { su.v[j] += t.v[j]; sd.v[j] += d.v[j]; if (a == 0 && b == 0) uc.v[j] = t.v[j]; }
+      for (int b = 0; b < 3; ++b) {
+        const long long off = (((long long)n * g.H + hr[a]) * g.W + wc[b]) * g.C + c;
+        tx[b] = ldv<V>(x + off); td[b] = ldv<V>(dy + off);
       }
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        if (!(vr[a] && vc[b])) continue;
+        const float sgate = gh + g.gw[n * g.W + wc[b]];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float uu = tx[b].v[j] * ((gcv.v[j] + sgate) * (1.f / 3.f));
+          su.v[j] += uu; sd.v[j] += td[b].v[j]; if (a == 1 && b == 1) uc.v[j] = uu;
+        }
+      }
+    }
     FVec<V> o;
 #pragma unroll
     for (int j = 0; j < V; ++j) o.v[j] = 2.f * (uc.v[j] - su.v[j] * (1.f / 9.f)) * (0.2f / 9.f) * sd.v[j];
@@ -310,27 +329,33 @@ __global__ void __launch_bounds__(256) k_mca_bwd_du(const T* __restrict__ dy, co
     FVec<V> o, se;
 #pragma unroll
     for (int j = 0; j < V; ++j) { o.v[j] = 0.f; se.v[j] = 0.f; }
+    const bool vr[3] = {h > 0, true, h < g.H - 1}, vc[3] = {w > 0, true, w < g.W - 1};
+    const int hr[3] = {vr[0] ? h - 1 : h, h, vr[2] ? h + 1 : h}, wc[3] = {vc[0] ? w - 1 : w, w, vc[2] ? w + 1 : w};
 #pragma unroll
-    for (int a = -1; a <= 1; ++a)
+    for (int a = -1; a <= 1; ++a) {
+      FVec<V> dv[3], ev[3]; unsigned char codes[3][V];   // one row of neighbours at a time, loads unconditional (clamped + masked)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const long long off = (((long long)n * g.H + hr[a + 1]) * g.W + wc[b]) * g.C + c;
+        dv[b] = ldv<V>(dy + off); ev[b] = ldv<V>(E + off);
+        if constexpr (V == 8) *reinterpret_cast<uint2*>(codes[b]) = *reinterpret_cast<const uint2*>(idx + off);
+        else if constexpr (V == 4) *reinterpret_cast<unsigned int*>(codes[b]) = *reinterpret_cast<const unsigned int*>(idx + off);
+        else { for (int j = 0; j < V; ++j) codes[b][j] = idx[off + j]; }
+      }
 #pragma unroll
       for (int b = -1; b <= 1; ++b) {
-        int hh = h + a, ww = w + b;
-        if (hh < 0 || hh >= g.H || ww < 0 || ww >= g.W) continue;
-        long long off = (((long long)n * g.H + hh) * g.W + ww) * g.C + c;
-        FVec<V> d = ldv<V>(dy + off), e = ldv<V>(E + off);
-        int want = (1 - a) * 3 + (1 - b);          // position of (h,w) inside the window centred at (hh,ww)
-        unsigned char codes[V];                    // V arg-index bytes in one aligned load
-        if constexpr (V == 8) *reinterpret_cast<uint2*>(codes) = *reinterpret_cast<const uint2*>(idx + off);
-        else if constexpr (V == 4) *reinterpret_cast<unsigned int*>(codes) = *reinterpret_cast<const unsigned int*>(idx + off);
-        else { for (int j = 0; j < V; ++j) codes[j] = idx[off + j]; }
+        if (!(vr[a + 1] && vc[b + 1])) continue;
+        const int want = (1 - a) * 3 + (1 - b);          // position of (h,w) inside the window centred at (hh,ww)
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-          unsigned char code = codes[j];
-          float r = ((code & 15) == want ? d.v[j] : 0.f) - ((code >> 4) == want ? d.v[j] : 0.f);
-          o.v[j] += 0.2f * r; se.v[j] += e.v[j];
-          if (a == 0 && b == 0) o.v[j] += 0.51f * d.v[j] + e.v[j];
+          const unsigned char code = codes[b + 1][j];
+          const float d = dv[b + 1].v[j];
+          float r = ((code & 15) == want ? d : 0.f) - ((code >> 4) == want ? d : 0.f);
+          o.v[j] += 0.2f * r; se.v[j] += ev[b + 1].v[j];
+          if (a == 0 && b == 0) o.v[j] += 0.51f * d + ev[b + 1].v[j];
         }
       }
+    }
     const T* dyp = dy + p * g.C;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
