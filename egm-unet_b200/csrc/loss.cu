@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) k_loss_pass1(const float* __restrict__ lo
 #pragma unroll
   for (int c = 0; c < EGM_MAXC; ++c) { inter[c] = 0.f; psum[c] = 0.f; tsum[c] = 0.f; }
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
-    int h = (int)(p / W), w = (int)(p - (long long)h * W);
+    const int h = (int)((unsigned)p / (unsigned)W), w = (int)((unsigned)p - (unsigned)h * (unsigned)W);   // H*W < 2^31 (checked by the launcher)
     long long t = tg[p];
     float z[EGM_MAXC], mx = -INFINITY;
 #pragma unroll
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) k_loss_pass2(const float* __restrict__ lo
   const float KX[3][3] = {{1, 0, -1}, {2, 0, -2}, {1, 0, -1}};
   const float KY[3][3] = {{1, 2, 1}, {0, 0, 0}, {-1, -2, -1}};
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
-    int h = (int)(p / W), w = (int)(p - (long long)h * W);
+    const int h = (int)((unsigned)p / (unsigned)W), w = (int)((unsigned)p - (unsigned)h * (unsigned)W);   // H*W < 2^31 (checked by the launcher)
     long long t = tg[p];
     float z[EGM_MAXC], mx = -INFINITY;
 #pragma unroll
@@ -152,13 +152,22 @@ __global__ void __launch_bounds__(256) k_loss_pass2(const float* __restrict__ lo
       for (int c = 0; c < EGM_MAXC; ++c) if (c < C) g[c] = 0.f;
     }
     float st = 0.f;
+    unsigned char bb[3][3];                            // unconditional (clamped) loads first, masks applied afterwards
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        int ph = h - (r - 1), pw = w - (s - 1);
+        ph = ph < 0 ? 0 : (ph >= H ? H - 1 : ph); pw = pw < 0 ? 0 : (pw >= W ? W - 1 : pw);
+        bb[r][s] = sm[(long long)ph * W + pw];
+      }
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
         int ph = h - (r - 1), pw = w - (s - 1);
         if (ph < 0 || ph >= H || pw < 0 || pw >= W) continue;
-        unsigned char b = sm[(long long)ph * W + pw];
+        unsigned char b = bb[r][s];
         st += K4[r][s] * (float)((int)(b & 3) - 1) + K8[r][s] * (float)((int)((b >> 2) & 3) - 1)
             + KX[r][s] * (float)((int)((b >> 4) & 3) - 1) + KY[r][s] * (float)((int)((b >> 6) & 3) - 1);
       }
@@ -178,6 +187,7 @@ extern "C" int egm_loss_fwd_bwd(const float* logits, const long long* target, co
                                 int with_dice, float grad_scale, float* loss_out, float* dlogits, void* workspace, long long workspace_bytes, void* stream) {
   EGM_REQUIRE(C >= 1 && C <= EGM_MAXC, EGM_E_SHAPE, "loss: num_classes %d > %d", C, EGM_MAXC);
   EGM_REQUIRE(N >= 1 && N <= 65535, EGM_E_SHAPE, "loss: batch %d", N);
+  EGM_REQUIRE((long long)H * W < (1ll << 31), EGM_E_SHAPE, "loss: H*W must be < 2^31");
   EGM_REQUIRE(workspace_bytes >= egm_loss_workspace_bytes(N, C, H, W), EGM_E_BADARG, "loss: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   long long accb = (long long)(ACC_HDR + 3LL * N * C) * sizeof(double);
