@@ -202,8 +202,21 @@ struct ConvTcParams {
   int stages, aBytes, bStride, tmemCols, accCols;
   int nChunk, coChunks;                               // Cout is processed in coChunks slices of nChunk (<= 256) channels
   int wres;                                           // 1: the whole packed weight tensor stays resident in smem (single Cout slice)
+  int kps;                                            // 9: thin 3x3 layers -- all 9 tap tiles of an output tile share ONE pipeline stage
+                                                      // (one barrier round trip, straight-line TMA issue and MMA issue per tile); else 1
   OutView out;
 };
+
+// KPS consecutive K iterations of one stage, KS MMAs each, as straight-line code
+template <int KPS, int KS>
+__device__ __forceinline__ void issue_group(uint32_t d, uint64_t ad, uint64_t bd, uint32_t aStep, uint32_t bStep, uint32_t idesc) {
+#pragma unroll
+  for (int j = 0; j < KPS; ++j) {
+#pragma unroll
+    for (int k = 0; k < KS; ++k) umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (j | k) ? 1u : 0u);
+    ad += aStep; bd += bStep;
+  }
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                                                           __nv_bfloat16* __restrict__ y, const float* __restrict__ bias, ConvTcParams p) {
@@ -212,7 +225,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   const int taps = p.kh * p.kw;
   const int kIters = taps * p.kChunks;
   uint8_t* sA = smem;
-  uint8_t* sB = sA + (size_t)p.stages * p.aBytes;                       // ring of weight tiles, or the resident [taps][kChunks] tiles
+  const size_t stageA = (size_t)p.kps * p.aBytes;                      // one stage holds kps A tiles
+  uint8_t* sB = sA + (size_t)p.stages * stageA;                         // ring of weight tiles, or the resident [taps][kChunks] tiles
   const int nB = p.wres ? kIters : p.stages;
   uint64_t* full = (uint64_t*)(sB + (size_t)nB * p.bStride);
   uint64_t* empty = full + p.stages;
@@ -249,6 +263,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       const int chunk = tile % p.coChunks, sp_t = tile / p.coChunks;
       const int n = sp_t / tilesPerImg, r = sp_t - n * tilesPerImg;
       const int h0 = (r / p.tilesW) * TILE_H, w0 = (r % p.tilesW) * TILE_W, co0 = chunk * p.nChunk;
+      if (p.kps == 9) {
+        // thin 3x3 layer: the per-tap loop below costs ~150 dependent instructions per tap in this single warp (ncu: the producer
+        // was the busiest warp) -- here one wait, one expect_tx and nine back-to-back TMA issues with compile-time tap offsets
+        mbar_wait(&empty[s], ph ^ 1);
+        if (leader) {
+          mbar_expect_tx(&full[s], (uint32_t)(9 * p.aBytes));
+          uint8_t* dst = sA + (size_t)s * stageA;
+#pragma unroll
+          for (int tt = 0; tt < 9; ++tt)
+            tma_load_4d(dst + (size_t)tt * p.aBytes, &tmX, &full[s], 0, w0 + (tt % 3 - 1) * p.dil, h0 + (tt / 3 - 1) * p.dil, n);
+        }
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+        continue;
+      }
       int dh = -p.pad, t = 0;
       for (int kr = 0; kr < p.kh; ++kr, dh += p.dil) {
         int dw = -p.pad;
@@ -295,6 +323,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         __syncwarp();                                                                                                  \
         if (++s == p.stages) { s = 0; ph ^= 1; }                                                                       \
       }
+      if (p.kps == 9) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (leader) {
+          const uint64_t ad = adBase + (uint64_t)(s * (uint32_t)(stageA >> 4));
+          if (ksteps == 1) issue_group<9, 1>(d, ad, bdBase, aStep, bStep, idesc); else issue_group<9, 2>(d, ad, bdBase, aStep, bStep, idesc);
+          umma_commit(&empty[s]);
+        }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      } else
       if (ksteps == 4) { EGM_V1_KLOOP(4) } else if (ksteps == 2) { EGM_V1_KLOOP(2) } else { EGM_V1_KLOOP(1) }
 #undef EGM_V1_KLOOP
       if (leader) umma_commit(&tfull[acc]);
@@ -643,7 +682,8 @@ extern "C" int egm_conv2d_tc_view(const void* x, long long x_cstride, long long 
   p.bStride = (p.nChunk * p.bkc * 2 + 1023) / 1024 * 1024;
   const long long wresBytes = (long long)kh * kw * p.kChunks * p.bStride;
   p.wres = (p.coChunks == 1 && wresBytes <= 72 * 1024) ? 1 : 0;
-  int per = p.aBytes + (p.wres ? 0 : p.bStride);
+  p.kps = (p.wres && p.kChunks == 1 && p.bkc <= 32 && kh == 3 && kw == 3) ? 9 : 1;      // thin 3x3 (dilated GRFB branches)
+  int per = p.kps * p.aBytes + (p.wres ? 0 : p.bStride);
   p.stages = (int)((198 * 1024 - (p.wres ? wresBytes : 0)) / per); if (p.stages > 8) p.stages = 8; if (p.stages < 2) p.stages = 2;
   p.accCols = (p.nChunk + 31) / 32 * 32; p.tmemCols = pow2_cols(2 * p.accCols);
   CUtensorMap tmX, tmW;
