@@ -1041,12 +1041,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_co
 }
 
 static bool wgrad_stack_disabled() { static int v = -1; if (v < 0) { const char* e = getenv("EGM_NO_WGRAD_STACK"); v = (e && e[0] == '1') ? 1 : 0; } return v == 1; }
+// row stacking applies: Cout chunk <= 64 (one A atom per kernel row), >= 2 kernel rows per MMA, accumulators fit in TMEM
+static bool wgrad_stackable(int Cin, int Cout, int kh, int kw) {
+  if (wgrad_stack_disabled() || kh < 2) return false;
+  const int mch = Cout > 64 ? 128 : pick_bkc(Cout), nch = pick_bkc(Cin);
+  if (mch > 64) return false;
+  int rpm = 128 / mch; if (rpm > kh) rpm = kh;
+  return rpm >= 2 && cdiv(kh, rpm) * kw * nch <= 512;
+}
 static bool wgrad_halo_eligible(int Cin, int Cout, int kh, int kw, int dil) {
   if (halo_disabled()) return false;
-  int pad = dil * (kh - 1) / 2;
-  if (pad > 3) return false;
-  int nch = pick_bkc(Cin);
-  return kw * nch <= 256;
+  const int pad = dil * (kh - 1) / 2, nch = pick_bkc(Cin);
+  if (kw * nch > 256) return false;
+  if (pad <= 3) return true;
+  // dilated: in stacked mode the X tile needs no vertical halo (16 rows x (8 + 2*pad) columns), so wide dilations fit
+  if (!wgrad_stackable(Cin, Cout, kh, kw)) return false;
+  const int haloW = HT_W + 2 * pad;
+  if (haloW > 256) return false;
+  // two pipeline stages (A atoms of every MMA group + the X tile with its tap slack) must fit in shared memory
+  const int mch = Cout > 64 ? 128 : pick_bkc(Cout), aAtomCh = mch >= 64 ? 64 : mch;
+  int rpm = 128 / mch; if (rpm > kh) rpm = kh;
+  const long long aBytes = (long long)cdiv(kh, rpm) * (128 / aAtomCh) * TILE_PIX * aAtomCh * 2;
+  const long long halo = ((long long)haloW * HT_H * nch * 2 + (long long)(kw - 1) * dil * nch * 2 + 1023) / 1024 * 1024;
+  return 2 * (aBytes + halo) + 2048 <= 220 * 1024;
 }
 static int launch_wgrad_halo(const NhwcView& xv, const NhwcView& dyv, float* dwp, int N, int H, int W, int Cin, int Cout, int kh, int kw, int dil, cudaStream_t st) {
   WgradHaloParams p{};
@@ -1067,9 +1084,12 @@ static int launch_wgrad_halo(const NhwcView& xv, const NhwcView& dyv, float* dwp
   p.tmemCols = pow2_cols(p.rowsPerGroup * perRow);
   p.rpm = 128 / p.mch; if (p.rpm > kh) p.rpm = kh;
   p.nGroups = cdiv(kh, p.rpm);
-  p.stack = (kh > 1 && p.mAtoms == 1 && p.rpm >= 2 && p.nGroups * perRow <= 512 && !wgrad_stack_disabled()) ? 1 : 0;
+  p.stack = wgrad_stackable(Cin, Cout, kh, kw) ? 1 : 0;
+  EGM_REQUIRE(p.stack || p.pad <= 3, EGM_E_SHAPE, "wgrad_tc_halo: dilated layers need the stacked mode");
   if (p.stack) {                                         // nGroups accumulators; q rows cover [0, H + (kh-1)*dil)
     p.rowsPerGroup = kh; p.rowGroups = 1; p.tmemCols = pow2_cols(p.nGroups * perRow);
+    p.haloH = HT_H;                                      // the X window is not row-shifted in this mode: no vertical halo
+    p.haloBytes = p.haloW * p.haloH * p.rowB; p.haloStride = (p.haloBytes + (kw - 1) * dil * p.rowB + 1023) / 1024 * 1024;
     p.tilesH = cdiv(H + (kh - 1) * dil, HT_H); p.numTiles = N * p.tilesH * p.tilesW;
     const int atoms = p.nGroups * (128 / p.aAtomCh);    // every MMA addresses 128/aAtomCh atoms from its first one
     p.aBytes = atoms * p.aAtomBytes;

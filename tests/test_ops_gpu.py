@@ -288,7 +288,9 @@ TC_CASES = [  # cin, cout, k, dil, H, W, N
     (256, 256, 3, 1, 15, 15, 1), (512, 256, 3, 1, 12, 12, 1), (256, 128, 3, 1, 16, 16, 1), (64, 32, 3, 1, 33, 47, 1),
     (32, 32, 3, 12, 30, 30, 1), (64, 64, 1, 1, 20, 20, 1), (32, 32, 7, 1, 18, 18, 1), (128, 384, 1, 1, 9, 9, 1),
     (16, 16, 7, 1, 20, 24, 2), (112, 16, 1, 1, 16, 16, 1), (16, 16, 3, 24, 30, 30, 1), (64, 16, 1, 1, 10, 10, 1), (16, 64, 1, 1, 10, 10, 1),
-    (256, 512, 3, 1, 10, 10, 1), (224, 32, 1, 1, 12, 12, 1), (48, 48, 3, 1, 18, 20, 1), (80, 96, 3, 1, 12, 20, 2), (448, 64, 1, 1, 9, 9, 1)]
+    (256, 512, 3, 1, 10, 10, 1), (224, 32, 1, 1, 12, 12, 1), (48, 48, 3, 1, 18, 20, 1), (80, 96, 3, 1, 12, 20, 2), (448, 64, 1, 1, 9, 9, 1),
+    # dilated GRFB branch shapes: thin ones take the one-stage k_conv_tc path and the row-stacked halo wgrad; 64 channels fall back
+    (64, 64, 3, 12, 20, 20, 1), (64, 64, 3, 36, 24, 24, 1), (16, 16, 3, 36, 30, 30, 2), (32, 32, 3, 24, 17, 21, 1), (32, 16, 3, 36, 8, 6, 2)]
 
 
 @pytest.mark.parametrize("case", TC_CASES)
