@@ -67,3 +67,19 @@ def test_confusion_matrix_and_meters_cpu():
     ml = MetricLogger()
     ml.update(loss=1.5)
     assert "loss" in str(ml)
+
+
+def test_fastdiv_reciprocal_is_exact():
+    """csrc/common.cuh FastDiv (33-bit Granlund-Montgomery reciprocal used by every grid-stride kernel's index decoding):
+    q = (umulhi(x, m) + x) >> s with s = ceil(log2 d), m = floor(2^32 (2^s - d) / d) + 1 must equal x // d for all x < 2^32."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    ds = np.unique(np.concatenate([np.arange(1, 2050), rng.integers(1, 2 ** 31 - 1, 3000), [2 ** 31 - 1, 2 ** 30, 3 * 2 ** 20 + 1]])).astype(np.uint64)
+    xs = np.concatenate([rng.integers(0, 2 ** 32, 4000, dtype=np.uint64), np.array([0, 1, 2 ** 31 - 1, 2 ** 31, 2 ** 32 - 1], dtype=np.uint64)])
+    for d in ds.tolist():
+        s = 0 if d <= 1 else int(d - 1).bit_length()
+        m = ((1 << 32) * ((1 << s) - d)) // d + 1
+        assert m < 2 ** 32
+        x = xs if d > 4096 else np.concatenate([xs, np.arange(0, 5 * d, dtype=np.uint64), (np.arange(1, 40, dtype=np.uint64) * np.uint64(d)) - np.uint64(1)])
+        q = (((x * np.uint64(m)) >> np.uint64(32)) + x) >> np.uint64(s)
+        assert np.array_equal(q, x // np.uint64(d)), d
