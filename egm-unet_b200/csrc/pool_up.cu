@@ -120,17 +120,26 @@ __global__ void k_upcat_bwd_low(const T* __restrict__ dcat, T* __restrict__ dlow
     FVec<V> acc;
 #pragma unroll
     for (int j = 0; j < V; ++j) acc.v[j] = 0.f;
-    for (int a = 0; a < 6; ++a) {
-      if (wh[a] == 0.f) continue;
-      int h = 2 * hl - 2 + a + g.padt; if (h < 0 || h >= g.H) continue;
-      for (int b = 0; b < 6; ++b) {
-        if (ww[b] == 0.f) continue;
-        int w = 2 * wl - 2 + b + g.padl; if (w < 0 || w >= g.W) continue;
-        FVec<V> d = ldv<V>(dcat + (((long long)n * g.H + h) * g.W + w) * C + g.Cs + cu);
-        float f = wh[a] * ww[b];
+    // rows with a non-zero weight only (uniform-ish skip), but inside a row all 6 candidate loads are issued unconditionally on
+    // clamped coordinates and masked through the weight: 6 loads in flight instead of 6 dependent, predicated ones
 #pragma unroll
-        for (int j = 0; j < V; ++j) acc.v[j] = fmaf(f, d.v[j], acc.v[j]);
+    for (int a = 0; a < 6; ++a) {
+      int h = 2 * hl - 2 + a + g.padt;
+      if (wh[a] == 0.f || h < 0 || h >= g.H) continue;
+      const T* rowp = dcat + (((long long)n * g.H + h) * g.W) * C + g.Cs + cu;
+      FVec<V> d[6]; float f[6];
+#pragma unroll
+      for (int b = 0; b < 6; ++b) {
+        int w = 2 * wl - 2 + b + g.padl;
+        const bool ok = w >= 0 && w < g.W;
+        f[b] = ok ? wh[a] * ww[b] : 0.f;
+        w = w < 0 ? 0 : (w >= g.W ? g.W - 1 : w);
+        d[b] = ldv<V>(rowp + (long long)w * C);
       }
+#pragma unroll
+      for (int b = 0; b < 6; ++b)
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc.v[j] = fmaf(f[b], d[b].v[j], acc.v[j]);
     }
     stv<V>(dlow + p * g.Cu + cu, acc);
   }
