@@ -94,17 +94,36 @@ def call(name: str, *args):
         if L.fn["egm_device_check"]() != 0:
             raise RuntimeError("egm_b200: " + L.last_error())
         L.device_checked = True
+    # launch on the current stream of the device that OWNS the operands (not of whatever device happens to be current):
+    # `--device cuda:1` without torch.cuda.set_device must not launch into cuda:0's context
+    dev = None
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            dev = a.device
+            break
+    if dev is not None and dev.type == "cuda" and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            return call(name, *args)
     stream = torch.cuda.current_stream().cuda_stream
-    if _PROFILE is not None:
+    prof = _PROFILE is not None
+    if prof and _WINDOW is not None:
+        idx = _WINDOW[2]
+        _WINDOW[2] = idx + 1
+        if idx == _WINDOW[0]:
+            torch.cuda._sleep(_WINDOW[3])      # block the stream while this window's launches are queued behind it
+        prof = _WINDOW[0] <= idx < _WINDOW[1]
+    if prof:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     rc = L.fn["egm_" + name](*[_conv_arg(a) for a in args], stream)
     if rc != 0:
         raise RuntimeError(f"egm_{name} failed ({rc}): {L.last_error()}")
-    if _PROFILE is not None:
+    if prof:
         e1.record()
         key = name
-        if _PROFILE_DETAIL and (name.startswith("conv2d") or name.startswith("bn_act") or name in ("bn_stats", "copy_slice", "mca_bwd_du", "highpass3")):
+        if _PROFILE_DETAIL_ALL:
+            key = name + ":" + ",".join(str(a) for a in args if isinstance(a, int))
+        elif _PROFILE_DETAIL and (name.startswith("conv2d") or name.startswith("bn_act") or name in ("bn_stats", "copy_slice", "mca_bwd_du", "highpass3")):
             key = name + ":" + ",".join(str(a) for a in args if isinstance(a, int))
         _PROFILE.append((key, e0, e1))
     LAUNCH_COUNTER[0] += 1
@@ -117,24 +136,47 @@ def query(name: str, *args):
 
 _PROFILE = None
 _PROFILE_DETAIL = bool(os.environ.get("EGM_PROFILE_DETAIL"))
+_PROFILE_DETAIL_ALL = False          # bench.py: every key carries the call's integer arguments (shapes)
 
 
-def profile_step(fn):
-    """Run fn() once with a CUDA-event pair around every C-ABI call (on the launch stream); returns
-    {entry point: {"ms": summed device time, "calls": n}}.  Diagnostic only -- never inside a timed region."""
-    global _PROFILE
+_WINDOW = None      # [first call index, end call index, running call index, spin cycles] while a windowed profile runs
+
+
+def profile_step(fn, window: int = 0, spin_ms: float = 15.0):
+    """Run fn() with a CUDA-event pair around every C-ABI call (on the launch stream); returns
+    {entry point: {"ms": summed device time, "calls": n}}.  Diagnostic only -- never inside a timed region.
+
+    window = 0: one pass, every call bracketed.  The Python launch loop is slower than the GPU, so the stream runs dry between
+    kernels and each event delta also contains that kernel's launch latency (~10-16 us).
+    window = W > 0: fn() is run ceil(calls / W) times; pass k brackets only calls [kW, (k+1)W) and blocks the stream with a
+    `spin_ms` spin kernel right before them, so those W launches (and their event records) are all queued before the first
+    one starts: the kernels run back to back and the deltas are pure device time."""
+    global _PROFILE, _WINDOW
     torch.cuda.synchronize()
-    _PROFILE = []
+    recs = []
     try:
-        fn()
+        if window <= 0:
+            _PROFILE = recs
+            fn()
+        else:
+            cycles = int(spin_ms * 1e-3 * 1.9e9)
+            k, total = 0, None
+            while total is None or k * window < total:
+                _PROFILE = recs
+                _WINDOW = [k * window, (k + 1) * window, 0, cycles]
+                fn()
+                torch.cuda.synchronize()
+                total = _WINDOW[2]
+                k += 1
         torch.cuda.synchronize()
         out = {}
-        for name, e0, e1 in _PROFILE:
+        for name, e0, e1 in recs:
             d = out.setdefault(name, {"ms": 0.0, "calls": 0})
             d["ms"] += e0.elapsed_time(e1)
             d["calls"] += 1
     finally:
         _PROFILE = None
+        _WINDOW = None
     return dict(sorted(out.items(), key=lambda kv: -kv[1]["ms"]))
 
 

@@ -259,13 +259,11 @@ static int bn_bwd_reduce_impl(const void* dy, long long dy_cstride, long long dy
     EGM_DISPATCH_DTYPE(dtype, {
       if (mode == 0) {
         const size_t smb = bs::ring_bytes<2>(tail);
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(k_bn_bwd_reduce_stream<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+        static bool attr[64] = {}; egm_ensure_smem(k_bn_bwd_reduce_stream<T, false>, (int)smb, attr);
         k_bn_bwd_reduce_stream<T, false><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st>>>((const T*)dy, (const T*)z, nullptr, a, M * C, C, sums, tl);
       } else {
         const size_t smb = bs::ring_bytes<3>(tail);
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(k_bn_bwd_reduce_stream<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+        static bool attr[64] = {}; egm_ensure_smem(k_bn_bwd_reduce_stream<T, true>, (int)smb, attr);
         k_bn_bwd_reduce_stream<T, true><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st>>>((const T*)dy, (const T*)z, (const T*)aux, a, M * C, C, sums, tl);
       }
     });
@@ -344,14 +342,12 @@ extern "C" int egm_bn_act_bwd_apply(const void* dy, long long dy_cstride, long l
     EGM_DISPATCH_DTYPE(dtype, {
       if (mode == 0) {
         const size_t smb = bs::ring_bytes<2>(0);
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(k_bn_bwd_apply_stream<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+        static bool attr[64] = {}; egm_ensure_smem(k_bn_bwd_apply_stream<T, false>, (int)smb, attr);
         k_bn_bwd_apply_stream<T, false><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, (cudaStream_t)stream>>>(
             (const T*)dy, (const T*)z, nullptr, a, (T*)dz, nullptr, 0, M * C, C);
       } else {
         const size_t smb = bs::ring_bytes<3>(0);
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(k_bn_bwd_apply_stream<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+        static bool attr[64] = {}; egm_ensure_smem(k_bn_bwd_apply_stream<T, true>, (int)smb, attr);
         k_bn_bwd_apply_stream<T, true><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, (cudaStream_t)stream>>>(
             (const T*)dy, (const T*)z, (const T*)aux, a, (T*)dz, (T*)daux, daux_accumulate, M * C, C);
       }
@@ -402,10 +398,10 @@ static bool bn_stats_stream_launch(const void* x, int dtype, long long M, int C,
   if (!bn_stream_eligible(0, M, C, cstride, coff) || (dtype != EGM_F32 && dtype != EGM_BF16)) return false;
   const size_t smb = bs::ring_bytes<1>(2 * bs::CONSUMERS * bs::V * sizeof(float));
   if (dtype == EGM_F32) {
-    static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_bn_stats_stream<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+    static bool attr[64] = {}; egm_ensure_smem(k_bn_stats_stream<float>, (int)smb, attr);
     k_bn_stats_stream<float><<<bn_stream_grid(M * C, 4), bs::THREADS, smb, st>>>((const float*)x, M * C, C, sums, tl);
   } else {
-    static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_bn_stats_stream<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+    static bool attr[64] = {}; egm_ensure_smem(k_bn_stats_stream<__nv_bfloat16>, (int)smb, attr);
     k_bn_stats_stream<__nv_bfloat16><<<bn_stream_grid(M * C, 2), bs::THREADS, smb, st>>>((const __nv_bfloat16*)x, M * C, C, sums, tl);
   }
   return true;
@@ -417,13 +413,11 @@ static bool bn_fwd_stream_launch(const void* z, long long zcs, long long zco, co
   EGM_DISPATCH_DTYPE(dtype, {
     if (a.mode == 0) {
       const size_t smb = bs::ring_bytes<1>(0);
-      static bool attr = false;
-      if (!attr) { cudaFuncSetAttribute(k_bn_act_fwd_stream<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+      static bool attr[64] = {}; egm_ensure_smem(k_bn_act_fwd_stream<T, false>, (int)smb, attr);
       k_bn_act_fwd_stream<T, false><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st>>>((const T*)z, nullptr, a, (T*)y, M * C, C);
     } else {
       const size_t smb = bs::ring_bytes<2>(0);
-      static bool attr = false;
-      if (!attr) { cudaFuncSetAttribute(k_bn_act_fwd_stream<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb); attr = true; }
+      static bool attr[64] = {}; egm_ensure_smem(k_bn_act_fwd_stream<T, true>, (int)smb, attr);
       k_bn_act_fwd_stream<T, true><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st>>>((const T*)z, (const T*)aux, a, (T*)y, M * C, C);
     }
   });

@@ -36,6 +36,12 @@ static inline int egm_num_sms() {
   }
   return sms;
 }
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: set it once per (kernel, device), not once per process
+template <typename K>
+static inline void egm_ensure_smem(K kernel, int bytes, bool (&done)[64]) {
+  int dev = 0; cudaGetDevice(&dev); dev &= 63;
+  if (!done[dev]) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); done[dev] = true; }
+}
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------- dtype dispatch

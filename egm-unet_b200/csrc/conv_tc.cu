@@ -406,11 +406,16 @@ struct ConvHaloParams {
   int rowB, haloW, haloH, haloBytes, haloStride, wTapStride, stages, tmemCols, accCols;
   int nacc;                                          // TMEM accumulator buffers in flight (2..8)
   int ksteps;                                        // MMAs (K=16) per tap = ceil(Cin/16); rowB may be wider than Cin*2 (zero-filled)
-  int exp;                                           // EGM_EXP diagnostic bit mask (timing ablations; results are wrong):
-                                                     // 1 = no global stores, 4 = no MMAs, 8 = no TMA loads
+  int exp;                                           // EGM_DIAG builds only: EGM_EXP bit mask (timing ablations; results are wrong):
+                                                     // 1 = no global stores, 4 = no MMAs, 8 = no TMA loads.  Compiled out of the shipped .so.
   OutView out;
 };
 constexpr int HT_H = 16, HT_W = 8;
+#ifdef EGM_DIAG
+#define EGM_EXPBIT(b) (p.exp & (b))
+#else
+#define EGM_EXPBIT(b) (0)
+#endif
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                                                                __nv_bfloat16* __restrict__ y, const float* __restrict__ bias, ConvHaloParams p) {
@@ -453,7 +458,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
       const int h0 = (r / p.tilesW) * HT_H, w0 = (r % p.tilesW) * HT_W;
       mbar_wait(&empty[s], ph ^ 1);
       if (leader) {
-        if (p.exp & 8) mbar_arrive(&full[s]);
+        if (EGM_EXPBIT(8)) mbar_arrive(&full[s]);
         else {
           mbar_expect_tx(&full[s], (uint32_t)p.haloBytes);
           tma_load_4d(sA + (size_t)s * p.haloStride, &tmX, &full[s], 0, w0 - p.pad, h0 - p.pad, n);
@@ -485,13 +490,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
         uint64_t bd = bd0, adr = ad0;
         // 3x3 kernels (the DoubleConv layers): mode decided once per tile, the 9 taps are straight-line code -- every branch in this
         // single-thread issue path costs about as much as an MMA
-        if (p.kh == 1 && !(p.exp & 4)) {
+        if (p.kh == 1 && !EGM_EXPBIT(4)) {
           if (ksteps == 4) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16(d, ad0 + 2 * k, bd0 + 2 * k, idesc, k ? 1u : 0u);
           } else if (ksteps == 2) { umma_bf16(d, ad0, bd0, idesc, 0u); umma_bf16(d, ad0 + 2, bd0 + 2, idesc, 1u); }
           else umma_bf16(d, ad0, bd0, idesc, 0u);
-        } else if (p.kh == 7 && p.kw == 7 && ksteps <= 2 && !(p.exp & 4)) {          // merged FusionConv 7x7 (16 / 32 channels)
+        } else if (p.kh == 7 && p.kw == 7 && ksteps <= 2 && !EGM_EXPBIT(4)) {          // merged FusionConv 7x7 (16 / 32 channels)
           if (ksteps == 1) {
 #pragma unroll
             for (int r = 0; r < 7; ++r) {
@@ -512,7 +517,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
               adr += aRow;
             }
           }
-        } else if (p.kh == 3 && p.kw == 3 && !(p.exp & 4)) {
+        } else if (p.kh == 3 && p.kw == 3 && !EGM_EXPBIT(4)) {
           if (ksteps == 2) {
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
@@ -547,7 +552,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
             }
           }
         } else
-        for (int r = 0; r < ((p.exp & 4) ? 0 : p.kh); ++r) {
+        for (int r = 0; r < (EGM_EXPBIT(4) ? 0 : p.kh); ++r) {
           uint64_t ad = adr;
           for (int c = 0; c < p.kw; ++c) {
             if (ksteps == 4) {
@@ -586,7 +591,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
           uint32_t v[32];
           tmem_ld32(t0 + c, v);
           tmem_ld_wait();
-          if (valid && !(p.exp & 1)) { store16(yp + c, v, bias ? bias + c : nullptr); store16(yp + c + 16, v + 16, bias ? bias + c + 16 : nullptr); }
+          if (valid && !EGM_EXPBIT(1)) { store16(yp + c, v, bias ? bias + c : nullptr); store16(yp + c + 16, v + 16, bias ? bias + c + 16 : nullptr); }
         }
       } else if (p.out.dense) {
         for (int c = 0; c < p.Cout; c += 16) {
@@ -636,15 +641,18 @@ static int launch_conv_halo(const NhwcView& xv, const void* wpk, const float* bi
   p.stages = (int)((198 * 1024 - wres) / p.haloStride); if (p.stages > 8) p.stages = 8; if (p.stages < 2) p.stages = 2;
   p.accCols = (Cout + 31) / 32 * 32;
   p.nacc = 512 / p.accCols; if (p.nacc > 8) p.nacc = 8; if (p.nacc < 2) p.nacc = 2;
+  p.exp = 0;
+#ifdef EGM_DIAG
   { const char* ev = getenv("EGM_EXP"); p.exp = ev ? atoi(ev) : 0; }
+#endif
   p.tmemCols = pow2_cols(p.nacc * p.accCols);
   CUtensorMap tmX, tmW;
   p.out = ov;
   int e = make_map_nhwc(&tmX, xv, N, H, W, p.rowB / 2, p.haloW, p.haloH); if (e) return e;
   e = make_map_w(&tmW, wpk, kh * kw, Cout, Cin, p.rowB / 2, Cout); if (e) return e;
   size_t smem = wres + (size_t)p.stages * p.haloStride + 1024 + 1408;
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_conv_tc_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+  static bool attr_set[64] = {};
+  egm_ensure_smem(k_conv_tc_halo, 227 * 1024, attr_set);
   int grid = p.numTiles < egm_num_sms() ? p.numTiles : egm_num_sms();
   k_conv_tc_halo<<<grid, TC_THREADS, smem, st>>>(tmX, tmW, (__nv_bfloat16*)y, bias, p);
   return egm_check_launch("conv2d_tc_halo");
@@ -691,8 +699,8 @@ extern "C" int egm_conv2d_tc_view(const void* x, long long x_cstride, long long 
   int e = make_map_nhwc(&tmX, xv, N, H, W, p.bkc, TILE_W, TILE_H); if (e) return e;
   e = make_map_w(&tmW, w_packed_bf16, kh * kw, Cout, Cin, p.bkc, p.nChunk); if (e) return e;
   size_t smem = (size_t)p.stages * per + (p.wres ? (size_t)wresBytes : 0) + 1024 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+  static bool attr_set[64] = {};
+  egm_ensure_smem(k_conv_tc, 227 * 1024, attr_set);
   int grid = p.numTiles < egm_num_sms() ? p.numTiles : egm_num_sms();
   k_conv_tc<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmX, tmW, (__nv_bfloat16*)y, bias, p);
   EGM_LAUNCH_CHECK("conv2d_tc"); return EGM_OK;
@@ -1105,8 +1113,8 @@ static int launch_wgrad_halo(const NhwcView& xv, const NhwcView& dyv, float* dwp
   int e = make_map_nhwc(&tmDY, dyv, N, H, W, p.aAtomCh, HT_W, HT_H); if (e) return e;
   e = make_map_nhwc(&tmX, xv, N, H, W, p.nch, p.haloW, p.haloH); if (e) return e;
   size_t smem = (size_t)p.stages * p.stageBytes + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_wgrad_tc_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+  static bool attr_set[64] = {};
+  egm_ensure_smem(k_wgrad_tc_halo, 227 * 1024, attr_set);
   long long grid = units * p.splits;
   EGM_REQUIRE(grid < (1ll << 31), EGM_E_SHAPE, "wgrad_tc: grid too large");
   k_wgrad_tc_halo<<<(unsigned)grid, TC_THREADS, smem, st>>>(tmDY, tmX, dwp, p);
@@ -1149,8 +1157,8 @@ extern "C" int egm_conv2d_wgrad_tc_view(const void* x, long long x_cstride, long
   int e = make_map_nhwc(&tmDY, dyv, N, H, W, aAtomCh, TILE_W, TILE_H); if (e) return e;
   e = make_map_nhwc(&tmX, xv, N, H, W, p.nch, TILE_W, TILE_H); if (e) return e;
   size_t smem = (size_t)p.stages * p.stageBytes + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+  static bool attr_set[64] = {};
+  egm_ensure_smem(k_wgrad_tc, 227 * 1024, attr_set);
   long long grid = units * p.splits;
   EGM_REQUIRE(grid < (1ll << 31), EGM_E_SHAPE, "wgrad_tc: grid too large");
   k_wgrad_tc<<<(unsigned)grid, TC_THREADS, smem, st>>>(tmDY, tmX, dw_packed, p);

@@ -7,7 +7,7 @@
 #include "common.cuh"
 
 #define EGM_MAXC 16
-// accumulator layout (double): [0] ce_num [1] ce_den [2] lap4 [3] lap8 [4] sobel, then per (n,c): inter, psum, tsum
+// accumulator layout (double): [0] ce_num [1] ce_den [2] lap4 [3] lap8 [4] sobel [5] out-of-range labels, then per (n,c): inter, psum, tsum
 #define ACC_HDR 8
 
 __device__ __forceinline__ float tgt0(const long long* t0, int H, int W, int h, int w) {
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) k_loss_pass1(const float* __restrict__ lo
   const long long HW = (long long)H * W;
   const float* lg = logits + (long long)n * C * HW;
   const long long* tg = target + (long long)n * HW;
-  float ce_num = 0.f, ce_den = 0.f, s4 = 0.f, s8 = 0.f, ss = 0.f;
+  float ce_num = 0.f, ce_den = 0.f, s4 = 0.f, s8 = 0.f, ss = 0.f, nbad = 0.f;
   float inter[EGM_MAXC], psum[EGM_MAXC], tsum[EGM_MAXC];
 #pragma unroll
   for (int c = 0; c < EGM_MAXC; ++c) { inter[c] = 0.f; psum[c] = 0.f; tsum[c] = 0.f; }
@@ -59,7 +59,11 @@ __global__ void __launch_bounds__(256) k_loss_pass1(const float* __restrict__ lo
     float se = 0.f;
 #pragma unroll
     for (int c = 0; c < EGM_MAXC; ++c) if (c < C) { z[c] = expf(z[c] - mx); se += z[c]; }
-    if (t != ignore_index) {
+    // a label that is neither ignore_index nor a class id makes the reference raise (F.cross_entropy / one_hot device assert); here such
+    // pixels are dropped from BOTH the CE and the Dice sums, never index class_weight, and are counted in loss_out[6]
+    const bool bad = t != ignore_index && (t < 0 || t >= C);
+    nbad += bad ? 1.f : 0.f;
+    if (t != ignore_index && !bad) {
       float inv = 1.f / se;
 #pragma unroll
       for (int c = 0; c < EGM_MAXC; ++c) if (c < C) {
@@ -77,6 +81,7 @@ __global__ void __launch_bounds__(256) k_loss_pass1(const float* __restrict__ lo
   v = block_sum(s4, red); if (threadIdx.x == 0) atomicAdd(acc + 2, (double)v);
   v = block_sum(s8, red); if (threadIdx.x == 0) atomicAdd(acc + 3, (double)v);
   v = block_sum(ss, red); if (threadIdx.x == 0) atomicAdd(acc + 4, (double)v);
+  v = block_sum(nbad, red); if (threadIdx.x == 0 && v != 0.f) atomicAdd(acc + 5, (double)v);
 #pragma unroll
   for (int c = 0; c < EGM_MAXC; ++c) if (c < C) {
     double* a = acc + ACC_HDR + ((long long)n * C + c) * 3;
@@ -86,7 +91,7 @@ __global__ void __launch_bounds__(256) k_loss_pass1(const float* __restrict__ lo
   }
 }
 
-// out[0] = total, out[1..5] = ce, dice, laplace, lap, sobel
+// out[0] = total, out[1..5] = ce, dice, laplace, lap, sobel, out[6] = number of out-of-range labels (0 for valid input)
 __global__ void k_loss_finalize(const double* __restrict__ acc, int N, int C, double NHW, int with_dice, float* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double eps = 1e-6;
@@ -101,7 +106,7 @@ __global__ void k_loss_finalize(const double* __restrict__ acc, int N, int C, do
   double dice = 1.0 - d / (double)(N * C);
   double l4 = acc[2] / NHW, l8 = acc[3] / NHW, sb = acc[4] / NHW;
   out[0] = with_dice ? (float)(ce + dice + l4 + l8 + sb) : (float)ce;
-  out[1] = (float)ce; out[2] = (float)dice; out[3] = (float)l4; out[4] = (float)l8; out[5] = (float)sb;
+  out[1] = (float)ce; out[2] = (float)dice; out[3] = (float)l4; out[4] = (float)l8; out[5] = (float)sb; out[6] = (float)acc[5];
 }
 
 __global__ void __launch_bounds__(256) k_loss_pass2(const float* __restrict__ logits, const long long* __restrict__ target, const float* __restrict__ weight,
@@ -140,7 +145,7 @@ __global__ void __launch_bounds__(256) k_loss_pass2(const float* __restrict__ lo
 #pragma unroll
     for (int c = 0; c < EGM_MAXC; ++c) if (c < C) { z[c] = expf(z[c] - mx); se += z[c]; }
     float g[EGM_MAXC];
-    if (t != ignore_index) {
+    if (t != ignore_index && t >= 0 && t < C) {          // same validity rule as pass 1
       float inv = 1.f / se, dot = 0.f, wt = weight ? weight[(int)t] : 1.f;
       float dp[EGM_MAXC];
 #pragma unroll
@@ -182,7 +187,7 @@ extern "C" long long egm_loss_workspace_bytes(int N, int C, int H, int W) {
   accb = (accb + 255) / 256 * 256;
   return accb + (long long)N * H * W;
 }
-// logits fp32 NCHW, target int64 [N,H,W]; loss_out[6] (total, ce, dice, laplace, lap, sobel); dlogits may be null (forward only).
+// logits fp32 NCHW, target int64 [N,H,W]; loss_out[8] (total, ce, dice, laplace, lap, sobel, #out-of-range labels, unused); dlogits may be null (forward only).
 extern "C" int egm_loss_fwd_bwd(const float* logits, const long long* target, const float* class_weight, int N, int C, int H, int W, int ignore_index,
                                 int with_dice, float grad_scale, float* loss_out, float* dlogits, void* workspace, long long workspace_bytes, void* stream) {
   EGM_REQUIRE(C >= 1 && C <= EGM_MAXC, EGM_E_SHAPE, "loss: num_classes %d > %d", C, EGM_MAXC);

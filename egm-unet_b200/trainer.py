@@ -36,13 +36,18 @@ class Trainer:
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.mom_buf = torch.empty(self.store.total, dtype=torch.float32, device=self.dev)
         call("memset_zero", self.mom_buf, self.store.total * 4)
-        self._hp_host = torch.empty(4, dtype=torch.float32).pin_memory()
+        # hyper-parameters reach the device through a RING of pinned slots: the H2D copies are asynchronous, so a slot must not be
+        # rewritten before its copy has executed (the LR changes every step under the reference's scheduler)
+        self._hp_ring = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(16)]
+        self._hp_events = [None] * 16
+        self._hp_i = 0
         self.hp = torch.empty(4, dtype=torch.float32, device=self.dev)
         self.loss_terms = None
         self.comm_stream = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
         self.num_buckets = num_buckets
         self.use_graph = use_graph
-        self._graph = None            # CUDA graph of forward + loss + backward (+ SGD when single-rank)
+        self._graph = None            # last replayed CUDA graph of forward + loss + backward (+ SGD when single-rank)
+        self._graphs = {}             # (shapes, dtype, store) -> (graph, static image, static target, static loss)
         self._wplan, self._wplan_key = None, None
         self.batch_weights = os.environ.get("EGM_NO_WEIGHT_PLAN", "0") != "1"
         self._gkey = None
@@ -50,22 +55,63 @@ class Trainer:
         self.reducer = None
         if self.world > 1:
             self.reducer = BucketReducer(self.store.grads, self.store.ranges, num_buckets, process_group, self.comm_stream)
+            self.sync_replicas()
         self._set_hp()
 
+    def sync_replicas(self, src: int = 0):
+        """PyTorch-DDP construction semantics: every rank starts from rank `src`'s parameters AND buffers (BN running statistics,
+        num_batches_tracked), whatever seed or checkpoint the other ranks were built from."""
+        if self.world <= 1:
+            return
+        dist.broadcast(self.store.params, src, group=self.pg)
+        for b in self.model.buffers():
+            dist.broadcast(b, src, group=self.pg)
+
+    def _rebind_store(self):
+        """The parameters no longer alias the flat store (model.to(), load_state_dict(assign=True), ...): build a new store and
+        re-bind EVERYTHING that pointed into the old one -- bucket reducer, weight plan, captured graph, momentum."""
+        old = self.store
+        st = self.store = _store_for(self.model)
+        if st.total == old.total and st.params.device == self.mom_buf.device:
+            pass                                   # same layout: the momentum buffer carries over element for element
+        else:
+            self.mom_buf = torch.empty(st.total, dtype=torch.float32, device=self.dev)
+            call("memset_zero", self.mom_buf, st.total * 4)
+        self._graph, self._gkey = None, None
+        self._graphs = {}
+        self._wplan, self._wplan_key = None, None
+        if self.world > 1:
+            self.reducer = BucketReducer(st.grads, st.ranges, self.num_buckets, self.pg, self.comm_stream)
+        return st
+
     def _set_hp(self):
-        self._hp_host[0], self._hp_host[1], self._hp_host[2], self._hp_host[3] = self.lr, self.momentum, self.wd, 1.0 / self.world
-        self.hp.copy_(self._hp_host, non_blocking=True)
+        i = self._hp_i = (self._hp_i + 1) % len(self._hp_ring)
+        if self._hp_events[i] is not None:
+            self._hp_events[i].synchronize()       # 16 updates ago: long done unless nothing ever synchronised
+        h = self._hp_ring[i]
+        h[0], h[1], h[2], h[3] = self.lr, self.momentum, self.wd, 1.0 / self.world
+        self.hp.copy_(h, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self._hp_events[i] = ev
 
     def set_lr(self, lr: float):
         if lr != self.lr:
             self.lr = lr
             self._set_hp()
 
+    def set_hyper(self, lr: float, momentum: float, weight_decay: float):
+        if (lr, momentum, weight_decay) != (self.lr, self.momentum, self.wd):
+            self.lr, self.momentum, self.wd = lr, momentum, weight_decay
+            self._set_hp()
+
     # ------------------------------------------------------------------ one step
     def forward_backward(self, image: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         m, st = self.model, self.store
         if not st.valid():
-            st = self.store = _store_for(m)
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("Trainer: parameter storage changed during CUDA-graph capture")
+            st = self._rebind_store()
         ctx = Ctx(m.compute_dtype, self.dev, True, True, st.grad_slot, use_tc=m.use_tensor_cores)
         # batched weight preparation: registered during the first (eager) step, two launches per step afterwards.  The eager
         # multi-rank path keeps per-conv gradient unpacking because its bucket all-reduces start as soon as a bucket is complete.
@@ -110,6 +156,9 @@ class Trainer:
     def step(self, image: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """image [N,3,H,W] fp32 cuda, target [N,H,W] int64 cuda -> loss (0-dim device tensor)."""
         self._calls += 1
+        if not self.store.valid():
+            self._rebind_store()
+            self._calls = 1                      # the first step after a rebind runs eagerly (re-registers the weight plan)
         if self.use_graph and self._calls > 1:
             return self._graph_step(image, target)
         loss = self.forward_backward(image, target)
@@ -119,35 +168,37 @@ class Trainer:
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole step
     def _graph_step(self, image: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-        """The ~1300 kernel launches of a step are captured once (all kernels take plain pointers and never sync or
-        allocate; torch's allocator serves the capture from a private pool) and replayed with new inputs copied into
+        """The ~800 kernel launches of a step are captured once per input shape (all kernels take plain pointers and never sync
+        or allocate; torch's allocator serves the capture from a private pool) and replayed with new inputs copied into
         static buffers.  With several ranks the graph holds forward+backward; the flat-bucket all-reduce and the fused
         SGD run right after it on the same stream."""
-        key = (tuple(image.shape), tuple(target.shape), self.model.compute_dtype)
-        if self._graph is None or key != self._gkey:
-            self._gkey = key
-            self._s_img = torch.empty_like(image)
-            self._s_tgt = torch.empty_like(target)
-            self._s_img.copy_(image)
-            self._s_tgt.copy_(target)
+        key = (tuple(image.shape), tuple(target.shape), self.model.compute_dtype, id(self.store))
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= 3:                          # e.g. full batches + the short last batch of an epoch; bound the pools
+                self._graphs.pop(next(iter(self._graphs)))
+            s_img, s_tgt = torch.empty_like(image), torch.empty_like(target)
+            s_img.copy_(image)
+            s_tgt.copy_(target)
             reducer, self.reducer = self.reducer, None          # no side-stream traffic inside the capture
             try:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    loss = self.forward_backward(self._s_img, self._s_tgt)
+                    loss = self.forward_backward(s_img, s_tgt)
                     if self.world == 1:
                         call("sgd_step", self.store.params, self.store.grads, self.mom_buf, self.store.total, self.hp)
             finally:
                 self.reducer = reducer
-            self._graph, self._s_loss = g, loss
+            ent = self._graphs[key] = (g, s_img, s_tgt, loss)
         else:
-            self._s_img.copy_(image, non_blocking=True)
-            self._s_tgt.copy_(target, non_blocking=True)
-        self._graph.replay()
+            ent[1].copy_(image, non_blocking=True)
+            ent[2].copy_(target, non_blocking=True)
+        self._graph = ent[0]
+        ent[0].replay()
         if self.world > 1:
             dist.all_reduce(self.store.grads, op=dist.ReduceOp.SUM, group=self.pg)
             call("sgd_step", self.store.params, self.store.grads, self.mom_buf, self.store.total, self.hp)
-        return self._s_loss
+        return ent[3]
 
     # ------------------------------------------------------------------ host-fed loop (what train_one_epoch does, pipelined)
     def run(self, host_batches):
@@ -157,6 +208,15 @@ class Trainer:
         (train_utils/train_and_eval.py:55-73) but without its two serialisation points: the H2D copy of batch i+1 runs on a
         copy stream while batch i computes (double-buffered device staging), and every loss is read back with an async D2H
         into pinned memory that is only waited for one step later ("lazy metric read-back")."""
+        out = []
+        for ready in self.run_iter(host_batches):
+            out.extend(ready)
+        return out
+
+    def run_iter(self, host_batches, pre_step=None, post_step=None):
+        """Generator form of `run` (what `train_utils.train_one_epoch` drives): yields once per issued step -- plus once at the
+        end -- the list of losses (floats, in step order) whose read-back has completed since the previous yield.
+        `pre_step()` runs right before a step is launched (set the LR there), `post_step()` right after."""
         dev = self.dev
         copy_stream = getattr(self, "_copy_stream", None) or torch.cuda.Stream(device=dev)
         self._copy_stream = copy_stream
@@ -171,7 +231,7 @@ class Trainer:
 
         def prefetch(slot, batch):
             img_h, tgt_h = batch
-            if bufs[slot] is None or bufs[slot][0].shape != img_h.shape:
+            if bufs[slot] is None or bufs[slot][0].shape != img_h.shape or bufs[slot][1].shape != tgt_h.shape:
                 bufs[slot] = (torch.empty(img_h.shape, dtype=torch.float32, device=dev), torch.empty(tgt_h.shape, dtype=torch.int64, device=dev))
             if freed[slot] is not None:
                 copy_stream.wait_event(freed[slot])          # the step that last read this slot has consumed it
@@ -182,23 +242,28 @@ class Trainer:
                 ev.record(copy_stream)
             ready[slot] = ev
 
-        losses, pending = [], []
+        pending = []
         nxt = next(it, None)
         if nxt is None:
-            return losses
+            return
         prefetch(0, nxt)
         i = 0
         while nxt is not None:
             slot = i & 1
+            done = []
             compute.wait_event(ready[slot])
+            if pre_step is not None:
+                pre_step()
             loss = self.step(bufs[slot][0], bufs[slot][1])
             ev = torch.cuda.Event()
             ev.record(compute)
             freed[slot] = ev
+            if post_step is not None:
+                post_step()
             if len(pending) >= 2:                            # wait for (and recycle the slot of) the loss issued two steps ago
                 h, e = pending.pop(0)
                 e.synchronize()
-                losses.append(float(h[0]))
+                done.append(float(h[0]))
                 free_hosts.append(h)
             host = free_hosts.pop()
             host.copy_(loss.detach().reshape(1), non_blocking=True)
@@ -209,7 +274,9 @@ class Trainer:
             if nxt is not None:
                 prefetch((i + 1) & 1, nxt)
             i += 1
+            yield done
+        done = []
         for h, e in pending:
             e.synchronize()
-            losses.append(float(h[0]))
-        return losses
+            done.append(float(h[0]))
+        yield done

@@ -38,10 +38,20 @@ Tensor = torch.Tensor
 # (conv outputs, BN+activation outputs, block outputs) is rounded to bf16 and back, arithmetic staying fp32.  This is the
 # "reference computed with bf16-stored activations" the bf16 parity tests compare against (tests/test_model_gpu.py).
 STORAGE = None
+# error-budget switch (tools/bf16_error_budget.py): storage classes listed here stay fp32 even when STORAGE is set.
+# classes: "dc_z" DoubleConv conv outputs (pre-BN), "dc_y" DoubleConv BN+ReLU outputs, "bc_z"/"bc_y" the same for the GRFB BasicConvs,
+# "conv" other conv outputs (FusionConv, shortcut, RGA, out_conv inputs), "edge" edge-enhancer tensors, "mca" MCALayer output,
+# "mix" FusionConv f+s*ca, "grfb" GRFB residual / gated outputs, "rga" RGA gate tensors, "up" upsampled tensors, "input"
+STORAGE_FP32 = frozenset()
+STORAGE_FP16 = frozenset()      # classes stored as IEEE fp16 (11-bit significand) instead of STORAGE
 
 
-def _r(x: Tensor) -> Tensor:
-    return x if STORAGE is None else x.to(STORAGE).to(x.dtype)
+def _r(x: Tensor, tag: str = "conv") -> Tensor:
+    if STORAGE is None or tag in STORAGE_FP32:
+        return x
+    if tag in STORAGE_FP16:
+        return x.to(torch.float16).to(x.dtype)
+    return x.to(STORAGE).to(x.dtype)
 
 
 def _bn(sd, p: str, x: Tensor, train: bool, momentum: float, upd: Optional[dict], eps: float = 1e-5) -> Tensor:
@@ -63,29 +73,29 @@ def _bn(sd, p: str, x: Tensor, train: bool, momentum: float, upd: Optional[dict]
     return x * scale[None, :, None, None] + (b - mean * scale)[None, :, None, None]
 
 
-def _conv(sd, p: str, x: Tensor, padding=0, dilation=1, groups=1) -> Tensor:
-    return _r(F.conv2d(x, sd[p + ".weight"], sd.get(p + ".bias"), 1, padding, dilation, groups))
+def _conv(sd, p: str, x: Tensor, padding=0, dilation=1, groups=1, tag: str = "conv") -> Tensor:
+    return _r(F.conv2d(x, sd[p + ".weight"], sd.get(p + ".bias"), 1, padding, dilation, groups), tag)
 
 
 def double_conv(sd, p, x, train, upd, i0=0, i1=3):
     """DoubleConv: src/unet.py:7-18 == src/EGM-UNet.py:44-55 (conv idx i0,i1; BN idx +1)."""
-    x = _r(F.relu(_bn(sd, f"{p}.{i0 + 1}", _conv(sd, f"{p}.{i0}", x, 1), train, 0.1, upd)))
-    x = _r(F.relu(_bn(sd, f"{p}.{i1 + 1}", _conv(sd, f"{p}.{i1}", x, 1), train, 0.1, upd)))
+    x = _r(F.relu(_bn(sd, f"{p}.{i0 + 1}", _conv(sd, f"{p}.{i0}", x, 1, tag="dc_z"), train, 0.1, upd)), "dc_y")
+    x = _r(F.relu(_bn(sd, f"{p}.{i1 + 1}", _conv(sd, f"{p}.{i1}", x, 1, tag="dc_z"), train, 0.1, upd)), "dc_y")
     return x
 
 
 def basic_conv(sd, p, x, train, upd, padding=0, dilation=1, groups=1, relu=True):
     """BasicConv: src/EGM-UNet.py:958-975 (BN momentum 0.01)."""
-    x = _bn(sd, p + ".bn", _conv(sd, p + ".conv", x, padding, dilation, groups), train, 0.01, upd)
-    return _r(F.relu(x) if relu else x)
+    x = _bn(sd, p + ".bn", _conv(sd, p + ".conv", x, padding, dilation, groups, tag="bc_z"), train, 0.01, upd)
+    return _r(F.relu(x) if relu else x, "bc_y")
 
 
 def edge_enhancer(sd, p, x, train, upd):
     """EdgeAwareFeatureEnhancer: src/EGM-UNet.py:872-886."""
-    e = _r(x - F.avg_pool2d(x, 3, 1, 1))                  # count_include_pad=True -> /9
-    z = _conv(sd, p + ".weight_generator.0", e)
+    e = _r(x - F.avg_pool2d(x, 3, 1, 1), "edge")          # count_include_pad=True -> /9
+    z = _conv(sd, p + ".weight_generator.0", e, tag="edge")
     w = torch.sigmoid(_bn(sd, p + ".weight_generator.1", z, train, 0.1, upd))
-    return _r(w * x + x)
+    return _r(w * x + x, "edge")
 
 
 def mca_gate(sd, p, x):
@@ -113,7 +123,7 @@ def mca_layer(sd, p, x):
     var = F.avg_pool2d((u - mean) ** 2, 3, 1, 1)
     n, c, h, w = u.shape
     shuf = u.view(n, 4, c // 4, h, w).transpose(1, 2).reshape(n, c, h, w)
-    return _r(0.4 * u + 0.2 * rng + 0.2 * var + 0.1 * (1.1 * u) + 0.1 * shuf)
+    return _r(0.4 * u + 0.2 * rng + 0.2 * var + 0.1 * (1.1 * u) + 0.1 * shuf, "mca")
 
 
 def fusion_conv(sd, p, x):
@@ -125,7 +135,7 @@ def fusion_conv(sd, p, x):
     def mlp(v):
         return F.conv2d(F.relu(F.conv2d(v, sd[p + ".channel_attention.fc.0.weight"])), sd[p + ".channel_attention.fc.2.weight"])
     ca = torch.sigmoid(mlp(F.adaptive_avg_pool2d(f, 1)) + mlp(F.adaptive_max_pool2d(f, 1)))
-    return _conv(sd, p + ".up", _r(f + s * ca))
+    return _conv(sd, p + ".up", _r(f + s * ca, "mix"))
 
 
 def grfb(sd, p, x, train, upd, visual=12, scale=0.1):
@@ -147,9 +157,9 @@ def grfb(sd, p, x, train, upd, visual=12, scale=0.1):
     cat = torch.cat([x, d, e, c], 1)
     out = fusion_conv(sd, p + ".fusion_conv", cat)
     zs = _conv(sd, p + ".shortcut.conv", x)
-    out = _r(F.relu(out * scale + _bn(sd, p + ".shortcut.bn", zs, train, 0.01, upd)))
+    out = _r(F.relu(out * scale + _bn(sd, p + ".shortcut.bn", zs, train, 0.01, upd)), "grfb")
     t = torch.sigmoid(_conv(sd, p + ".target_enhancer.0", out, 1))
-    return _r(out * (1 + t.mean(1, keepdim=True)))
+    return _r(out * (1 + t.mean(1, keepdim=True)), "grfb")
 
 
 def rga(sd, p, x):
@@ -158,13 +168,13 @@ def rga(sd, p, x):
     half = dim // 2
     fused = _conv(sd, p + ".proj_in", x)
     base, gates = fused[:, :half], fused[:, half:]
-    gates = _r(_conv(sd, p + ".dwconv", gates, 1, 1, gates.shape[1]) * sd[p + ".scale"])
+    gates = _r(_conv(sd, p + ".dwconv", gates, 1, 1, gates.shape[1]) * sd[p + ".scale"], "rga")
     out = base
     for i in range(2):
         g = gates[:, i * half:(i + 1) * half]
-        g = _r(F.gelu(_conv(sd, f"{p}.gate_convs.{i}.0", g)))
+        g = _r(F.gelu(_conv(sd, f"{p}.gate_convs.{i}.0", g)), "rga")
         g = torch.sigmoid(_conv(sd, f"{p}.gate_convs.{i}.2", g))
-        out = _r(out * g)
+        out = _r(out * g, "rga")
         if i == 0:
             out = _conv(sd, p + ".transform_convs.0", out)
     return _conv(sd, p + ".proj_out", out)
@@ -177,7 +187,7 @@ def up_block(sd, p, x1, x2, train, upd):
     else:
         x1 = F.interpolate(x1, scale_factor=2, mode="bilinear", align_corners=True)
     dy, dx = x2.shape[2] - x1.shape[2], x2.shape[3] - x1.shape[3]
-    x1 = _r(F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2]))
+    x1 = _r(F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2]), "up")
     return double_conv(sd, p + ".conv", torch.cat([x2, x1], 1), train, upd)
 
 
@@ -188,20 +198,20 @@ def down_block(sd, p, x, train, upd, variant):
     q = p + ".1"
     if variant == "unet":
         return double_conv(sd, q, x, train, upd)
-    x = _r(F.relu(_bn(sd, q + ".1", _conv(sd, q + ".0", x, 1), train, 0.1, upd)))
+    x = _r(F.relu(_bn(sd, q + ".1", _conv(sd, q + ".0", x, 1, tag="dc_z"), train, 0.1, upd)), "dc_y")
     if variant == "egm":
         x = mca_layer(sd, q + ".3", x)
         c2, g = 4, 7
     else:
         c2, g = 3, 6
-    x = _r(F.relu(_bn(sd, f"{q}.{c2 + 1}", _conv(sd, f"{q}.{c2}", x, 1), train, 0.1, upd)))
+    x = _r(F.relu(_bn(sd, f"{q}.{c2 + 1}", _conv(sd, f"{q}.{c2}", x, 1, tag="dc_z"), train, 0.1, upd)), "dc_y")
     return grfb(sd, f"{q}.{g}", x, train, upd)
 
 
 def forward(sd: Dict[str, Tensor], x: Tensor, variant: str = "egm", train: bool = True,
             bn_updates: Optional[dict] = None) -> Tensor:
     """Whole-model forward -> logits [N,num_classes,H,W]. variant in {'unet','egm','yuan'}."""
-    x1 = double_conv(sd, "in_conv", _r(x), train, bn_updates)
+    x1 = double_conv(sd, "in_conv", _r(x, "input"), train, bn_updates)
     x2 = down_block(sd, "down1", x1, train, bn_updates, variant)
     x3 = down_block(sd, "down2", x2, train, bn_updates, variant)
     x4 = down_block(sd, "down3", x3, train, bn_updates, variant)

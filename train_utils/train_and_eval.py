@@ -30,11 +30,82 @@ def evaluate(model, data_loader, device, num_classes):
     return confmat, dice.value.item()
 
 
+def _fused_trainer(model, optimizer, num_classes):
+    """The fused step (egm_unet_b200.trainer.Trainer: forward + criterion + backward + gradient all-reduce + SGD as ONE replayed
+    CUDA graph) bound to (model, optimizer) -- possible when the optimizer is the plain SGD train.py:113-118 builds over all of
+    the model's parameters.  Returns None otherwise (Adam, several parameter groups, nesterov, frozen parameters ...): the
+    caller then runs the generic autograd loop.  The optimizer stays the owner of the hyper-parameters (lr / momentum /
+    weight_decay are re-read every step, so LR schedulers work) and its `momentum_buffer` state tensors alias the trainer's flat
+    momentum buffer, so `optimizer.state_dict()` checkpoints (train.py:152-156) and `load_state_dict` resumes keep working."""
+    from egm_unet_b200.models import _B200Net
+    from egm_unet_b200.trainer import Trainer
+    if not isinstance(model, _B200Net) or type(optimizer) is not torch.optim.SGD or len(optimizer.param_groups) != 1:
+        return None
+    g = optimizer.param_groups[0]
+    params = list(model.parameters())
+    if g.get("nesterov") or g.get("dampening", 0) != 0 or g.get("maximize") or len(g["params"]) != len(params):
+        return None
+    if any(a is not b for a, b in zip(g["params"], params)) or not all(p.requires_grad and p.is_cuda for p in params):
+        return None
+    tr = getattr(model, "_egm_trainer", None)
+    if tr is None or tr._owner is not optimizer or tr.num_classes != num_classes:
+        cw = [1.0, 2.0] if num_classes == 2 else None
+        tr = Trainer(model, lr=g["lr"], momentum=g["momentum"], weight_decay=g["weight_decay"], class_weight=cw, ignore_index=255,
+                     use_graph=True)
+        tr._owner, tr.num_classes = optimizer, num_classes
+        object.__setattr__(model, "_egm_trainer", tr)
+    if not tr.store.valid():
+        tr._rebind_store()
+    # momentum: optimizer.state[p]["momentum_buffer"] <-> view of the flat buffer (copy in whatever a resume loaded)
+    st = tr.store
+    for p, off in zip(st.plist, st.offsets):
+        view = tr.mom_buf[off:off + p.numel()].view(p.shape)
+        cur = optimizer.state[p].get("momentum_buffer") if p in optimizer.state else None
+        if cur is not None and cur.data_ptr() != view.data_ptr():
+            view.copy_(cur.to(view.device, torch.float32))
+        optimizer.state[p]["momentum_buffer"] = view
+    return tr
+
+
+_SCALER_WARNED = [False]
+
+
 def train_one_epoch(model, optimizer, data_loader, device, epoch, num_classes, lr_scheduler, print_freq=10, scaler=None):
+    """Reference signature and return value (train_utils/train_and_eval.py:43-75).
+
+    `scaler`: the reference uses a GradScaler for fp16 autocast (:57-65).  The B200 path stores activations in bf16 and
+    accumulates in fp32 inside its own kernels; bf16 has fp32's exponent range, so no loss scaling is needed.  A scaler is
+    accepted for call compatibility and deliberately left untouched (a warning says so once)."""
+    if scaler is not None and not _SCALER_WARNED[0]:
+        import warnings
+        warnings.warn("train_one_epoch: `scaler` is accepted for API compatibility but not used -- the B200 path computes in "
+                      "bf16 storage / fp32 accumulate, which needs no loss scaling")
+        _SCALER_WARNED[0] = True
     model.train()
     metric_logger = utils.MetricLogger(delimiter="  ")
     metric_logger.add_meter('lr', utils.SmoothedValue(window_size=1, fmt='{value:.6f}'))
     header = 'Epoch: [{}]'.format(epoch)
+    tr = _fused_trainer(model, optimizer, num_classes) if torch.device(device).type == "cuda" else None
+    if tr is not None:
+        # fast path: batches are prefetched to the device on a copy stream, each step is one CUDA-graph replay, and the loss is
+        # read back lazily (two steps later) instead of the reference's per-step `loss.item()` sync (:73).  MetricLogger sees every
+        # loss exactly once, in order; by the end of the epoch its statistics are those of the reference loop.
+        g = optimizer.param_groups[0]
+
+        def pre_step():
+            tr.set_hyper(g["lr"], g["momentum"], g["weight_decay"])
+
+        def post_step():
+            optimizer._opt_called = True          # the step ran inside the fused kernel sequence
+            lr_scheduler.step()
+
+        lr = g["lr"]
+        for ready in tr.run_iter(metric_logger.log_every(data_loader, print_freq, header), pre_step, post_step):
+            for v in ready:
+                metric_logger.update(loss=v)
+            lr = g["lr"]
+            metric_logger.update(lr=lr)
+        return metric_logger.meters["loss"].global_avg, lr
     loss_weight = torch.as_tensor([1.0, 2.0], device=device) if num_classes == 2 else None
     for image, target in metric_logger.log_every(data_loader, print_freq, header):
         image, target = image.to(device, non_blocking=True), target.to(device, non_blocking=True)
