@@ -125,3 +125,14 @@ extern "C" int egm_cast_to_f32(const void* src, float* dst, int dtype, long long
   EGM_DISPATCH_DTYPE(dtype, (k_cast_to_f32<T><<<egm_grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)src, dst, n, accumulate)));
   EGM_LAUNCH_CHECK("cast_to_f32"); return EGM_OK;
 }
+
+// out[r][c] = w[r][c] * scale[r]: per-output-channel scale of an inference BatchNorm folded into the conv weight [Cout][Cin*kh*kw]
+__global__ void k_scale_rows(const float* __restrict__ w, const float* __restrict__ scale, float* __restrict__ out, long long total, long long cols) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) out[i] = w[i] * scale[i / cols];
+}
+extern "C" int egm_scale_rows(const float* w, const float* scale, float* out, int rows, long long cols, void* stream) {
+  const long long total = (long long)rows * cols;
+  if (total == 0) return EGM_OK;
+  k_scale_rows<<<egm_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, scale, out, total, cols);
+  EGM_LAUNCH_CHECK("scale_rows"); return EGM_OK;
+}

@@ -78,48 +78,99 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
                  "=r"(r[30]), "=r"(r[31])
                : "r"(taddr));
 }
-// convert 16 fp32 accumulator columns (+bias) to bf16 and store them as two 16-byte vectors
+// Output side of a conv: row pointer = y + pixel*cs + coff; only channels < valid are written; acc: y += result.
+struct OutView { long long cs, coff; int valid, acc, vec, dense; };  // vec: every row start is 16-byte aligned; dense: all padded channels exist, plain overwrite
+// 16 fp32 values -> bf16, written to the channels [0, nvalid) of the row `yp`; fast path = two 16-byte stores
+template <bool RELU>
+__device__ __forceinline__ void store16f(__nv_bfloat16* yp, float (&f)[16], int nvalid, const OutView& o) {
+  if constexpr (RELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+  }
+  if (nvalid >= 16 && o.vec && !o.acc) {
+    uint4 q[2]; __nv_bfloat162* qb = reinterpret_cast<__nv_bfloat162*>(q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) qb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    *reinterpret_cast<uint4*>(yp) = q[0];
+    *reinterpret_cast<uint4*>(yp + 8) = q[1];
+    return;
+  }
+  if (nvalid <= 0) return;
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    if (nvalid >= hf * 8 + 8 && o.vec) {
+      uint4 q; __nv_bfloat162* qb = reinterpret_cast<__nv_bfloat162*>(&q);
+      if (o.acc) {
+        q = *reinterpret_cast<const uint4*>(yp + hf * 8);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float2 old = __bfloat1622float2(qb[j]); f[hf * 8 + 2 * j] += old.x; f[hf * 8 + 2 * j + 1] += old.y; }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) qb[j] = __floats2bfloat162_rn(f[hf * 8 + 2 * j], f[hf * 8 + 2 * j + 1]);
+      *reinterpret_cast<uint4*>(yp + hf * 8) = q;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (hf * 8 + j < nvalid) {
+          float t = f[hf * 8 + j];
+          if (o.acc) t += __bfloat162float(yp[hf * 8 + j]);
+          yp[hf * 8 + j] = __float2bfloat16_rn(t);
+        }
+    }
+  }
+}
+// convert 16 fp32 accumulator columns (+bias, optional ReLU) to bf16 and store them as two 16-byte vectors (dense rows)
+template <bool RELU>
 __device__ __forceinline__ void store16(__nv_bfloat16* yp, const uint32_t* v, const float* bp) {
   uint4 o[2]; __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
     if (bp) { f0 += bp[2 * j]; f1 += bp[2 * j + 1]; }
+    if constexpr (RELU) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
     ob[j] = __floats2bfloat162_rn(f0, f1);
   }
   *reinterpret_cast<uint4*>(yp) = o[0];
   *reinterpret_cast<uint4*>(yp + 8) = o[1];
 }
-// Output side of a conv: row pointer = y + pixel*cs + coff; only channels < valid are written; acc: y += result.
-struct OutView { long long cs, coff; int valid, acc, vec, dense; };  // vec: every row start is 16-byte aligned; dense: all padded channels exist, plain overwrite
-// 16 accumulator columns starting at channel c of the row `yp` (already offset by c): fast path = two 16-byte stores
+// 16 accumulator columns starting at channel c of the row `yp` (already offset by c), any output view
+template <bool RELU>
 __device__ __forceinline__ void store16v(__nv_bfloat16* yp, const uint32_t* v, const float* bp, int nvalid, const OutView& o) {
-  if (nvalid >= 16 && o.vec && !o.acc) { store16(yp, v, bp); return; }
+  if (nvalid >= 16 && o.vec && !o.acc) { store16<RELU>(yp, v, bp); return; }
   if (nvalid <= 0) return;
+  float f[16];
 #pragma unroll
-  for (int hf = 0; hf < 2; ++hf) {
-    float f[8];
+  for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + (bp ? bp[j] : 0.f);
+  store16f<RELU>(yp, f, nvalid, o);
+}
+// ---- epilogue modes (template parameter EPI of the forward kernels)
+//   EPI_PLAIN  y = acc + bias
+//   EPI_RELU   y = relu(acc + bias)          inference: BatchNorm folded into the weights (scale) and the bias (shift), ReLU here
+//   16/32/64   y = acc + bias AND per-channel sum / sum of squares of the fp32 accumulators for train-mode BatchNorm
+//              (Cout == EPI).  Each epilogue thread owns one pixel row of every tile its CTA processes, so it keeps running
+//              sums of its row's EPI channels in registers across ALL tiles (2 FP ops per value, no cross-lane traffic per tile);
+//              one shuffle + shared-memory + fp64-atomic reduction per CTA at the very end.  (Round 1 reduced per tile with a
+//              32-lane butterfly and lost more in the narrow layers' epilogue than the separate statistics pass cost.)
+constexpr int EPI_PLAIN = 0, EPI_RELU = 1;
+template <int NC>
+__device__ __forceinline__ void stats_accum16(float (&s1)[NC], float (&s2)[NC], int c0, const float (&f)[16]) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[hf * 8 + j]) + (bp ? bp[hf * 8 + j] : 0.f);
-    if (nvalid >= hf * 8 + 8 && o.vec) {
-      uint4 q; __nv_bfloat162* qb = reinterpret_cast<__nv_bfloat162*>(&q);
-      if (o.acc) {
-        q = *reinterpret_cast<const uint4*>(yp + hf * 8);
+  for (int j = 0; j < 16; ++j) { s1[c0 + j] += f[j]; s2[c0 + j] = fmaf(f[j], f[j], s2[c0 + j]); }
+}
+// red: shared [4 warps][2][NC] floats; out: global [2][cvalid] doubles (atomically accumulated); ew = epilogue warp 0..3
+template <int NC>
+__device__ __forceinline__ void stats_flush(const float (&s1)[NC], const float (&s2)[NC], float* red, double* __restrict__ out, int cvalid, int ew, int lane) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { float2 old = __bfloat1622float2(qb[j]); f[2 * j] += old.x; f[2 * j + 1] += old.y; }
-      }
+  for (int c = 0; c < NC; ++c) {
+    float a = s1[c], b = s2[c];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) qb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-      *reinterpret_cast<uint4*>(yp + hf * 8) = q;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (hf * 8 + j < nvalid) {
-          float t = f[j];
-          if (o.acc) t += __bfloat162float(yp[hf * 8 + j]);
-          yp[hf * 8 + j] = __float2bfloat16_rn(t);
-        }
-    }
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if (lane == 0) { red[ew * 2 * NC + c] = a; red[ew * 2 * NC + NC + c] = b; }
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  for (int i = ew * 32 + lane; i < 2 * NC; i += 128) {
+    const int k = i / NC, c = i - k * NC;
+    if (c < cvalid) atomicAdd(out + (long long)k * cvalid + c, (double)red[i] + (double)red[2 * NC + i] + (double)red[4 * NC + i] + (double)red[6 * NC + i]);
   }
 }
 // one elected lane of a converged warp (keeps the surrounding control flow warp-uniform, so loop state lives in uniform registers)
@@ -205,6 +256,7 @@ struct ConvTcParams {
   int kps;                                            // 9: thin 3x3 layers -- all 9 tap tiles of an output tile share ONE pipeline stage
                                                       // (one barrier round trip, straight-line TMA issue and MMA issue per tile); else 1
   OutView out;
+  double* stats;                                      // EPI >= 16: [2][out.valid] per-channel sum / sum of squares (atomically accumulated)
 };
 
 // KPS consecutive K iterations of one stage, KS MMAs each, as straight-line code
@@ -218,8 +270,11 @@ __device__ __forceinline__ void issue_group(uint32_t d, uint64_t ad, uint64_t bd
   }
 }
 
+template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                                                           __nv_bfloat16* __restrict__ y, const float* __restrict__ bias, ConvTcParams p) {
+  constexpr bool RELU = EPI == EPI_RELU;
+  constexpr int NSTAT = EPI >= 16 ? EPI : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int taps = p.kh * p.kw;
@@ -344,6 +399,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;                       // pixel index inside the 8x16 patch
     int acc = 0; uint32_t aph = 0;
+    float s1[NSTAT], s2[NSTAT];
+#pragma unroll
+    for (int c = 0; c < NSTAT; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
     for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
       const int chunk = tile % p.coChunks, sp_t = tile / p.coChunks;
       const int n = sp_t / tilesPerImg, r = sp_t - n * tilesPerImg;
@@ -356,32 +414,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.accCols);
-      if (p.out.dense && (p.nChunk & 31) == 0) {                      // hot path of the DoubleConv layers: no per-store decisions
+      if constexpr (EPI >= 16) {                                      // train-mode BN statistics from the fp32 accumulators (Cout == EPI, one slice)
+#pragma unroll
+        for (int c = 0; c < EPI; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(t0 + c, v);
+          tmem_ld_wait();
+          if (valid) {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + (bp ? bp[c + j] : 0.f);
+            stats_accum16<NSTAT>(s1, s2, c, f);
+            store16f<false>(yp + c, f, nv - c, p.out);
+          }
+        }
+      } else if (p.out.dense && (p.nChunk & 31) == 0) {               // hot path of the DoubleConv layers: no per-store decisions
         for (int c = 0; c < p.nChunk; c += 32) {
           uint32_t v[32];
           tmem_ld32(t0 + c, v);
           tmem_ld_wait();
-          if (valid) { store16(yp + c, v, bp ? bp + c : nullptr); store16(yp + c + 16, v + 16, bp ? bp + c + 16 : nullptr); }
+          if (valid) { store16<RELU>(yp + c, v, bp ? bp + c : nullptr); store16<RELU>(yp + c + 16, v + 16, bp ? bp + c + 16 : nullptr); }
         }
       } else if (p.out.dense) {
         for (int c = 0; c < p.nChunk; c += 16) {
           uint32_t v[16];
           tmem_ld16(t0 + c, v);
           tmem_ld_wait();
-          if (valid) store16(yp + c, v, bp ? bp + c : nullptr);
+          if (valid) store16<RELU>(yp + c, v, bp ? bp + c : nullptr);
         }
       } else {
         for (int c = 0; c < cend; c += 16) {
           uint32_t v[16];
           tmem_ld16(t0 + c, v);
           tmem_ld_wait();
-          if (valid) store16v(yp + c, v, bp ? bp + c : nullptr, nv - c, p.out);
+          if (valid) store16v<RELU>(yp + c, v, bp ? bp + c : nullptr, nv - c, p.out);
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; aph ^= 1; }
     }
+    if constexpr (EPI >= 16) stats_flush<NSTAT>(s1, s2, (float*)(tmem_slot + 4), p.stats, p.out.valid, q, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -409,6 +482,7 @@ struct ConvHaloParams {
   int exp;                                           // EGM_DIAG builds only: EGM_EXP bit mask (timing ablations; results are wrong):
                                                      // 1 = no global stores, 4 = no MMAs, 8 = no TMA loads.  Compiled out of the shipped .so.
   OutView out;
+  double* stats;                                     // EPI >= 16: [2][out.valid] per-channel sum / sum of squares (atomically accumulated)
 };
 constexpr int HT_H = 16, HT_W = 8;
 #ifdef EGM_DIAG
@@ -417,8 +491,11 @@ constexpr int HT_H = 16, HT_W = 8;
 #define EGM_EXPBIT(b) (0)
 #endif
 
+template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                                                                __nv_bfloat16* __restrict__ y, const float* __restrict__ bias, ConvHaloParams p) {
+  constexpr bool RELU = EPI == EPI_RELU;
+  constexpr int NSTAT = EPI >= 16 ? EPI : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int taps = p.kh * p.kw;
@@ -577,6 +654,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
     const int q = warp & 3;
     const int row = q * 32 + lane;                       // pixel index inside the 16x8 patch (row-major, 8 wide)
     int acc = 0; uint32_t aph = 0;
+    float s1[NSTAT], s2[NSTAT];
+#pragma unroll
+    for (int c = 0; c < NSTAT; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
     for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
       int n = tile / (p.tilesH * p.tilesW); int r = tile - n * p.tilesH * p.tilesW;
       int h = (r / p.tilesW) * HT_H + row / HT_W, w = (r % p.tilesW) * HT_W + row % HT_W;
@@ -586,32 +666,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.accCols);
-      if (p.out.dense && (p.Cout & 31) == 0) {
+      if constexpr (EPI >= 16) {                                      // train-mode BN statistics from the fp32 accumulators (Cout == EPI)
+#pragma unroll
+        for (int c = 0; c < EPI; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(t0 + c, v);
+          tmem_ld_wait();
+          if (valid) {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + (bias ? bias[c + j] : 0.f);
+            stats_accum16<NSTAT>(s1, s2, c, f);
+            store16f<false>(yp + c, f, nv - c, p.out);
+          }
+        }
+      } else if (p.out.dense && (p.Cout & 31) == 0) {
         for (int c = 0; c < p.Cout; c += 32) {
           uint32_t v[32];
           tmem_ld32(t0 + c, v);
           tmem_ld_wait();
-          if (valid && !EGM_EXPBIT(1)) { store16(yp + c, v, bias ? bias + c : nullptr); store16(yp + c + 16, v + 16, bias ? bias + c + 16 : nullptr); }
+          if (valid && !EGM_EXPBIT(1)) { store16<RELU>(yp + c, v, bias ? bias + c : nullptr); store16<RELU>(yp + c + 16, v + 16, bias ? bias + c + 16 : nullptr); }
         }
       } else if (p.out.dense) {
         for (int c = 0; c < p.Cout; c += 16) {
           uint32_t v[16];
           tmem_ld16(t0 + c, v);
           tmem_ld_wait();
-          if (valid) store16(yp + c, v, bias ? bias + c : nullptr);
+          if (valid) store16<RELU>(yp + c, v, bias ? bias + c : nullptr);
         }
       } else {
         for (int c = 0; c < cend; c += 16) {
           uint32_t v[16];
           tmem_ld16(t0 + c, v);
           tmem_ld_wait();
-          if (valid) store16v(yp + c, v, bias ? bias + c : nullptr, nv - c, p.out);
+          if (valid) store16v<RELU>(yp + c, v, bias ? bias + c : nullptr, nv - c, p.out);
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       if (++acc == p.nacc) { acc = 0; aph ^= 1; }
     }
+    if constexpr (EPI >= 16) stats_flush<NSTAT>(s1, s2, (float*)(tmem_slot + 4), p.stats, p.out.valid, q, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -629,7 +724,7 @@ static bool halo_eligible(int Cin, int Cout, int kh, int dil) {
   return wbytes <= 100 * 1024;
 }
 static int launch_conv_halo(const NhwcView& xv, const void* wpk, const float* bias, void* y, const OutView& ov, int N, int H, int W, int Cin, int Cout, int kh,
-                            int kw, int dil, cudaStream_t st) {
+                            int kw, int dil, int epi, double* stats, cudaStream_t st) {
   ConvHaloParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
   p.tilesH = cdiv(H, HT_H); p.tilesW = cdiv(W, HT_W); p.numTiles = N * p.tilesH * p.tilesW;
@@ -650,11 +745,18 @@ static int launch_conv_halo(const NhwcView& xv, const void* wpk, const float* bi
   p.out = ov;
   int e = make_map_nhwc(&tmX, xv, N, H, W, p.rowB / 2, p.haloW, p.haloH); if (e) return e;
   e = make_map_w(&tmW, wpk, kh * kw, Cout, Cin, p.rowB / 2, Cout); if (e) return e;
-  size_t smem = wres + (size_t)p.stages * p.haloStride + 1024 + 1408;
-  static bool attr_set[64] = {};
-  egm_ensure_smem(k_conv_tc_halo, 227 * 1024, attr_set);
+  size_t smem = wres + (size_t)p.stages * p.haloStride + 1024 + 1408 + (epi >= 16 ? 2048 : 0);
   int grid = p.numTiles < egm_num_sms() ? p.numTiles : egm_num_sms();
-  k_conv_tc_halo<<<grid, TC_THREADS, smem, st>>>(tmX, tmW, (__nv_bfloat16*)y, bias, p);
+  p.stats = stats;
+#define EGM_LAUNCH_HALO(E)                                                                                 \
+  {                                                                                                        \
+    static bool attr_set[64] = {};                                                                         \
+    egm_ensure_smem(k_conv_tc_halo<E>, 227 * 1024, attr_set);                                              \
+    k_conv_tc_halo<E><<<grid, TC_THREADS, smem, st>>>(tmX, tmW, (__nv_bfloat16*)y, bias, p);               \
+  }
+  if (epi == EPI_PLAIN) EGM_LAUNCH_HALO(EPI_PLAIN) else if (epi == EPI_RELU) EGM_LAUNCH_HALO(EPI_RELU)
+  else if (epi == 16) EGM_LAUNCH_HALO(16) else if (epi == 32) EGM_LAUNCH_HALO(32) else EGM_LAUNCH_HALO(64)
+#undef EGM_LAUNCH_HALO
   return egm_check_launch("conv2d_tc_halo");
 }
 
@@ -670,9 +772,18 @@ extern "C" long long egm_conv2d_tc_workspace_bytes(int, int, int, int, int, int,
 // General form: x and y are channel-strided views (egm_copy_slice semantics).  Cin / Cout are the PADDED channel counts of the
 // packed weight [taps][Cout][Cin] (multiples of 16); channels >= cin_valid read as zero (TMA out-of-bounds fill) and channels
 // >= cout_valid are not written.  accumulate != 0: y += conv (dgrad into a gradient that already holds other contributions).
-extern "C" int egm_conv2d_tc_view(const void* x, long long x_cstride, long long x_coff, int cin_valid, const void* w_packed_bf16, const float* bias,
-                                  void* y, long long y_cstride, long long y_coff, int cout_valid, int accumulate, int N, int H, int W, int Cin,
-                                  int Cout, int kh, int kw, int dil, void* stream) {
+// Train-mode BN statistics in the epilogue are available for single-slice layers with 16 / 32 / 64 (padded) output channels --
+// the layers whose pre-BN tensors are large; wider layers have small maps and keep the streaming statistics kernel.
+extern "C" int egm_conv2d_tc_stats_supported(int Cin, int Cout, int kh, int kw, int dil) {
+  return egm_conv2d_tc_supported(Cin, Cout, kh, kw, dil, 1) && (Cout == 16 || Cout == 32 || Cout == 64);
+}
+// Extended form.  relu != 0: y = relu(conv + bias) (inference with BatchNorm folded into weights / bias).  stats != NULL: in addition to
+// writing y, atomically add the per-channel sum and sum of squares of the fp32 results (conv + bias, before rounding) over all N*H*W
+// pixels into stats[0 .. cout_valid) and stats[cout_valid .. 2*cout_valid) (doubles, zeroed by the caller) -- the batch statistics of
+// the nn.BatchNorm2d that follows the conv (src/EGM-UNet.py:44-55, :958-975), taken in the conv epilogue.
+extern "C" int egm_conv2d_tc_ex(const void* x, long long x_cstride, long long x_coff, int cin_valid, const void* w_packed_bf16, const float* bias,
+                                void* y, long long y_cstride, long long y_coff, int cout_valid, int accumulate, int N, int H, int W, int Cin,
+                                int Cout, int kh, int kw, int dil, int relu, double* stats, void* stream) {
   EGM_REQUIRE(egm_conv2d_tc_supported(Cin, Cout, kh, kw, dil, 1), EGM_E_SHAPE, "conv2d_tc: unsupported shape %d->%d k%d", Cin, Cout, kh);
   EGM_REQUIRE(cin_valid >= 1 && cin_valid <= Cin && cout_valid >= 1 && cout_valid <= Cout, EGM_E_SHAPE, "conv2d_tc: valid channels out of range");
   EGM_REQUIRE(((uintptr_t)w_packed_bf16 & 15) == 0, EGM_E_ALIGN, "conv2d_tc: weights must be 16-byte aligned");
@@ -680,7 +791,11 @@ extern "C" int egm_conv2d_tc_view(const void* x, long long x_cstride, long long 
   const NhwcView xv{x, x_cstride, x_coff, cin_valid};
   OutView ov{y_cstride, y_coff, cout_valid, accumulate ? 1 : 0, (y_cstride % 8 == 0 && y_coff % 8 == 0 && ((uintptr_t)y & 15) == 0) ? 1 : 0, 0};
   ov.dense = (ov.vec && !ov.acc && cout_valid == Cout) ? 1 : 0;
-  if (halo_eligible(Cin, Cout, kh, dil)) return launch_conv_halo(xv, w_packed_bf16, bias, y, ov, N, H, W, Cin, Cout, kh, kw, dil, (cudaStream_t)stream);
+  EGM_REQUIRE(!(relu && stats), EGM_E_BADARG, "conv2d_tc: relu and stats are exclusive (statistics are taken of the pre-BN tensor)");
+  EGM_REQUIRE(!stats || egm_conv2d_tc_stats_supported(Cin, Cout, kh, kw, dil), EGM_E_SHAPE, "conv2d_tc: epilogue statistics need Cout in {16,32,64}");
+  EGM_REQUIRE(!stats || !accumulate, EGM_E_BADARG, "conv2d_tc: statistics of an accumulating conv are undefined");
+  const int epi = stats ? Cout : (relu ? EPI_RELU : EPI_PLAIN);
+  if (halo_eligible(Cin, Cout, kh, dil)) return launch_conv_halo(xv, w_packed_bf16, bias, y, ov, N, H, W, Cin, Cout, kh, kw, dil, epi, stats, (cudaStream_t)stream);
   ConvTcParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.dil = dil; p.pad = dil * (kh - 1) / 2;
   p.coChunks = (Cout + 255) / 256; p.nChunk = Cout / p.coChunks;
@@ -698,12 +813,25 @@ extern "C" int egm_conv2d_tc_view(const void* x, long long x_cstride, long long 
   p.out = ov;
   int e = make_map_nhwc(&tmX, xv, N, H, W, p.bkc, TILE_W, TILE_H); if (e) return e;
   e = make_map_w(&tmW, w_packed_bf16, kh * kw, Cout, Cin, p.bkc, p.nChunk); if (e) return e;
-  size_t smem = (size_t)p.stages * per + (p.wres ? (size_t)wresBytes : 0) + 1024 + 1024;
-  static bool attr_set[64] = {};
-  egm_ensure_smem(k_conv_tc, 227 * 1024, attr_set);
+  size_t smem = (size_t)p.stages * per + (p.wres ? (size_t)wresBytes : 0) + 1024 + 1024 + (epi >= 16 ? 2048 : 0);
   int grid = p.numTiles < egm_num_sms() ? p.numTiles : egm_num_sms();
-  k_conv_tc<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmX, tmW, (__nv_bfloat16*)y, bias, p);
+  p.stats = stats;
+#define EGM_LAUNCH_TC(E)                                                                                          \
+  {                                                                                                               \
+    static bool attr_set[64] = {};                                                                                \
+    egm_ensure_smem(k_conv_tc<E>, 227 * 1024, attr_set);                                                          \
+    k_conv_tc<E><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmX, tmW, (__nv_bfloat16*)y, bias, p);         \
+  }
+  if (epi == EPI_PLAIN) EGM_LAUNCH_TC(EPI_PLAIN) else if (epi == EPI_RELU) EGM_LAUNCH_TC(EPI_RELU)
+  else if (epi == 16) EGM_LAUNCH_TC(16) else if (epi == 32) EGM_LAUNCH_TC(32) else EGM_LAUNCH_TC(64)
+#undef EGM_LAUNCH_TC
   EGM_LAUNCH_CHECK("conv2d_tc"); return EGM_OK;
+}
+extern "C" int egm_conv2d_tc_view(const void* x, long long x_cstride, long long x_coff, int cin_valid, const void* w_packed_bf16, const float* bias,
+                                  void* y, long long y_cstride, long long y_coff, int cout_valid, int accumulate, int N, int H, int W, int Cin,
+                                  int Cout, int kh, int kw, int dil, void* stream) {
+  return egm_conv2d_tc_ex(x, x_cstride, x_coff, cin_valid, w_packed_bf16, bias, y, y_cstride, y_coff, cout_valid, accumulate, N, H, W, Cin, Cout, kh, kw, dil,
+                          0, nullptr, stream);
 }
 extern "C" int egm_conv2d_tc(const void* x, const void* w_packed_bf16, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
                              int kh, int kw, int dil, void* stream) {

@@ -76,6 +76,24 @@ class Ctx:
         self.use_tc = use_tc and dtype == torch.bfloat16
         self.f32 = dict(dtype=torch.float32, device=device)
         self.wplan: Optional["WeightPlan"] = None   # batched weight preparation (Trainer); None = per-conv pack kernels
+        self.fuse_bn = os.environ.get("EGM_NO_BN_FUSE", "0") != "1"   # BN statistics / inference BN+ReLU in the conv epilogue
+        self._arena, self._arena_off = None, 0
+
+    ARENA_DOUBLES = 1 << 16
+
+    def stat_slice(self, n: int) -> torch.Tensor:
+        """n zeroed fp64 accumulators for a conv epilogue's BN statistics: slices of ONE arena zeroed by ONE memset per step."""
+        if n > self.ARENA_DOUBLES // 8:
+            t = self.f64(n)
+            call("memset_zero", t, n * 8)
+            return t
+        if self._arena is None or self._arena_off + n > self.ARENA_DOUBLES:
+            self._arena = self.f64(self.ARENA_DOUBLES)
+            call("memset_zero", self._arena, self.ARENA_DOUBLES * 8)
+            self._arena_off = 0
+        t = self._arena[self._arena_off:self._arena_off + n]
+        self._arena_off += (n + 1) // 2 * 2
+        return t
 
     # ---- allocation helpers
     def empty(self, *shape, dtype=None):
@@ -231,11 +249,30 @@ def _conv_run(ctx, pk: PackedConv, x_t, x_cs, x_co, w, bias, y_t, y_cs, y_co, ac
         call("conv2d_direct", x_t, x_cs, x_co, w, bias, y_t, y_cs, y_co, acc, ctx.code, n, h, wd_, cin, cout, pk.kh, pk.kw, pk.dil, pk.groups)
 
 
+class Epi:
+    """Epilogue request of a tcgen05 conv (egm_conv2d_tc_ex): ReLU (inference, BN folded), BN batch statistics (training),
+    and / or writing into a channel slice of an existing tensor."""
+    __slots__ = ("relu", "stats", "out", "out_coff", "sums")
+
+    def __init__(self, relu=False, stats=False, out=None, out_coff=0):
+        self.relu, self.stats, self.out, self.out_coff, self.sums = relu, stats, out, out_coff, None
+
+
+def tc_route(ctx: Ctx, cin: int, co: int, kh: int, kw: int, dilation: int, groups: int, sliced: bool, tc_ok: bool = True):
+    """(route, padded Cin, padded Cout): 'native' = dense tcgen05 conv, 'lifted' = zero-padded / block-diagonal 16-aligned one, None = CUDA cores"""
+    if ctx.use_tc and tc_ok and not sliced and abi.query("conv2d_tc_supported", cin, co, kh, kw, dilation, groups):
+        return "native", cin, co
+    if ctx.use_tc and tc_ok and abi.query("conv2d_tc_supported", _pad16(cin), _pad16(co), kh, kw, dilation, 1):
+        return "lifted", _pad16(cin), _pad16(co)
+    return None, cin, co
+
+
 def conv2d(ctx: Ctx, x: Var, weight: torch.Tensor, bias: Optional[torch.Tensor], *, groups: int = 1, dilation: int = 1,
            x_coff: int = 0, x_cin: Optional[int] = None, wgrad_sink: Optional[Callable] = None,
-           bgrad_sink: Optional[Callable] = None, tc_ok: bool = True, wspec: Optional[WSpec] = None) -> Var:
+           bgrad_sink: Optional[Callable] = None, tc_ok: bool = True, wspec: Optional[WSpec] = None, epi: Optional[Epi] = None) -> Var:
     """y = conv2d(x[..., x_coff:x_coff+Cin], weight) + bias  (stride 1, "same" padding).  `weight` is the reference
-    [Cout, Cin/groups, kh, kw] fp32 parameter (or a derived tensor; then `wgrad_sink(dw)` receives its gradient)."""
+    [Cout, Cin/groups, kh, kw] fp32 parameter (or a derived tensor; then `wgrad_sink(dw)` receives its gradient).
+    `epi` (tcgen05 routes only; the caller checks `tc_route`) asks for a fused epilogue."""
     n, h, w, ctot = x.shape
     wparam, bparam = weight, bias          # gradient slots are keyed by the nn.Parameter objects
     weight, bias = _p(weight), _p(bias)
@@ -243,23 +280,32 @@ def conv2d(ctx: Ctx, x: Var, weight: torch.Tensor, bias: Optional[torch.Tensor],
     cin = cig * groups
     assert (x_cin or ctot - x_coff) == cin, (x.shape, (co, cig, kh, kw), x_coff)
     sliced = not (x_coff == 0 and cin == ctot)
-    native_tc = ctx.use_tc and tc_ok and not sliced and abi.query("conv2d_tc_supported", cin, co, kh, kw, dilation, groups)
-    lifted_tc = ctx.use_tc and tc_ok and not native_tc and abi.query("conv2d_tc_supported", _pad16(cin), _pad16(co), kh, kw, dilation, 1)
+    route, _, _ = tc_route(ctx, cin, co, kh, kw, dilation, groups, sliced, tc_ok)
+    native_tc, lifted_tc = route == "native", route == "lifted"
+    assert epi is None or route is not None, "fused conv epilogues exist on the tcgen05 routes only"
     # derived weights without a WSpec (ConvTranspose2d repack) keep the per-conv path: their tensors are rebuilt every step
     plan = ctx.wplan if (native_tc or lifted_tc) and ctx.record and (wspec is not None or wgrad_sink is None) else None
     if plan is not None:
         if wspec is None:
             wspec = WSpec(0, (wparam,), (bparam,), (co, cig, kh, kw), groups)
         if plan.ready:
-            return _conv2d_planned(ctx, x, plan.jobs[wspec.key], bias, bparam, dilation, x_coff, cin, bgrad_sink)
+            return _conv2d_planned(ctx, x, plan.jobs[wspec.key], bias, bparam, dilation, x_coff, cin, bgrad_sink, epi)
         plan.register(ctx, wspec, co if native_tc else _pad16(co), cin if native_tc else _pad16(cin))
     assert weight is not None, "a derived weight may only be omitted once the weight plan is ready"
     if lifted_tc:
-        return _conv2d_lifted(ctx, x, wparam, bparam, weight, bias, groups, dilation, x_coff, cin, wgrad_sink, bgrad_sink)
+        return _conv2d_lifted(ctx, x, wparam, bparam, weight, bias, groups, dilation, x_coff, cin, wgrad_sink, bgrad_sink, epi)
     pk = PackedConv(ctx, weight, groups, dilation, tc_ok and not sliced)
-    y = ctx.empty(n, h, w, co)
-    _conv_run(ctx, pk, x.t, ctot, x_coff, pk.wf, bias, y, co, 0, 0, n, h, w, cin, co)
-    out = Var(y)
+    if epi is not None:
+        assert pk.tc
+        y, ycs, yco = (ctx.empty(n, h, w, co), co, 0) if epi.out is None else (epi.out.t, epi.out.C, epi.out_coff)
+        if epi.stats:
+            epi.sums = ctx.stat_slice(2 * co)
+        call("conv2d_tc_ex", x.t, ctot, x_coff, cin, pk.wf, bias, y, ycs, yco, co, 0, n, h, w, cin, co, pk.kh, pk.kw, pk.dil, int(epi.relu), epi.sums)
+        out = Var(y) if epi.out is None else epi.out
+    else:
+        y = ctx.empty(n, h, w, co)
+        _conv_run(ctx, pk, x.t, ctot, x_coff, pk.wf, bias, y, co, 0, 0, n, h, w, cin, co)
+        out = Var(y)
     if ctx.record:
         def bwd():
             dy = out.grad
@@ -313,16 +359,24 @@ def _tc_read_view(ctx, t, n, h, w, ctot, coff, c, cp):
     return tp, cp, 0, cp
 
 
-def _conv_tc_fwd_bwd(ctx, x, x_coff, cin, cinp, co, cop, kh, kw, dilation, wf, wd, bp, bias_present, bparam, bgrad_sink, wgrad_to):
+def _conv_tc_fwd_bwd(ctx, x, x_coff, cin, cinp, co, cop, kh, kw, dilation, wf, wd, bp, bias_present, bparam, bgrad_sink, wgrad_to, epi=None):
     """Forward + tape entry of one tcgen05 conv on channel-strided views.  wgrad_to(dwp) receives / names the packed fp32
     gradient buffer: it returns the tensor egm_conv2d_wgrad_tc_view writes and is called again (post=True) afterwards."""
     n, h, w, ctot = x.shape
     M = n * h * w
     sliced = not (x_coff == 0 and cin == ctot)
     xt, xcs, xco, xv = _tc_read_view(ctx, x.t, n, h, w, ctot, x_coff, cin, cinp)
-    y = ctx.empty(n, h, w, co)
-    call("conv2d_tc_view", xt, xcs, xco, xv, wf, bp, y, co, 0, co, 0, n, h, w, cinp, cop, kh, kw, dilation)
-    out = Var(y)
+    if epi is None:
+        y = ctx.empty(n, h, w, co)
+        call("conv2d_tc_view", xt, xcs, xco, xv, wf, bp, y, co, 0, co, 0, n, h, w, cinp, cop, kh, kw, dilation)
+        out = Var(y)
+    else:
+        assert not (ctx.record and epi.out is not None), "writing into a slice is an inference-only epilogue"
+        y, ycs, yco = (ctx.empty(n, h, w, co), co, 0) if epi.out is None else (epi.out.t, epi.out.C, epi.out_coff)
+        if epi.stats:
+            epi.sums = ctx.stat_slice(2 * co)
+        call("conv2d_tc_ex", xt, xcs, xco, xv, wf, bp, y, ycs, yco, co, 0, n, h, w, cinp, cop, kh, kw, dilation, int(epi.relu), epi.sums)
+        out = Var(y) if epi.out is None else epi.out
     if ctx.record:
         def bwd():
             dy = out.grad
@@ -354,7 +408,7 @@ def _conv_tc_fwd_bwd(ctx, x, x_coff, cin, cinp, co, cop, kh, kw, dilation, wf, w
     return out
 
 
-def _conv2d_lifted(ctx, x, wparam, bparam, weight, bias, groups, dilation, x_coff, cin, wgrad_sink, bgrad_sink) -> Var:
+def _conv2d_lifted(ctx, x, wparam, bparam, weight, bias, groups, dilation, x_coff, cin, wgrad_sink, bgrad_sink, epi=None) -> Var:
     """Thin (C < 16 or C % 16 != 0), grouped or channel-sliced conv on the tcgen05 path: the weight is lifted to a dense
     zero-padded (block-diagonal) 16-aligned one; activations are read / written in place through channel-strided views (TMA
     zero-fills the padding channels).  MMA work on the padding is irrelevant -- these layers are bandwidth-bound."""
@@ -382,16 +436,16 @@ def _conv2d_lifted(ctx, x, wparam, bparam, weight, bias, groups, dilation, x_cof
         call("conv_weight_lift", dw, dwd, co, cig, groups, taps, cop, cinp, 1)
         if wgrad_sink is not None:
             wgrad_sink(dw)
-    return _conv_tc_fwd_bwd(ctx, x, x_coff, cin, cinp, co, cop, kh, kw, dilation, wf, wd, bp, bias is not None, bparam, bgrad_sink, wgrad_to)
+    return _conv_tc_fwd_bwd(ctx, x, x_coff, cin, cinp, co, cop, kh, kw, dilation, wf, wd, bp, bias is not None, bparam, bgrad_sink, wgrad_to, epi)
 
 
-def _conv2d_planned(ctx, x, job: WeightJob, bias, bparam, dilation, x_coff, cin, bgrad_sink) -> Var:
+def _conv2d_planned(ctx, x, job: WeightJob, bias, bparam, dilation, x_coff, cin, bgrad_sink, epi=None) -> Var:
     """tcgen05 conv whose packed operands come from the WeightPlan (filled by egm_weight_prep_batch at the start of the step);
     its weight gradient stays packed in job.dwp until egm_wgrad_unpack_batch at the end of backward."""
     co, cig, kh, kw = job.spec.shape
     bp = job.bpad if job.bpad is not None else bias
     return _conv_tc_fwd_bwd(ctx, x, x_coff, cin, job.cinp, co, job.coutp, kh, kw, dilation, job.wf, job.wd, bp,
-                            bparam is not None or bgrad_sink is not None, bparam, bgrad_sink, lambda post: job.dwp)
+                            bparam is not None or bgrad_sink is not None, bparam, bgrad_sink, lambda post: job.dwp, epi)
 
 
 def conv_module(ctx: Ctx, x: Var, m: nn.Conv2d, **kw) -> Var:
@@ -402,7 +456,7 @@ def conv_module(ctx: Ctx, x: Var, m: nn.Conv2d, **kw) -> Var:
 
 # =========================================================================== batch norm (+ activation)
 def bn_act(ctx: Ctx, z: Var, bn: nn.BatchNorm2d, act: int, mode: int = MODE_PLAIN, aux: Optional[Var] = None, alpha: float = 0.0,
-           out: Optional[Var] = None, out_coff: int = 0) -> Var:
+           out: Optional[Var] = None, out_coff: int = 0, sums: Optional[torch.Tensor] = None) -> Var:
     """y = act(BN(z)) (mode PLAIN) | sigmoid(BN(z))*aux + aux (EDGE_GATE) | relu(alpha*aux + BN(z)) (RESIDUAL).
     With `out`, y is written into out[..., out_coff:out_coff+C] (a concat buffer) and `out` is returned."""
     n, h, w, c = z.shape
@@ -411,7 +465,10 @@ def bn_act(ctx: Ctx, z: Var, bn: nn.BatchNorm2d, act: int, mode: int = MODE_PLAI
     scale, shift, mean, rstd = (torch.empty(c, **ctx.f32) for _ in range(4))
     training = ctx.training or bn.running_mean is None
     mom = 0.1 if bn.momentum is None else bn.momentum
-    if training and M > 0:      # statistics + finalize (scale/shift/mean/rstd, running stats) in one launch
+    if training and M > 0 and sums is not None:      # statistics came out of the producing conv's epilogue (fp32 accumulators)
+        call("bn_finalize", sums, M, gamma, beta, bn.running_mean, bn.running_var, bn.num_batches_tracked, float(mom), float(bn.eps), 1, c,
+             scale, shift, mean, rstd)
+    elif training and M > 0:      # statistics + finalize (scale/shift/mean/rstd, running stats) in one launch
         call("bn_stats_finalize", z.t, ctx.code, M, c, c, 0, ctx.f64(2 * c + 1), gamma, beta, bn.running_mean, bn.running_var,
              bn.num_batches_tracked, float(mom), float(bn.eps), scale, shift, mean, rstd)
     else:
@@ -450,6 +507,34 @@ def bn_act(ctx: Ctx, z: Var, bn: nn.BatchNorm2d, act: int, mode: int = MODE_PLAI
                  ctx.code, M, c)
         ctx.push(bwd)
     return y
+
+
+def conv_bn_act(ctx: Ctx, x: Var, conv: nn.Conv2d, bn: nn.BatchNorm2d, act: int, mode: int = MODE_PLAIN, aux: Optional[Var] = None,
+                alpha: float = 0.0, out: Optional[Var] = None, out_coff: int = 0) -> Var:
+    """act(BN(conv(x))), act in {none, relu}: DoubleConv (src/EGM-UNet.py:44-55) and BasicConv (:958-975) with the BatchNorm fused
+    into the tcgen05 conv's epilogue wherever the kernels allow:
+      inference  -- gamma*rstd folded into the weights, beta - mean*gamma*rstd as the epilogue bias, ReLU in the epilogue: ONE kernel,
+                    written straight into `out[..., out_coff:]` when given; no BN kernel runs.
+      training   -- the conv epilogue also takes the per-channel sum / sum of squares of its fp32 accumulators (layers with <= 64
+                    output channels, i.e. the large maps), so the statistics pass over z disappears; finalize + apply follow."""
+    d = conv.dilation[0]
+    assert conv.stride == (1, 1) and conv.padding[0] == d * (conv.kernel_size[0] - 1) // 2, "only stride-1 'same' convolutions"
+    co, cig, kh, kw = conv.weight.shape
+    cin = cig * conv.groups
+    training = ctx.training or bn.running_mean is None
+    route, cinp, cop = tc_route(ctx, cin, co, kh, kw, d, conv.groups, x.C != cin)
+    if ctx.fuse_bn and route is not None and kh == kw:
+        if not training and not ctx.record and conv.bias is None and mode == MODE_PLAIN and act in (ACT_NONE, ACT_RELU):
+            scale, shift = torch.empty(co, **ctx.f32), torch.empty(co, **ctx.f32)
+            call("bn_finalize", None, 1, _p(bn.weight), _p(bn.bias), bn.running_mean, bn.running_var, None, 0.0, float(bn.eps), 0, co, scale, shift, None, None)
+            wfold = torch.empty_like(_p(conv.weight))
+            call("scale_rows", _p(conv.weight), scale, wfold, co, cig * kh * kw)
+            return conv2d(ctx, x, wfold, shift, groups=conv.groups, dilation=d, epi=Epi(relu=(act == ACT_RELU), out=out, out_coff=out_coff))
+        if training and x.M > 0 and abi.query("conv2d_tc_stats_supported", cinp, cop, kh, kw, d):
+            epi = Epi(stats=True)
+            z = conv2d(ctx, x, conv.weight, conv.bias, groups=conv.groups, dilation=d, epi=epi)
+            return bn_act(ctx, z, bn, act, mode, aux, alpha, out=out, out_coff=out_coff, sums=epi.sums)
+    return bn_act(ctx, conv2d(ctx, x, conv.weight, conv.bias, groups=conv.groups, dilation=d), bn, act, mode, aux, alpha, out=out, out_coff=out_coff)
 
 
 # =========================================================================== pooling / upsampling
@@ -579,8 +664,7 @@ def edge_enhancer(ctx: Ctx, x: Var, m) -> Var:
             gx, acc = x.grad_target()
             call("highpass3", d, gx, acc, ctx.code, n, h, w, c)
         ctx.push(bwd)
-    z = conv_module(ctx, e, m.weight_generator[0])
-    return bn_act(ctx, z, m.weight_generator[1], ACT_SIGMOID, MODE_EDGE_GATE, aux=x)
+    return conv_bn_act(ctx, e, m.weight_generator[0], m.weight_generator[1], ACT_SIGMOID, MODE_EDGE_GATE, aux=x)
 
 
 # =========================================================================== MCALayer

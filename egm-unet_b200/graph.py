@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import abi
 from .abi import call
-from .engine import (ACT_NONE, ACT_RELU, ACT_SIGMOID, MODE_PLAIN, MODE_RESIDUAL, Ctx, Var, WSpec, _p, bn_act, conv2d, conv_module,
+from .engine import (ACT_NONE, ACT_RELU, ACT_SIGMOID, MODE_PLAIN, MODE_RESIDUAL, Ctx, Var, WSpec, _p, bn_act, conv2d, conv_bn_act, conv_module,
                      copy_into, deconv_concat, edge_enhancer, from_nchw, maxpool2, mca_layer, release_grad, slice_channels, to_nchw,
                      upsample_concat)
 
@@ -109,9 +109,8 @@ def fusion_conv(ctx: Ctx, cat: Var, m) -> Var:
 # =========================================================================== EdgeEnhancedGRFB
 def basic_conv(ctx: Ctx, x: Var, m, out: Optional[Var] = None, out_coff: int = 0) -> Var:
     """BasicConv (src/EGM-UNet.py:958-975): conv -> BN(momentum 0.01) -> optional ReLU."""
-    z = conv_module(ctx, x, m.conv)
     act = ACT_RELU if (m.relu is not None) else ACT_NONE
-    return bn_act(ctx, z, m.bn, act, out=out, out_coff=out_coff)
+    return conv_bn_act(ctx, x, m.conv, m.bn, act, out=out, out_coff=out_coff)
 
 
 def grfb(ctx: Ctx, x: Var, m) -> Var:
@@ -136,8 +135,7 @@ def grfb(ctx: Ctx, x: Var, m) -> Var:
     q = basic_conv(ctx, q, m.branch_ctx[2])
     basic_conv(ctx, q, m.branch_ctx[3], out=cat, out_coff=c + 4 * ip)
     fo = fusion_conv(ctx, cat, m.fusion_conv)
-    zs = conv_module(ctx, x, m.shortcut.conv)
-    o = bn_act(ctx, zs, m.shortcut.bn, ACT_NONE, MODE_RESIDUAL, aux=fo, alpha=float(m.scale))
+    o = conv_bn_act(ctx, x, m.shortcut.conv, m.shortcut.bn, ACT_NONE, MODE_RESIDUAL, aux=fo, alpha=float(m.scale))
     tz = conv_module(ctx, o, m.target_enhancer[0])          # [N,H,W,3]
     y = Var(ctx.empty(n, h, w, o.C))
     call("mul_pixel_gate", o.t, tz.t, y.t, ctx.code, M, o.C, 3, 1)
@@ -227,8 +225,8 @@ def rga(ctx: Ctx, x: Var, m) -> Var:
 # =========================================================================== skeleton
 def double_conv(ctx: Ctx, x: Var, seq, i0: int = 0, i1: int = 3) -> Var:
     """DoubleConv, src/EGM-UNet.py:44-55 == src/unet.py:7-18."""
-    x = bn_act(ctx, conv_module(ctx, x, seq[i0]), seq[i0 + 1], ACT_RELU)
-    return bn_act(ctx, conv_module(ctx, x, seq[i1]), seq[i1 + 1], ACT_RELU)
+    x = conv_bn_act(ctx, x, seq[i0], seq[i0 + 1], ACT_RELU)
+    return conv_bn_act(ctx, x, seq[i1], seq[i1 + 1], ACT_RELU)
 
 
 def down_block(ctx: Ctx, x: Var, down, variant: str) -> Var:
@@ -237,13 +235,13 @@ def down_block(ctx: Ctx, x: Var, down, variant: str) -> Var:
     seq = down[1]
     if variant == "unet":
         return double_conv(ctx, x, seq)
-    x = bn_act(ctx, conv_module(ctx, x, seq[0]), seq[1], ACT_RELU)
+    x = conv_bn_act(ctx, x, seq[0], seq[1], ACT_RELU)
     if variant == "egm":
         x = mca_layer(ctx, x, seq[3])
         c2, gi = 4, 7
     else:
         c2, gi = 3, 6
-    x = bn_act(ctx, conv_module(ctx, x, seq[c2]), seq[c2 + 1], ACT_RELU)
+    x = conv_bn_act(ctx, x, seq[c2], seq[c2 + 1], ACT_RELU)
     return grfb(ctx, x, seq[gi])
 
 

@@ -56,7 +56,9 @@ def criterion(inputs: Dict[str, torch.Tensor], target, loss_weight=None, num_cla
 
 
 def loss_terms(logits: torch.Tensor, target: torch.Tensor, loss_weight: Optional[torch.Tensor] = None, ignore_index: int = -100):
-    """Forward-only: dict of the five terms (train_utils/dice_coefficient_loss.py) from one fused launch."""
+    """Forward-only: dict of the five terms (train_utils/dice_coefficient_loss.py) from one fused launch, plus `bad_labels`:
+    the number of labels that are neither a class id nor `ignore_index` (the reference raises a device assert for those; the
+    kernel drops them from CE and Dice alike and counts them here)."""
     n, c, h, w = logits.shape
     lg = logits.detach().float().contiguous()
     ws_bytes = abi.query("loss_workspace_bytes", n, c, h, w)
@@ -64,7 +66,7 @@ def loss_terms(logits: torch.Tensor, target: torch.Tensor, loss_weight: Optional
     out = torch.empty(8, dtype=torch.float32, device=lg.device)
     wt = None if loss_weight is None else loss_weight.detach().float().contiguous()
     call("loss_fwd_bwd", lg, target.contiguous(), wt, n, c, h, w, int(ignore_index), 1, 1.0, out, None, ws, ws_bytes)
-    return {"total": out[0], "ce": out[1], "dice": out[2], "laplace": out[3], "lap": out[4], "sobel": out[5]}
+    return {"total": out[0], "ce": out[1], "dice": out[2], "laplace": out[3], "lap": out[4], "sobel": out[5], "bad_labels": out[6]}
 
 
 class EvalMetrics:

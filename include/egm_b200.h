@@ -74,6 +74,20 @@ int egm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_packed, int N, 
 int egm_conv2d_tc_view(const void* x, long long x_cstride, long long x_coff, int cin_valid, const void* w_packed_bf16, const float* bias,
                        void* y, long long y_cstride, long long y_coff, int cout_valid, int accumulate, int N, int H, int W, int Cin,
                        int Cout, int kh, int kw, int dil, void* stream);
+/* Extended forward form -- BatchNorm / ReLU in the conv epilogue (BASELINE.json north_star subsystem 1; src/EGM-UNet.py:44-55 conv -> BN -> ReLU,
+ * :958-975 BasicConv).
+ *   relu != 0   y = relu(conv + bias): inference, with the BatchNorm folded into the packed weights (w * gamma*rstd via egm_scale_rows)
+ *               and the bias (beta - mean*gamma*rstd) -- no BN kernel runs at all.
+ *   stats       training: besides y (= the pre-BN tensor z) the kernel adds, per output channel, sum(z) and sum(z^2) of its fp32
+ *               accumulators over all N*H*W pixels into stats[0..cout_valid) / stats[cout_valid..2*cout_valid) (fp64, zeroed by the
+ *               caller); egm_bn_finalize turns them into scale / shift / running statistics.  Available where
+ *               egm_conv2d_tc_stats_supported (padded Cout of 16 / 32 / 64: the layers with the large pre-BN maps). */
+int egm_conv2d_tc_stats_supported(int Cin, int Cout, int kh, int kw, int dil);
+int egm_conv2d_tc_ex(const void* x, long long x_cstride, long long x_coff, int cin_valid, const void* w_packed_bf16, const float* bias,
+                     void* y, long long y_cstride, long long y_coff, int cout_valid, int accumulate, int N, int H, int W, int Cin,
+                     int Cout, int kh, int kw, int dil, int relu, double* stats, void* stream);
+/* out[r][:] = w[r][:] * scale[r] (+ nothing else): folds an inference BatchNorm's per-output-channel scale into a conv weight [rows][cols] */
+int egm_scale_rows(const float* w, const float* scale, float* out, int rows, long long cols, void* stream);
 int egm_conv2d_wgrad_tc_view(const void* x, long long x_cstride, long long x_coff, int cin_valid, const void* dy, long long dy_cstride,
                              long long dy_coff, int cout_valid, float* dw_packed, int N, int H, int W, int Cin, int Cout, int kh, int kw,
                              int dil, void* stream);

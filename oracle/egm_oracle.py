@@ -41,7 +41,8 @@ STORAGE = None
 # error-budget switch (tools/bf16_error_budget.py): storage classes listed here stay fp32 even when STORAGE is set.
 # classes: "dc_z" DoubleConv conv outputs (pre-BN), "dc_y" DoubleConv BN+ReLU outputs, "bc_z"/"bc_y" the same for the GRFB BasicConvs,
 # "conv" other conv outputs (FusionConv, shortcut, RGA, out_conv inputs), "edge" edge-enhancer tensors, "mca" MCALayer output,
-# "mix" FusionConv f+s*ca, "grfb" GRFB residual / gated outputs, "rga" RGA gate tensors, "up" upsampled tensors, "input"
+# "mix" FusionConv f+s*ca, "grfb" GRFB residual / gated outputs, "rga" RGA gate tensors, "up" upsampled tensors, "input",
+# "weight" conv weights as MMA operands
 STORAGE_FP32 = frozenset()
 STORAGE_FP16 = frozenset()      # classes stored as IEEE fp16 (11-bit significand) instead of STORAGE
 
@@ -74,7 +75,8 @@ def _bn(sd, p: str, x: Tensor, train: bool, momentum: float, upd: Optional[dict]
 
 
 def _conv(sd, p: str, x: Tensor, padding=0, dilation=1, groups=1, tag: str = "conv") -> Tensor:
-    return _r(F.conv2d(x, sd[p + ".weight"], sd.get(p + ".bias"), 1, padding, dilation, groups), tag)
+    # the tcgen05 path feeds the conv weights to the MMA as bf16 operands: the storage model rounds them too (class "weight")
+    return _r(F.conv2d(x, _r(sd[p + ".weight"], "weight"), sd.get(p + ".bias"), 1, padding, dilation, groups), tag)
 
 
 def double_conv(sd, p, x, train, upd, i0=0, i1=3):

@@ -1,7 +1,8 @@
 """GPU: whole-model parity of the CUDA path (through the drop-in modules -> C-ABI) against the committed reference fixtures
-and the CPU oracle.  Tolerances: fp32 check mode logits 1e-4 rel-to-max (reference states 1e-5 per-op; whole-net fp32
-round-off is ~3e-6, see gen_golden) ; bf16 logits rtol 2e-2 of the logit range, argmax agreement >= 99.9% away from ties,
-Dice/mIoU within 1e-3 -- BASELINE.json north_star."""
+and the CPU oracle.  Tolerances (BASELINE.json north_star): fp32 check mode logits 1e-5 rel-to-max; bf16 logits rtol 2e-2, argmax
+agreement >= 99.9 %, Dice/mIoU within 1e-3 -- where the bf16 bars are not reachable with bf16-stored activations the same quantity
+is computed for the reference arithmetic under that storage model and the CUDA path must be within 1.1x of it (both printed;
+tests/test_configs_gpu.py holds the BASELINE-config-size versions)."""
 import os
 
 import numpy as np
@@ -39,8 +40,8 @@ def test_fp32_check_mode_matches_reference_fixture(variant, tag):
     loss = E.criterion({"out": out}, target.cuda(), lw, num_classes=2, ignore_index=255)
     loss.backward()
     ref = torch.from_numpy(fx["logits"])
-    assert rel_err(out.detach().cpu(), ref) < 1e-4
-    assert abs(float(loss) - float(fx["loss"])) / abs(float(fx["loss"])) < 1e-4
+    assert rel_err(out.detach().cpu(), ref) < 1e-5, rel_err(out.detach().cpu(), ref)
+    assert abs(float(loss) - float(fx["loss"])) / abs(float(fx["loss"])) < 1e-5
     norms = dict(zip(fx["grad_keys"].tolist(), fx["grad_norm"].tolist()))
     bad = []
     for k, p in model.named_parameters():
@@ -64,7 +65,7 @@ def test_fp32_check_mode_matches_reference_fixture(variant, tag):
     model.eval()
     with torch.no_grad():
         ev = model(image.cuda())["out"]
-    assert rel_err(ev.cpu(), torch.from_numpy(fx["logits_eval"])) < 1e-4
+    assert rel_err(ev.cpu(), torch.from_numpy(fx["logits_eval"])) < 1e-5
 
 
 @pytest.mark.parametrize("variant,tag", [("unet", "unet_2x64x48"), ("egm", "egm_2x64x48"), ("yuan", "yuan_2x64x64")])
@@ -103,7 +104,9 @@ def test_bf16_matches_reference_fixture(variant, tag):
 
 @pytest.mark.parametrize("variant", ["unet", "egm"])
 def test_bf16_masks_and_metrics_vs_oracle(variant):
-    """argmax agreement >= 99.9 % (on pixels whose oracle margin exceeds the bf16 noise), Dice / mIoU within 1e-3."""
+    """north_star: argmax agreement >= 99.9 %, Dice / mIoU within 1e-3 -- asserted as such; where bf16-stored activations make a bar
+    unreachable (random-init weights leave many near-tie pixels) the CUDA path must be within 1.1x of the SAME quantity measured
+    on the reference arithmetic with bf16-stored activations."""
     model = build(variant)
     sd = synth.fill_state_dict(model.state_dict())
     model.load_state_dict(sd)
@@ -112,19 +115,25 @@ def test_bf16_masks_and_metrics_vs_oracle(variant):
     with torch.no_grad():
         out = model(image.cuda())["out"].cpu()
         ref = O.forward(sd, image, variant, False)
+        O.STORAGE = torch.bfloat16
+        try:
+            sim = O.forward(sd, image, variant, False)
+        finally:
+            O.STORAGE = None
+
+    def metrics(x):
+        agree = float((x.argmax(1) == ref.argmax(1)).float().mean())
+        d = abs(O.dice_metric(x, target) - O.dice_metric(ref, target))
+        m = abs(O.miou(O.confusion_matrix(target, x.argmax(1), 2)) - O.miou(O.confusion_matrix(target, ref.argmax(1), 2)))
+        return 1 - agree, d, m
+    ours, model_ = metrics(out), metrics(sim)
+    print(f"{variant}: (argmax disagreement, |dDice|, |dmIoU|) CUDA bf16 {ours} | bf16-storage reference {model_}")
+    for o, s_, name in zip(ours, model_, ("argmax disagreement", "Dice", "mIoU")):
+        assert o <= 1e-3 or o <= 1.1 * s_ + 1e-4, (name, o, s_)
+    # confident pixels (oracle margin above the bf16 noise) must agree outright
     margin = (ref[:, 0] - ref[:, 1]).abs()
-    span = float(ref.max() - ref.min())
-    sure = margin > 0.05 * span
-    agree = (out.argmax(1) == ref.argmax(1))
-    assert float(agree[sure].float().mean()) >= 0.999
-    assert float(agree.float().mean()) >= 0.97
-    # metrics computed on the oracle's mask as "target" so the comparison is a mask-vs-mask Dice / mIoU
-    tgt = ref.argmax(1)
-    m_ref, m_out = O.confusion_matrix(tgt, ref.argmax(1), 2), O.confusion_matrix(tgt, out.argmax(1), 2)
-    assert abs(O.miou(m_ref) - O.miou(m_out)) < 5e-2
-    d = abs(O.dice_metric(out, target) - O.dice_metric(ref, target))
-    m = abs(O.miou(O.confusion_matrix(target, out.argmax(1), 2)) - O.miou(O.confusion_matrix(target, ref.argmax(1), 2)))
-    assert d < 1e-3 + 0.02 * (1 - float(agree.float().mean())) * 50 and m < 1e-3 + 0.02 * (1 - float(agree.float().mean())) * 50
+    sure = margin > 0.05 * float(ref.max() - ref.min())
+    assert float((out.argmax(1) == ref.argmax(1))[sure].float().mean()) >= 0.999
 
 
 def test_sgd_trainer_step_matches_oracle():
@@ -172,7 +181,7 @@ def test_bf16_train_logits_rtol_at_realistic_size(variant):
     # The north_star asks rtol 2e-2; with bf16-stored activations that is not reachable for this net by ANY implementation:
     # the reference arithmetic itself, with activations rounded to bf16 at the same points, is 3.5-3.8e-2 away from fp32
     # (torch's own CPU autocast(bf16) of the reference: 4.3e-2 -- DESIGN.md).  The CUDA path must be no worse than that model.
-    assert rms < 5e-2 and rms <= 1.25 * rms_sim + 2e-3, (rms, rms_sim)
+    assert rms <= 2e-2 or rms <= 1.1 * rms_sim + 1e-4, (rms, rms_sim)
 
 
 @pytest.mark.parametrize("variant", ["unet", "egm"])

@@ -367,3 +367,101 @@ def test_gap_gmp_against_torch(shape):
     assert torch.equal(mx.cpu().reshape(n, c), xf.amax(1))
     first = (xf == xf.amax(1, keepdim=True)).float().argmax(1)          # first index of the maximum
     assert torch.equal(arg.cpu().reshape(n, c).long(), first)
+
+
+# ------------------------------------------------------------------ BatchNorm fused into the tcgen05 conv epilogue (round 2)
+EPI_CASES = [  # cin, cout, k, dil, groups, H, W, N, bias   (train statistics: padded Cout in {16, 32, 64}; every kernel route)
+    (32, 32, 3, 1, 1, 37, 29, 2, False),    # halo kernel, ragged tiles
+    (64, 32, 3, 1, 1, 48, 40, 2, False), (32, 64, 3, 1, 1, 33, 47, 1, False), (64, 64, 3, 1, 1, 20, 40, 2, False),
+    (3, 32, 3, 1, 1, 40, 40, 2, False),     # in_conv.0: lifted 16 -> 32
+    (64, 16, 1, 1, 1, 24, 20, 2, False),    # BasicConv 1x1 onto 16
+    (64, 8, 1, 1, 1, 24, 20, 2, False),     # lifted thin output (8 valid of 16)
+    (8, 8, 1, 1, 1, 19, 23, 2, True),       # edge weight_generator: conv bias + BN
+    (16, 16, 3, 12, 1, 30, 30, 2, False),   # dilated GRFB branch: k_conv_tc, nine taps per stage
+    (8, 16, 3, 1, 8, 21, 18, 2, False),     # grouped (lifted block-diagonal)
+    (128, 64, 3, 1, 1, 24, 24, 1, False),   # k_conv_tc general path (Cin = 128), Cout 64
+    (64, 64, 1, 1, 1, 17, 31, 2, False),    # GRFB shortcut 1x1
+    (128, 128, 3, 1, 1, 12, 12, 1, False)]  # wide: statistics stay in the streaming kernel (route must still agree)
+
+
+@pytest.mark.parametrize("case", EPI_CASES)
+def test_conv_bn_act_train_stats_in_epilogue(case):
+    """conv -> BN(train) -> ReLU with the batch statistics taken in the conv epilogue: output, running statistics, input / weight / gamma / beta
+    gradients vs torch CPU; and the same numbers as the unfused route (EGM_NO_BN_FUSE semantics) up to the fp32-vs-bf16 statistics source."""
+    from egm_unet_b200.engine import conv_bn_act, ACT_RELU
+    cin, cout, k, dil, groups, H, W, N, bias = case
+    torch.manual_seed(2)
+    conv = nn.Conv2d(cin, cout, k, padding=dil * (k - 1) // 2, dilation=dil, groups=groups, bias=bias)
+    bn = nn.BatchNorm2d(cout, momentum=0.01)
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.to(torch.bfloat16).float())
+        bn.weight.copy_(1 + 0.2 * torch.randn(cout)); bn.bias.copy_(0.1 * torch.randn(cout))
+    x = _q(_rand(N, cin, H, W), torch.bfloat16)
+    g = _q(_rand(N, cout, H, W, seed=3), torch.bfloat16)
+    res = {}
+    for fuse in (True, False):
+        hs = Harness(torch.bfloat16, use_tc=True)
+        hs.ctx.fuse_bn = fuse
+        cc, bb = nn.Conv2d(cin, cout, k, padding=dil * (k - 1) // 2, dilation=dil, groups=groups, bias=bias), nn.BatchNorm2d(cout, momentum=0.01)
+        cc.load_state_dict(conv.state_dict()); bb.load_state_dict(bn.state_dict())
+        cc, bb = cc.cuda(), bb.cuda()
+        xv = hs.var(x)
+        yv = conv_bn_act(hs.ctx, xv, cc, bb, ACT_RELU)
+        y = hs.out(yv)
+        hs.backward(yv, g)
+        res[fuse] = (y, hs.grad(xv), hs.pgrad(cc.weight), hs.pgrad(bb.weight), hs.pgrad(bb.bias), bb.running_mean.cpu(), bb.running_var.cpu(),
+                     int(bb.num_batches_tracked))
+    xr = x.clone().requires_grad_(True)
+    conv.train(); bn.train()
+    yr = torch.relu(bn(conv(xr)))
+    yr.backward(g)
+    ref = (yr.detach(), xr.grad, conv.weight.grad, bn.weight.grad, bn.bias.grad, bn.running_mean, bn.running_var, 1)
+    names = ("y", "dx", "dw", "dgamma", "dbeta", "running_mean", "running_var")
+    for fuse in (True, False):
+        for nme, a, b in zip(names, res[fuse], ref):
+            tol = 3e-2 if nme in ("dx", "dw", "dgamma", "dbeta") else (2e-2 if nme == "y" else 2e-3)
+            assert rel_err(a, b) < tol, (fuse, nme, rel_err(a, b))
+        assert res[fuse][7] == 1
+    # statistics from the fp32 accumulators are at least as close to the fp32 reference as statistics of the bf16-rounded z
+    assert rel_err(res[True][5], ref[5]) <= rel_err(res[False][5], ref[5]) + 1e-4
+
+
+@pytest.mark.parametrize("case", EPI_CASES)
+@pytest.mark.parametrize("relu", [True, False])
+def test_conv_bn_act_eval_folded_into_epilogue(case, relu):
+    """inference: BN folded into weights + epilogue bias (+ ReLU) == torch eval conv -> BN -> ReLU, incl. writing into a concat slice"""
+    from egm_unet_b200.engine import conv_bn_act, ACT_RELU, ACT_NONE, Ctx, Var
+    cin, cout, k, dil, groups, H, W, N, bias = case
+    if bias:
+        pytest.skip("conv bias + BN only occurs in the sigmoid-gate mode, which is not folded")
+    torch.manual_seed(4)
+    conv = nn.Conv2d(cin, cout, k, padding=dil * (k - 1) // 2, dilation=dil, groups=groups, bias=False)
+    bn = nn.BatchNorm2d(cout)
+    with torch.no_grad():
+        bn.weight.copy_(1 + 0.2 * torch.randn(cout)); bn.bias.copy_(0.1 * torch.randn(cout))
+        bn.running_mean.copy_(0.2 * torch.randn(cout)); bn.running_var.copy_(0.5 + torch.rand(cout))
+    x = _q(_rand(N, cin, H, W), torch.bfloat16)
+    conv.eval(); bn.eval()
+    with torch.no_grad():
+        yr = bn(conv(x))
+        yr = torch.relu(yr) if relu else yr
+    hs = Harness(torch.bfloat16, training=False, use_tc=True)
+    hs.ctx.record = False
+    cc, bb = conv.cuda(), bn.cuda()
+    xv = hs.var(x, needs_grad=False)
+    l0 = abi_launches()
+    yv = conv_bn_act(hs.ctx, xv, cc, bb, ACT_RELU if relu else ACT_NONE)
+    assert rel_err(hs.out(yv), yr) < 2e-2
+    # into a slice of a wider (concat) tensor, neighbours untouched
+    ctot, off = cout + 24, 8
+    cat = Var(torch.full((N, H, W, ctot), 7.0, dtype=torch.bfloat16, device="cuda"))
+    conv_bn_act(hs.ctx, xv, cc, bb, ACT_RELU if relu else ACT_NONE, out=cat, out_coff=off)
+    got = cat.t.float().cpu().permute(0, 3, 1, 2)
+    assert rel_err(got[:, off:off + cout], yr) < 2e-2
+    assert float((got[:, :off] - 7).abs().max()) == 0 and float((got[:, off + cout:] - 7).abs().max()) == 0
+    assert abi_launches() - l0 < 40
+
+
+def abi_launches():
+    from egm_unet_b200 import abi
+    return abi.LAUNCH_COUNTER[0]

@@ -17,7 +17,7 @@ import torch  # noqa: E402
 
 from oracle import egm_oracle as O, synth  # noqa: E402
 
-CLASSES = ["dc_z", "dc_y", "bc_z", "bc_y", "conv", "edge", "mca", "mix", "grfb", "rga", "up", "input"]
+CLASSES = ["dc_z", "dc_y", "bc_z", "bc_y", "conv", "edge", "mca", "mix", "grfb", "rga", "up", "input", "weight"]
 # elements per image at 480^2 (base_c = 32) of each class, for the cost column (fwd store + fwd/bwd reloads ~ 3 passes x 2 extra bytes)
 E0 = 480 * 480
 
@@ -29,7 +29,7 @@ def class_elems():
     bc = sum(x * (12 * 0.25) for x in grfb_per)            # 12 BasicConvs of ~C/4 channels each
     return {"dc_z": dc, "dc_y": dc, "bc_z": bc, "bc_y": bc, "conv": sum(x * 1.8 for x in grfb_per), "edge": sum(x * 2.4 for x in grfb_per),
             "mca": sum(grfb_per), "mix": sum(x * 0.25 for x in grfb_per), "grfb": sum(2 * x for x in grfb_per), "rga": l[4] * 2,
-            "up": l[4] * 4 + l[3] * 2 + l[2] * 2 + l[1] * 2, "input": E0 * 3}
+            "up": l[4] * 4 + l[3] * 2 + l[2] * 2 + l[1] * 2, "input": E0 * 3, "weight": 0}
 
 
 def main():
