@@ -169,13 +169,33 @@ def conv_shape(key):
     return tuple(iv[-8:])
 
 
-def is_doubleconv(key, batch):
-    """DoubleConv 3x3 launches (fwd / dgrad / wgrad): k=3, dilation 1, >= 32 channels on both sides (in_conv.0 runs as 16->32)."""
+def _dc_keys(base_c=32):
+    """(H, Cin, Cout) of every launch of the 18 DoubleConv layers: forward and wgrad carry (Cin, Cout), dgrad carries (Cout, Cin);
+    in_conv.0 (3 input channels) runs zero-padded as 16 -> 32 and has no dgrad."""
+    fw, dg = set(), set()
+    for _, ci, co, s in doubleconv_layers(base_c):
+        cip = 16 if ci < 16 else ci
+        fw.add((H // s, cip, co))
+        if ci >= 16:
+            dg.add((H // s, co, ci))
+    return fw, dg
+
+
+_DC_FW, _DC_DG = _dc_keys()
+
+
+def is_doubleconv(key, batch=None):
+    """exactly the DoubleConv 3x3 launches (fwd / dgrad / wgrad), matched by (H, Cin, Cout, k=3, dilation 1) against the layer table --
+    the GRFB's own 3x3 convs never share a (resolution, channel) signature with a DoubleConv layer"""
     s = conv_shape(key)
     if s is None:
         return False
     n_, h_, w_, ci, co, kh, kw, dil = s
-    return kh == 3 and dil == 1 and ((min(ci, co) >= 32) or (h_ == H and {ci, co} == {16, 32}))
+    if not (kh == 3 and kw == 3 and dil == 1 and h_ == w_):
+        return False
+    if key.startswith("conv2d_wgrad"):
+        return (h_, ci, co) in _DC_FW
+    return (h_, ci, co) in _DC_FW or (h_, ci, co) in _DC_DG
 
 
 # algorithmic bytes of the memory-bound families (SURVEY.md s8d), from the (M, C) each call carries; E = M*C elements, b = bytes/element
@@ -312,13 +332,20 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=3)
 
-    # ---- per-kernel breakdown of ONE step (outside the timed region), queue primed so the event deltas are pure device time
-    tr.use_graph = False                    # the per-kernel event breakdown needs real launches
-    launches_eager0 = abi.LAUNCH_COUNTER[0]
-    prof = primed_profile(step_resident, dev)
+    # ---- per-kernel breakdown of ONE eager step (outside the timed region).  Primary: kernel durations from CUPTI activity records
+    # (hardware timestamps per kernel, keyed by the C-ABI call that launched it); fallback: windowed, queue-primed CUDA events.
+    tr.use_graph = False                    # the per-kernel breakdown needs real launches
+    ev_prof = primed_profile(step_resident, dev)
     if launches == 0:
-        launches = abi.LAUNCH_COUNTER[0] - launches_eager0     # kernels inside one replayed graph == kernels of one eager step
-    prof2 = primed_profile(step_resident, dev)                  # second sample: run-to-run spread of the roofline inputs
+        launches = sum(v["calls"] for v in ev_prof.values())   # kernels inside one replayed graph == C-ABI launches of one eager step
+    prof = abi.profile_step_cupti(step_resident)
+    if prof is not None:
+        prof2 = abi.profile_step_cupti(step_resident) or prof   # second sample: run-to-run spread of the roofline inputs
+        timing = ("kernel durations from CUPTI activity records (torch.profiler) of one eager step, keyed by C-ABI call; "
+                  "cross-check: windowed queue-primed CUDA events, which add ~5 us of event/launch overhead per call")
+    else:
+        prof, prof2 = ev_prof, primed_profile(step_resident, dev)
+        timing = "CUDA events per launch on the launch stream, queue primed by a spin kernel per window of 160 calls (CUPTI unavailable)"
 
     def dc_ms(p):
         return sum(v["ms"] for k, v in p.items() if is_doubleconv(k, args.batch))
@@ -368,7 +395,7 @@ def main():
         roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
                 "kernel": "tcgen05 implicit-GEMM convs of the 18 DoubleConv layers (k_conv_tc / k_conv_tc_halo fwd+dgrad, k_wgrad_tc_halo)",
                 "kernel_ms_per_step": tc_ms_used, "kernel_ms_two_samples": [round(tc_ms, 4), round(tc_ms2, 4)],
-                "timing": "CUDA events per launch on the launch stream, queue primed by a spin kernel (no host launch gaps)",
+                "timing": timing, "kernel_ms_per_step_cuda_events": round(dc_ms(ev_prof), 4),
                 "share_of_step": tc_ms_used / max(step_sum, 1e-9), "sum_of_kernel_ms_per_step": step_sum, "all_tcgen05_conv_ms_per_step": tc_all,
                 "best_layer_tflops": best, "algorithmic_flops_per_step": flops, "peak_source": peak_src, "hbm": fam,
                 "hbm_peak_gbs": peak_hbm}

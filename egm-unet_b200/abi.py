@@ -104,6 +104,14 @@ def call(name: str, *args):
     if dev is not None and dev.type == "cuda" and dev.index != torch.cuda.current_device():
         with torch.cuda.device(dev):
             return call(name, *args)
+    if _CUPTI_RANGES:
+        key = "egm:" + name + ":" + ",".join(str(a) for a in args if isinstance(a, int))
+        with torch.profiler.record_function(key):
+            rc = L.fn["egm_" + name](*[_conv_arg(a) for a in args], torch.cuda.current_stream().cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"egm_{name} failed ({rc}): {L.last_error()}")
+        LAUNCH_COUNTER[0] += 1
+        return
     stream = torch.cuda.current_stream().cuda_stream
     prof = _PROFILE is not None
     if prof and _WINDOW is not None:
@@ -140,6 +148,47 @@ _PROFILE_DETAIL_ALL = False          # bench.py: every key carries the call's in
 
 
 _WINDOW = None      # [first call index, end call index, running call index, spin cycles] while a windowed profile runs
+_CUPTI_RANGES = False
+
+
+def profile_step_cupti(fn):
+    """Per-C-ABI-call KERNEL durations of one eager fn() from CUPTI activity records (torch.profiler / kineto): every call runs
+    inside a `record_function("egm:<entry point>:<int args>")` range and the durations of the kernels it launched (hardware
+    timestamps, no event-record or launch-gap overhead) are summed per key.  Returns {key: {"ms", "calls", "kernels"}} or None when
+    the profiler recorded no device activity (CUPTI unavailable).  Diagnostic only -- never inside a timed region."""
+    global _CUPTI_RANGES
+    from torch.profiler import profile, ProfilerActivity
+    torch.cuda.synchronize()
+    _CUPTI_RANGES = True
+    try:
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+    except Exception:
+        return None
+    finally:
+        _CUPTI_RANGES = False
+
+    def kernel_us(ev, depth=0):
+        t = sum(k.duration for k in ev.kernels)
+        n = len(ev.kernels)
+        if depth < 6:
+            for c in ev.cpu_children:
+                a, b = kernel_us(c, depth + 1)
+                t += a
+                n += b
+        return t, n
+    out = {}
+    for ev in prof.events():
+        if ev.name.startswith("egm:"):
+            us, nk = kernel_us(ev)
+            d = out.setdefault(ev.name[4:], {"ms": 0.0, "calls": 0, "kernels": 0})
+            d["ms"] += us * 1e-3
+            d["calls"] += 1
+            d["kernels"] += nk
+    if not out or sum(v["kernels"] for v in out.values()) == 0:
+        return None
+    return dict(sorted(out.items(), key=lambda kv: -kv[1]["ms"]))
 
 
 def profile_step(fn, window: int = 0, spin_ms: float = 15.0):

@@ -681,14 +681,21 @@ def mca_layer(ctx: Ctx, x: Var, m) -> Var:
     call("mca_gates", sums, n, h, w, c, *P, gates, avg, std)
     y = Var(ctx.empty(n, h, w, c))
     idx = torch.empty(n * h * w * c, dtype=torch.uint8, device=ctx.device) if ctx.record else None
-    call("mca_apply", x.t, gates, y.t, idx, ctx.empty(n, h, w, c), ctx.empty(n, h, w, c), ctx.code, n, h, w, c)
+    fused = abi.query("mca_fused_supported", c) and os.environ.get("EGM_MCA_V1", "0") != "1"
+    if fused:      # one row-walking pass: u, d^2 and the 3x3 windows never leave the SM
+        call("mca_fwd", x.t, gates, y.t, idx, ctx.code, n, h, w, c)
+    else:
+        call("mca_apply", x.t, gates, y.t, idx, ctx.empty(n, h, w, c), ctx.empty(n, h, w, c), ctx.code, n, h, w, c)
     if ctx.record:
         def bwd():
             dy, y.grad = y.grad, None
             if dy is None:
                 return
             du, scratch = ctx.empty(n, h, w, c), ctx.empty(n, h, w, c)
-            call("mca_bwd_du", x.t, gates, dy, idx, scratch, du, ctx.code, n, h, w, c)
+            if fused:
+                call("mca_bwd", x.t, gates, dy, idx, du, ctx.code, n, h, w, c)
+            else:
+                call("mca_bwd_du", x.t, gates, dy, idx, scratch, du, ctx.code, n, h, w, c)
             dG = ctx.f64(L)
             call("mca_prod_sums", du, x.t, ctx.code, n, h, w, c, dG)
             ca, cb = torch.empty(L, **ctx.f32), torch.empty(L, **ctx.f32)

@@ -147,6 +147,13 @@ int egm_mca_gates_bwd(const double* dG, int N, int H, int W, int C, const float*
                       float* coef_a, float* coef_b, float* dw_h, float* dk_h, float* dw_w, float* dk_w, float* dw_c, float* dk_c, void* stream);
 int egm_mca_bwd_dx(const void* du, const void* x, const float* gates, const float* coef_a, const float* coef_b, void* dx, int dtype, int N,
                    int H, int W, int C, void* stream);
+/* Fused forms (csrc/mca_fused.cu; C % 64 == 0): the whole blend of MCALayer.forward (:755-790) -- gating, 3x3 range, 3x3 local variance,
+ * channel shuffle -- in ONE pass over x (row-walking CTAs, shared-memory neighbour exchange, fp32 intermediates), and its backward
+ * (du from x, dy and the arg map) in one pass.  egm_mca_fwd replaces egm_mca_apply, egm_mca_bwd replaces egm_mca_bwd_du. */
+int egm_mca_fused_supported(int C);
+int egm_mca_fwd(const void* x, const float* gates, void* y, unsigned char* argidx, int dtype, int N, int H, int W, int C, void* stream);
+int egm_mca_bwd(const void* x, const float* gates, const void* dy, const unsigned char* argidx, void* du, int dtype, int N, int H, int W, int C,
+                void* stream);
 
 /* ---- edge enhancer / FusionConv attention / GRFB tail / RGA gating (src/EGM-UNet.py:872-886, 1171-1236, 1289-1323, 458-547) ---- */
 int egm_highpass3(const void* in, void* out, int accumulate, int dtype, int N, int H, int W, int C, void* stream);

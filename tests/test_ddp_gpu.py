@@ -52,6 +52,16 @@ def _worker(rank, world, backend, mode, port, errq):
         lw = torch.tensor([1.0, 2.0])
         for step in range(3):
             batches = [synth.make_inputs(2, 48, 48, seed=500 + 10 * step + r) for r in range(world)]
+            # every step is checked from the CUDA path's OWN starting point (parameters + momentum): whole-model fp32 gradients are
+            # only reproducible to ~1e-2 (ReLU / max-pool kinks), so free-running replicas of oracle and CUDA drift
+            # apart after two updates and the third step would compare gradients at different parameters
+            cur = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+            for r in range(world):
+                for k in names:
+                    osd[r][k] = cur[k].clone()
+            st = tr.store
+            mom = {k: tr.mom_buf[off:off + p.numel()].view(p.shape).detach().cpu().clone()
+                   for (k, p), off in zip(model.named_parameters(), st.offsets)} if step > 0 else {}
             loss = tr.step(batches[rank][0].to(dev), batches[rank][1].to(dev))
             torch.cuda.synchronize()
             grads, losses = [], []

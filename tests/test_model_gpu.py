@@ -128,8 +128,15 @@ def test_bf16_masks_and_metrics_vs_oracle(variant):
         return 1 - agree, d, m
     ours, model_ = metrics(out), metrics(sim)
     print(f"{variant}: (argmax disagreement, |dDice|, |dmIoU|) CUDA bf16 {ours} | bf16-storage reference {model_}")
-    for o, s_, name in zip(ours, model_, ("argmax disagreement", "Dice", "mIoU")):
-        assert o <= 1e-3 or o <= 1.1 * s_ + 1e-4, (name, o, s_)
+    # ~150 flipped pixels of 51 200 here: the flip count itself has a ~8 % (1 sigma) sampling noise, so 1.25x is the resolution of
+    # this size; tests/test_configs_gpu.py asserts 1.1x at 1024^2 where the count is in the thousands.  Dice / mIoU are taken
+    # mask-vs-reference-mask (a monotone function of the flips), see _mask_metrics there.
+    tgt = ref.argmax(1)
+    d_o, d_s = 1 - O.dice_metric(out, tgt), 1 - O.dice_metric(sim, tgt)
+    m_o, m_s = 1 - O.miou(O.confusion_matrix(tgt, out.argmax(1), 2)), 1 - O.miou(O.confusion_matrix(tgt, sim.argmax(1), 2))
+    print(f"{variant}: mask-vs-reference-mask 1-Dice {d_o:.5f} (model {d_s:.5f}), 1-mIoU {m_o:.5f} (model {m_s:.5f})")
+    for o, s_, name in ((ours[0], model_[0], "argmax disagreement"), (d_o, d_s, "Dice"), (m_o, m_s, "mIoU")):
+        assert o <= 1e-3 or o <= 1.25 * s_ + 1e-4, (name, o, s_)
     # confident pixels (oracle margin above the bf16 noise) must agree outright
     margin = (ref[:, 0] - ref[:, 1]).abs()
     sure = margin > 0.05 * float(ref.max() - ref.min())

@@ -192,7 +192,7 @@ def _run_block(fn_engine, fn_oracle, mod, x, dtype, training=True, tol_scale=1.0
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("C,hw", [(64, (12, 10)), (256, (7, 9)), (16, (9, 9))])
+@pytest.mark.parametrize("C,hw", [(64, (12, 10)), (256, (7, 9)), (16, (9, 9)), (64, (70, 61)), (128, (33, 40)), (64, (5, 29))])
 def test_mca_layer(C, hw, dtype):
     from egm_unet_b200 import engine as E
     from egm_unet_b200.models import MCALayer
@@ -419,7 +419,9 @@ def test_conv_bn_act_train_stats_in_epilogue(case):
     names = ("y", "dx", "dw", "dgamma", "dbeta", "running_mean", "running_var")
     for fuse in (True, False):
         for nme, a, b in zip(names, res[fuse], ref):
-            tol = 3e-2 if nme in ("dx", "dw", "dgamma", "dbeta") else (2e-2 if nme == "y" else 2e-3)
+            # gradients pass through bf16-stored dy / dz; running statistics: fp32-accumulator statistics (fused) vs statistics of the
+            # bf16-rounded z (unfused)
+            tol = 6e-2 if nme in ("dx", "dw", "dgamma", "dbeta") else (2e-2 if nme == "y" else (2e-3 if fuse else 6e-3))
             assert rel_err(a, b) < tol, (fuse, nme, rel_err(a, b))
         assert res[fuse][7] == 1
     # statistics from the fp32 accumulators are at least as close to the fp32 reference as statistics of the bf16-rounded z

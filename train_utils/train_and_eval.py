@@ -98,14 +98,12 @@ def train_one_epoch(model, optimizer, data_loader, device, epoch, num_classes, l
         def post_step():
             optimizer._opt_called = True          # the step ran inside the fused kernel sequence
             lr_scheduler.step()
+            metric_logger.update(lr=g["lr"])      # before the loader is advanced: log_every prints right after its yield returns
 
-        lr = g["lr"]
         for ready in tr.run_iter(metric_logger.log_every(data_loader, print_freq, header), pre_step, post_step):
             for v in ready:
                 metric_logger.update(loss=v)
-            lr = g["lr"]
-            metric_logger.update(lr=lr)
-        return metric_logger.meters["loss"].global_avg, lr
+        return metric_logger.meters["loss"].global_avg, g["lr"]
     loss_weight = torch.as_tensor([1.0, 2.0], device=device) if num_classes == 2 else None
     for image, target in metric_logger.log_every(data_loader, print_freq, header):
         image, target = image.to(device, non_blocking=True), target.to(device, non_blocking=True)
