@@ -39,9 +39,14 @@ __global__ void k_highpass3(const T* __restrict__ in, T* __restrict__ out, int N
     stv<V>(out + p * C + c, o);
   }
 }
+int egm_highpass3_walk_launch(const void* in, void* out, int accumulate, int dtype, int N, int H, int W, int C, cudaStream_t st);   // mca_fused.cu
 extern "C" int egm_highpass3(const void* in, void* out, int accumulate, int dtype, int N, int H, int W, int C, void* stream) {
   long long total = (long long)N * H * W * C;
   if (total == 0) return EGM_OK;
+  // C % 64 == 0 (the GRFB-level enhancers): shared-memory-staged row walk; thin tensors (the C/8 enhancer inside branch_edge): gather kernel
+  static int walk = -1;
+  if (walk < 0) { const char* e = getenv("EGM_NO_STENCIL_WALK"); walk = (e && e[0] == '1') ? 0 : 1; }
+  if (walk && egm_highpass3_walk_launch(in, out, accumulate, dtype, N, H, W, C, (cudaStream_t)stream)) { EGM_LAUNCH_CHECK("highpass3(walk)"); return EGM_OK; }
   int v = egm_pick_vec(C);
   EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_highpass3<T, V><<<egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream>>>((const T*)in, (T*)out, N, H, W, C / V, accumulate))));
   EGM_LAUNCH_CHECK("highpass3"); return EGM_OK;

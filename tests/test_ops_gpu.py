@@ -467,3 +467,26 @@ def test_conv_bn_act_eval_folded_into_epilogue(case, relu):
 def abi_launches():
     from egm_unet_b200 import abi
     return abi.LAUNCH_COUNTER[0]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C,hw", [(64, (70, 61)), (128, (33, 40)), (64, (5, 29)), (256, (30, 30)), (16, (19, 23))])
+def test_highpass3_walk_and_gather(C, hw, dtype):
+    """out (+)= x - avgpool3x3(x) (EdgeAwareFeatureEnhancer, src/EGM-UNet.py:875,883): the shared-memory row-walking kernel (C % 64 == 0) and the
+    gather kernel (thin tensors) against torch, plain and accumulating (the backward form)."""
+    from egm_unet_b200 import abi
+    from egm_unet_b200.abi import call
+    x = _q(_rand(2, C, *hw), dtype)
+    ref = x - F.avg_pool2d(x, 3, 1, 1)
+    hs = Harness(dtype)
+    xv = hs.var(x, needs_grad=False)
+    out = torch.empty_like(xv.t)
+    n, h, w, c = xv.shape
+    call("highpass3", xv.t, out, 0, hs.ctx.code, n, h, w, c)
+    got = out.float().cpu().permute(0, 3, 1, 2)
+    tol = 1e-5 if dtype == torch.float32 else 1.2e-2
+    assert rel_err(got, ref) < tol
+    base = _q(_rand(2, C, *hw, seed=9), dtype)
+    acc = hs.var(base, needs_grad=False).t.clone()
+    call("highpass3", xv.t, acc, 1, hs.ctx.code, n, h, w, c)
+    assert rel_err(acc.float().cpu().permute(0, 3, 1, 2), base + ref) < tol
