@@ -15,8 +15,17 @@
 // E = 2 (u - avg3x3 u) (0.2/9) box3x3(dy); the gate gradients need global sums of du*x, taken by egm_mca_prod_sums afterwards.
 #include "common.cuh"
 
+#ifndef MF_CC
+#define MF_CC 64
+#endif
+#ifndef MF_MINB_FWD
+#define MF_MINB_FWD 1
+#endif
+#ifndef MF_MINB_BWD
+#define MF_MINB_BWD 1
+#endif
 namespace mf {
-constexpr int CC = 64;            // channels per CTA
+constexpr int CC = MF_CC;         // channels per CTA
 constexpr int V = 4;              // channels per thread
 constexpr int CV = CC / V;        // 16 channel vectors
 constexpr int TX = 32;            // pixel columns per CTA (incl. 2 + 2 halo)
@@ -55,12 +64,12 @@ __device__ __forceinline__ void st4(float* p, const float (&f)[4]) { *reinterpre
 // ===================================================================================== forward
 // smem: U[5][TX][CC] (ring over rows: r, r-1, r-2, r-3 are read while r+1 is written) | D[2][TX][CC]
 template <typename T>
-__global__ void __launch_bounds__(mf::THREADS, 1) k_mca_fwd(const T* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ idx, McaFusedParams g) {
+__global__ void __launch_bounds__(mf::THREADS, MF_MINB_FWD) k_mca_fwd(const T* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ idx, McaFusedParams g) {
   using namespace mf;
   extern __shared__ float sm[];
   float* U = sm;
   float* D = sm + 5 * ROW;
-  const int tid = threadIdx.x, cv = tid & (CV - 1), tx = tid >> 4;
+  const int tid = threadIdx.x, cv = tid & (CV - 1), tx = tid / CV;
   const int chunks = g.C / CC;
   const int n = blockIdx.z / chunks, c0 = (blockIdx.z - n * chunks) * CC + cv * V;
   const int wx = blockIdx.x * TW - HALO + tx;
@@ -234,7 +243,7 @@ extern "C" int egm_mca_fwd(const void* x, const float* gates, void* y, unsigned 
 //   DY [6][TX][CC] fp32   dy rows r .. r-4                    (the routed terms of output row r-3 read rows r-4 .. r-2)
 //   IX [6][TX][CV] u32    arg codes of the same rows
 template <typename T>
-__global__ void __launch_bounds__(mf::THREADS, 1) k_mca_bwd(const T* __restrict__ x, const T* __restrict__ dy, const unsigned char* __restrict__ idx,
+__global__ void __launch_bounds__(mf::THREADS, MF_MINB_BWD) k_mca_bwd(const T* __restrict__ x, const T* __restrict__ dy, const unsigned char* __restrict__ idx,
                                                            T* __restrict__ du, McaFusedParams g) {
   using namespace mf;
   extern __shared__ float sm[];
@@ -242,7 +251,7 @@ __global__ void __launch_bounds__(mf::THREADS, 1) k_mca_bwd(const T* __restrict_
   float* E = U + 3 * ROW;
   float* DY = E + 2 * ROW;
   unsigned* IX = reinterpret_cast<unsigned*>(DY + 6 * ROW);
-  const int tid = threadIdx.x, cv = tid & (CV - 1), tx = tid >> 4;
+  const int tid = threadIdx.x, cv = tid & (CV - 1), tx = tid / CV;
   const int chunks = g.C / CC;
   const int n = blockIdx.z / chunks, c0 = (blockIdx.z - n * chunks) * CC + cv * V;
   const int wx = blockIdx.x * TW - HALO + tx;
@@ -402,7 +411,7 @@ __global__ void __launch_bounds__(mf::THREADS, 2) k_highpass3_walk(const T* __re
   using mf::CC; using mf::V; using mf::CV; using mf::ROW;
   using namespace hp;
   extern __shared__ float sm[];
-  const int tid = threadIdx.x, cv = tid & (CV - 1), tx = tid >> 4;
+  const int tid = threadIdx.x, cv = tid & (CV - 1), tx = tid / CV;
   const int chunks = C / CC;
   const int n = blockIdx.z / chunks, c0 = (blockIdx.z - n * chunks) * CC + cv * V;
   const int wx = blockIdx.x * TW - HALO + tx;

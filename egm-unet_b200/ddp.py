@@ -59,14 +59,25 @@ class BucketReducer:
         self.pending[self.owner[param_index]].discard(param_index)
 
     def flush_ready(self):
-        """call after a tape closure returned (all its kernels are enqueued): launch every bucket that became complete"""
+        """call after a tape closure returned (all its kernels are enqueued): launch every bucket that became complete.
+        Buckets go out strictly in index order (last parameters first), so `before_launch(b)` hooks may rely on every earlier
+        bucket having been handled."""
         for b, (lo, hi, _) in enumerate(self.buckets):
-            if not self.launched[b] and not self.pending[b]:
-                self._launch(b, lo, hi)
+            if self.launched[b]:
+                continue
+            if self.pending[b]:
+                break
+            self._launch(b, lo, hi)
+
+    # optional hook(bucket index) run on the compute stream right before a bucket's all-reduce is issued: the Trainer uses it to
+    # scatter the packed tcgen05 weight gradients of that bucket into the flat buffer (engine.WeightPlan.unpack_bucket)
+    before_launch = None
 
     def _launch(self, b, lo, hi):
         self.launched[b] = True
         self.order.append(b)
+        if self.before_launch is not None:
+            self.before_launch(b)
         view = self.flat[lo:hi]
         if self.flat.is_cuda and self.comm_stream is not None:
             ev = torch.cuda.Event()

