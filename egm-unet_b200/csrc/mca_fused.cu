@@ -15,14 +15,18 @@
 // E = 2 (u - avg3x3 u) (0.2/9) box3x3(dy); the gate gradients need global sums of du*x, taken by egm_mca_prod_sums afterwards.
 #include "common.cuh"
 
+// Tunables (tools/build_mca_variants.sh + tools/mca_variants.py measured them on the cfg2 shapes, profiles/mca_variants_r2.txt):
+// 32 channels x 32 columns per CTA = 256 threads, >= 2 CTAs per SM was the fastest of the five configurations tried -- these kernels
+// are instruction-issue bound (~130 instructions per element in the forward, the arg-tracking 3x3 max/min being the largest part), so
+// what matters is how many independent barrier groups an SM can interleave, not bytes in flight.
 #ifndef MF_CC
-#define MF_CC 64
+#define MF_CC 32
 #endif
 #ifndef MF_MINB_FWD
-#define MF_MINB_FWD 1
+#define MF_MINB_FWD 2
 #endif
 #ifndef MF_MINB_BWD
-#define MF_MINB_BWD 1
+#define MF_MINB_BWD 2
 #endif
 namespace mf {
 constexpr int CC = MF_CC;         // channels per CTA

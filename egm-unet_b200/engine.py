@@ -142,7 +142,45 @@ def to_nchw(ctx: Ctx, x: Var) -> torch.Tensor:
     return y
 
 
-def seed_grad_from_nchw(ctx: Ctx, x: Var, g_nchw: torch.Tensor):
+class LogitsHandle:
+    """Stands in for the logits Var when OutConv is fused with the layout change (`out_conv`): the backward seed is the fp32 NCHW
+    dlogits tensor itself, never rounded to the activation dtype."""
+    __slots__ = ("grad_nchw",)
+
+    def __init__(self):
+        self.grad_nchw: Optional[torch.Tensor] = None
+
+
+def out_conv(ctx: Ctx, y: Var, conv: nn.Conv2d):
+    """OutConv (src/EGM-UNet.py:952-956): 1x1 conv + bias -> (fp32 NCHW logits, backward-seed handle).  One kernel reads the NHWC
+    activation and writes the NCHW logits in fp32; the backward reads fp32 NCHW dlogits and yields dy, dW, db in one pass."""
+    n, h, w, c = y.shape
+    k = conv.out_channels
+    if conv.kernel_size == (1, 1) and conv.groups == 1 and abi.query("outconv_supported", c, k):
+        logits = torch.empty(n, k, h, w, **ctx.f32)
+        wt, bs = _p(conv.weight), _p(conv.bias)
+        call("outconv_fwd", y.t, wt, bs, logits, ctx.code, n, h * w, c, k)
+        hd = LogitsHandle()
+        if ctx.record:
+            def bwd():
+                dl, hd.grad_nchw = hd.grad_nchw, None
+                if dl is None:
+                    return
+                gy = ctx.empty(n, h, w, c) if y.needs_grad else None
+                call("outconv_bwd", y.t, wt, dl, gy, ctx.grad_slot(conv.weight), ctx.grad_slot(conv.bias) if conv.bias is not None else None,
+                     ctx.code, n, h * w, c, k)
+                if gy is not None:
+                    y.accum(gy)
+            ctx.push(bwd)
+        return logits, hd
+    lv = conv_module(ctx, y, conv)
+    return to_nchw(ctx, lv), lv
+
+
+def seed_grad_from_nchw(ctx: Ctx, x, g_nchw: torch.Tensor):
+    if isinstance(x, LogitsHandle):
+        x.grad_nchw = g_nchw.contiguous()
+        return
     n, h, w, c = x.shape
     g = ctx.empty(n, h, w, c)
     call("nchw_to_nhwc", g_nchw.contiguous(), g, ctx.code, n, c, h, w)

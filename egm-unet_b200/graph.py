@@ -14,7 +14,7 @@ import torch.nn as nn
 from . import abi
 from .abi import call
 from .engine import (ACT_NONE, ACT_RELU, ACT_SIGMOID, MODE_PLAIN, MODE_RESIDUAL, Ctx, Var, WSpec, _p, bn_act, conv2d, conv_bn_act, conv_module,
-                     copy_into, deconv_concat, edge_enhancer, from_nchw, maxpool2, mca_layer, release_grad, slice_channels, to_nchw,
+                     copy_into, deconv_concat, edge_enhancer, from_nchw, maxpool2, mca_layer, out_conv, release_grad, slice_channels, to_nchw,
                      upsample_concat)
 
 
@@ -267,5 +267,4 @@ def net_forward(ctx: Ctx, model, x_nchw: torch.Tensor, variant: str):
     y = up_block(ctx, y, x3, model.up2)
     y = up_block(ctx, y, x2, model.up3)
     y = up_block(ctx, y, x1, model.up4)
-    lv = conv_module(ctx, y, model.out_conv[0])
-    return to_nchw(ctx, lv), lv
+    return out_conv(ctx, y, model.out_conv[0])          # (fp32 NCHW logits, backward-seed handle)

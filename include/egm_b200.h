@@ -130,6 +130,13 @@ int egm_deconv_weight_pack(float* w, float* wt, int Cin, int Cout, int mode, voi
 int egm_pixel_shuffle_concat_fwd(const void* skip, const void* z, void* out, int dtype, int N, int Hl, int Wl, int H, int W, int Cs, int Cu, void* stream);
 int egm_pixel_shuffle_concat_bwd(const void* dcat, void* dz, int dtype, int N, int Hl, int Wl, int H, int W, int Cs, int Cu, void* stream);
 
+/* ---- OutConv (src/EGM-UNet.py:952-956, src/unet.py:54-58) fused with the NHWC <-> NCHW change at the model boundary: fp32 logits out,
+ * fp32 dlogits in (neither is rounded to the activation dtype); backward yields dL/dy, dL/dW [K][C] and dL/dbias [K] in one pass ---- */
+int egm_outconv_supported(int C, int K);
+int egm_outconv_fwd(const void* y, const float* w, const float* bias, float* logits, int dtype, int N, long long HW, int C, int K, void* stream);
+int egm_outconv_bwd(const void* y, const float* w, const float* dlogits, void* dy, float* dw, float* dbias, int dtype, int N, long long HW, int C,
+                    int K, void* stream);
+
 /* ---- MCALayer (src/EGM-UNet.py:686-791, MCAGate :836-869) ---- */
 long long egm_mca_vec_len(int N, int H, int W, int C);
 long long egm_mca_vec_off_w(int N, int H);

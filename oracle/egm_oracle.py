@@ -224,7 +224,9 @@ def forward(sd: Dict[str, Tensor], x: Tensor, variant: str = "egm", train: bool 
     y = up_block(sd, "up2", y, x3, train, bn_updates)
     y = up_block(sd, "up3", y, x2, train, bn_updates)
     y = up_block(sd, "up4", y, x1, train, bn_updates)
-    return _conv(sd, "out_conv.0", y)
+    # OutConv: the CUDA path computes the logits from the (stored) activation with fp32 weights and writes them in fp32 (csrc/outconv.cu),
+    # so the storage model rounds neither the weight nor the result here
+    return F.conv2d(y, sd["out_conv.0.weight"], sd.get("out_conv.0.bias"))
 
 
 # --------------------------------------------------------------------------- #

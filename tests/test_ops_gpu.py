@@ -496,3 +496,33 @@ def test_highpass3_walk_and_gather(C, hw, dtype):
     acc = hs.var(base, needs_grad=False).t.clone()
     call("highpass3", xv.t, acc, 1, hs.ctx.code, n, h, w, c)
     assert rel_err(acc.float().cpu().permute(0, 3, 1, 2), base + ref) < tol
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C,K,hw", [(32, 2, (37, 29)), (64, 2, (16, 20)), (32, 4, (9, 11)), (48, 2, (8, 8))])
+def test_out_conv_fused_with_layout(C, K, hw, dtype):
+    """OutConv (1x1 + bias) reading NHWC and writing fp32 NCHW logits; backward from fp32 NCHW dlogits -> dy, dW, db (csrc/outconv.cu);
+    (48, 2) is an unsupported width and must take the generic conv + layout-conversion route with the same results."""
+    from egm_unet_b200.engine import out_conv, seed_grad_from_nchw
+    torch.manual_seed(3)
+    m = nn.Conv2d(C, K, 1)
+    x = _q(_rand(2, C, *hw), dtype)
+    g = _rand(2, K, *hw, seed=5)
+    hs = Harness(dtype)
+    xv = hs.var(x)
+    mc = nn.Conv2d(C, K, 1)
+    mc.load_state_dict(m.state_dict())
+    mc = mc.cuda()
+    logits, hd = out_conv(hs.ctx, xv, mc)
+    assert logits.dtype == torch.float32 and tuple(logits.shape) == (2, K, *hw)
+    xr = x.clone().requires_grad_(True)
+    yr = m(xr)
+    yr.backward(g)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert rel_err(logits.cpu(), yr.detach()) < tol
+    seed_grad_from_nchw(hs.ctx, hd, g.cuda())
+    hs.ctx.backward()
+    torch.cuda.synchronize()
+    assert rel_err(hs.grad(xv), xr.grad) < max(tol, 1e-2 if dtype == torch.bfloat16 else 0)
+    assert rel_err(hs.pgrad(mc.weight), m.weight.grad) < tol * 2
+    assert rel_err(hs.pgrad(mc.bias), m.bias.grad) < tol * 2
