@@ -431,6 +431,8 @@ def main():
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     if world > 1:
+        tr.close()                      # graphs that hold NCCL kernels must go before the communicator does
+        dist.barrier()
         dist.destroy_process_group()
 
 

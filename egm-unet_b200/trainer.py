@@ -59,7 +59,19 @@ class Trainer:
             self.sync_replicas()
             # graph mode: capture the bucketed NCCL all-reduces inside the step graph (gloo and other host-driven backends cannot be captured)
             self._nccl_in_graph = dist.get_backend(process_group) == "nccl" and os.environ.get("EGM_DDP_GRAPH_NCCL", "1") != "0"
+            if self._nccl_in_graph:       # interpreter exit tears the process group down: the graphs must be gone by then (see close())
+                import atexit
+                import weakref
+                ref = weakref.ref(self)
+                atexit.register(lambda: ref() is not None and ref().close())
         self._set_hp()
+
+    def close(self):
+        """Drop the captured step graphs (and their private memory pools).  REQUIRED before `dist.destroy_process_group()` when the
+        NCCL all-reduces live inside the graphs: destroying a communicator that instantiated graphs still reference hangs."""
+        self._graph = None
+        self._graphs.clear()
+        torch.cuda.synchronize(self.dev)
 
     def sync_replicas(self, src: int = 0):
         """PyTorch-DDP construction semantics: every rank starts from rank `src`'s parameters AND buffers (BN running statistics,

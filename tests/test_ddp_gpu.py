@@ -120,6 +120,9 @@ def _worker(rank, world, backend, mode, port, errq):
             assert torch.equal(lo, hi), f"step {step}: replicas diverged"
         if mode == "graph":
             assert tr._graph is not None, "graph mode never replayed a captured step"
+            if backend == "nccl":       # the bucketed all-reduces were captured INSIDE the step graph (overlap in the replayed step)
+                assert all(e[4] for e in tr._graphs.values()), "NCCL all-reduce was not captured into the graph"
+        tr.close()
         dist.barrier()
         dist.destroy_process_group()
     except Exception:
@@ -135,8 +138,10 @@ def _run(backend, mode):
     procs = [ctx.Process(target=_worker, args=(r, 2, backend, mode, port, errq)) for r in range(2)]
     for p in procs:
         p.start()
+    import time
+    deadline = time.time() + 240          # both workers together; a collective that hangs must not hold the GPU box
     for p in procs:
-        p.join(timeout=600)
+        p.join(timeout=max(1.0, deadline - time.time()))
     msgs = []
     while not errq.empty():
         msgs.append(errq.get())
