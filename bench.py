@@ -336,8 +336,7 @@ def main():
     # (hardware timestamps per kernel, keyed by the C-ABI call that launched it); fallback: windowed, queue-primed CUDA events.
     tr.use_graph = False                    # the per-kernel breakdown needs real launches
     ev_prof = primed_profile(step_resident, dev)
-    if launches == 0:
-        launches = sum(v["calls"] for v in ev_prof.values())   # kernels inside one replayed graph == C-ABI launches of one eager step
+    launches = max(launches, sum(v["calls"] for v in ev_prof.values()))   # kernels inside one replayed graph == C-ABI launches of one eager step
     prof = abi.profile_step_cupti(step_resident)
     if prof is not None:
         prof2 = abi.profile_step_cupti(step_resident) or prof   # second sample: run-to-run spread of the roofline inputs
