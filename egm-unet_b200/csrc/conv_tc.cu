@@ -8,7 +8,7 @@
 //      dgrad is the same kernel on dy with the flipped / transposed weights (egm_pack_conv_weight_tc writes both).
 //  wgrad            (k_wgrad_tc):  D[Cout x Cin] += dY[128 pixels x Cout]^T . X_shifted[128 pixels x Cin]   per tap
 //      M = Cout chunk (64/128), N = Cin chunk (<= 64), K = pixels.  Both operands MN-major (channels contiguous).
-//      Split over pixel ranges across CTAs; partial sums are reduced with fp32 red.global.add into dw[tap][ci][co].
+//      Split over pixel ranges across CTAs; partial sums are reduced with 16-byte fp32 vector reductions into dw[tap][co][ci].
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2..5 = epilogue (one TMEM lane quarter each).  smem ring of mbarrier-guarded stages; double-buffered accumulators.
@@ -180,6 +180,16 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 16 consecutive fp32 accumulators -> four 16-byte vector reductions (REDG.ADD.F32x4).  The split-K wgrad epilogues were bound by
+// the LSU's ~1.3 cycles per lane and reduction INSTRUCTION (scalar red: 256->256 @30^2 spent 33 of its 45 us per CTA there); the packed
+// gradient is laid out [tap][Cout][Cin] so that the 16 columns a thread reads from TMEM are contiguous in memory.
+__device__ __forceinline__ void red_add16(float* dst, const uint32_t (&v)[16]) {
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * m), "f"(__uint_as_float(v[4 * m])), "f"(__uint_as_float(v[4 * m + 1])),
+                 "f"(__uint_as_float(v[4 * m + 2])), "f"(__uint_as_float(v[4 * m + 3]))
+                 : "memory");
+}
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version=1 <<46 | layout <<61
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -969,13 +979,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
           uint32_t v[16];
           tmem_ld16(ta + c, v);
           tmem_ld_wait();
-          if (valid) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              int ci = cic * p.nch + c + i;
-              if (ci < p.Cin) atomicAdd(dwp + ((long long)(t0 + j) * p.Cin + ci) * p.Cout + co, __uint_as_float(v[i]));
-            }
-          }
+          if (valid && cic * p.nch + c < p.Cin) red_add16(dwp + ((long long)(t0 + j) * p.Cout + co) * p.Cin + cic * p.nch + c, v);
         }
       }
     }
@@ -1139,11 +1143,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_co
               uint32_t v[16];
               tmem_ld16(ta + c, v);
               tmem_ld_wait();
-              if (valid) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (cic * p.nch + c + i < p.Cin) atomicAdd(dwp + ((long long)tap * p.Cin + cic * p.nch + c + i) * p.Cout + co, __uint_as_float(v[i]));
-              }
+              if (valid && cic * p.nch + c < p.Cin) red_add16(dwp + ((long long)tap * p.Cout + co) * p.Cin + cic * p.nch + c, v);
             }
           }
         }
@@ -1161,11 +1161,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_co
               uint32_t v[16];
               tmem_ld16(ta + c, v);
               tmem_ld_wait();
-              if (valid) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (cic * p.nch + c + i < p.Cin) atomicAdd(dwp + ((long long)tap * p.Cin + cic * p.nch + c + i) * p.Cout + co, __uint_as_float(v[i]));
-              }
+              if (valid && cic * p.nch + c < p.Cin) red_add16(dwp + ((long long)tap * p.Cout + co) * p.Cin + cic * p.nch + c, v);
             }
           }
       }
@@ -1249,7 +1245,8 @@ static int launch_wgrad_halo(const NhwcView& xv, const NhwcView& dyv, float* dwp
   return egm_check_launch("conv2d_wgrad_tc_halo");
 }
 
-// dw_packed fp32 [taps][Cin][Cout] (same layout as the direct path; zeroed here)
+// dw_packed fp32 [taps][Cout][Cin] (NOT the [taps][Cin][Cout] of the CUDA-core path: see red_add16; unpack with egm_unpack_conv_wgrad_tc
+// or egm_wgrad_unpack_batch; zeroed here)
 // General form: x and dy are channel-strided views; Cin / Cout are the padded channel counts of dw_packed.
 extern "C" int egm_conv2d_wgrad_tc_view(const void* x, long long x_cstride, long long x_coff, int cin_valid, const void* dy, long long dy_cstride,
                                         long long dy_coff, int cout_valid, float* dw_packed, int N, int H, int W, int Cin, int Cout, int kh, int kw,
@@ -1291,6 +1288,21 @@ extern "C" int egm_conv2d_wgrad_tc_view(const void* x, long long x_cstride, long
   EGM_REQUIRE(grid < (1ll << 31), EGM_E_SHAPE, "wgrad_tc: grid too large");
   k_wgrad_tc<<<(unsigned)grid, TC_THREADS, smem, st>>>(tmDY, tmX, dw_packed, p);
   EGM_LAUNCH_CHECK("conv2d_wgrad_tc"); return EGM_OK;
+}
+// dw_packed [taps][Cout][Cin] (tcgen05 wgrad layout) -> dw [Cout][Cin][kh][kw]   (dw = beta*dw + unpacked)
+__global__ void k_unpack_dw_tc(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin, int taps, float beta) {
+  long long total = (long long)Cout * Cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int t = (int)(i % taps); long long q = i / taps;        // q = co*Cin + ci
+    float v = dwp[(long long)t * Cout * Cin + q];
+    dw[i] = beta != 0.f ? beta * dw[i] + v : v;
+  }
+}
+extern "C" int egm_unpack_conv_wgrad_tc(const float* dw_packed, float* dw, int Cout, int Cin, int kh, int kw, float beta, void* stream) {
+  long long total = (long long)Cout * Cin * kh * kw;
+  if (total == 0) return EGM_OK;
+  k_unpack_dw_tc<<<egm_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dw_packed, dw, Cout, Cin, kh * kw, beta);
+  EGM_LAUNCH_CHECK("unpack_conv_wgrad_tc"); return EGM_OK;
 }
 extern "C" int egm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_packed, int N, int H, int W, int Cin, int Cout, int kh, int kw, int dil,
                                    void* stream) {

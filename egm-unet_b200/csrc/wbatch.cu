@@ -18,7 +18,7 @@ struct EgmWJob {
   __nv_bfloat16* wf;        // [taps][CoutP][CinP]           forward B operand
   __nv_bfloat16* wd;        // [taps flipped][CinP][CoutP]   dgrad B operand (nullable)
   float* bpad;              // [CoutP] zero-padded (summed) bias (nullable)
-  const float* dwp;         // [taps][CinP][CoutP] packed fp32 weight gradient written by egm_conv2d_wgrad_tc
+  const float* dwp;         // [taps][CoutP][CinP] packed fp32 weight gradient written by egm_conv2d_wgrad_tc
   float* g[3];              // gradient destinations matching src[]
   int kind;                 // 0 = plain / grouped / zero-padded ("lifted"); 1 = 1x1 conv of cat[x,x]: W[:, :C] + W[:, C:]; 2 = 7x7+5x5+3x3 merged
   int Cout, Cin_g, groups;  // reference weight [Cout][Cin_g][kh][kw] (kind 1: src is [Cout][2*Cin_g])
@@ -87,13 +87,13 @@ __global__ void k_wgrad_unpack_batch(const EgmWJob* __restrict__ jobs, int n, lo
     const int taps = j.kh * j.kw;
     const int t = (int)(l % taps); const long long cc = l / taps; const int cil = (int)(cc % j.Cin_g); const int co = (int)(cc / j.Cin_g);
     if (j.kind == 1) {                                // both halves of the [Cout][2C] weight receive the folded gradient
-      const float v = j.dwp[(long long)cil * j.CoutP + co];
+      const float v = j.dwp[(long long)co * j.CinP + cil];
       float* g = j.g[0] + (long long)co * 2 * j.Cin_g;
       g[cil] = v; g[j.Cin_g + cil] = v;
       continue;
     }
     const int ci = (co / (j.Cout / j.groups)) * j.Cin_g + cil;
-    const float v = j.dwp[((long long)t * j.CinP + ci) * j.CoutP + co];
+    const float v = j.dwp[((long long)t * j.CoutP + co) * j.CinP + ci];
     j.g[0][l] = v;
     if (j.kind == 2) {
       const int r = t / 7, s = t - r * 7;

@@ -379,12 +379,13 @@ def conv2d(ctx: Ctx, x: Var, weight: torch.Tensor, bias: Optional[torch.Tensor],
                 call("conv2d_wgrad_tc", x.t, dy, dwp, n, h, w, cin, co, kh, kw, dilation)
             else:
                 call("conv2d_wgrad_direct", x.t, ctot, x_coff, dy, co, 0, dwp, ctx.code, n, h, w, cin, co, kh, kw, dilation, groups)
+            unpack = "unpack_conv_wgrad_tc" if pk.tc else "unpack_conv_wgrad"      # the tcgen05 wgrad packs [taps][Cout][Cin]
             if wgrad_sink is not None:
                 dw = torch.empty_like(weight)
-                call("unpack_conv_wgrad", dwp, dw, co, cig, kh, kw, 0.0)
+                call(unpack, dwp, dw, co, cig, kh, kw, 0.0)
                 wgrad_sink(dw)
             else:
-                call("unpack_conv_wgrad", dwp, ctx.grad_slot(wparam), co, cig, kh, kw, 0.0)
+                call(unpack, dwp, ctx.grad_slot(wparam), co, cig, kh, kw, 0.0)
             if bias is not None:
                 gb = torch.empty(co, **ctx.f32) if bgrad_sink is not None else ctx.grad_slot(bparam)
                 call("channel_sum", dy, ctx.code, n * h * w, co, co, 0, ctx.f64(2 * co), gb)
@@ -492,7 +493,7 @@ def _conv2d_lifted(ctx, x, wparam, bparam, weight, bias, groups, dilation, x_cof
             hold["dwp"] = torch.empty(wpd.numel(), **ctx.f32)
             return hold["dwp"]
         dwd = torch.empty_like(wpd)
-        call("unpack_conv_wgrad", hold.pop("dwp"), dwd, cop, cinp, kh, kw, 0.0)
+        call("unpack_conv_wgrad_tc", hold.pop("dwp"), dwd, cop, cinp, kh, kw, 0.0)
         dw = torch.empty_like(weight) if wgrad_sink is not None else ctx.grad_slot(wparam)
         call("conv_weight_lift", dw, dwd, co, cig, groups, taps, cop, cinp, 1)
         if wgrad_sink is not None:

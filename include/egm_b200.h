@@ -65,6 +65,9 @@ int egm_conv2d_tc(const void* x, const void* w_packed_bf16, const float* bias, v
                   int kh, int kw, int dil, void* stream);
 int egm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_packed, int N, int H, int W, int Cin, int Cout, int kh, int kw, int dil,
                         void* stream);
+/* the tcgen05 wgrad kernels leave dL/dW packed as fp32 [taps][Cout][Cin] (16-byte vector reductions from TMEM); this turns it into the
+ * nn.Conv2d layout [Cout][Cin][kh][kw]: dw = beta*dw + unpacked */
+int egm_unpack_conv_wgrad_tc(const float* dw_packed, float* dw, int Cout, int Cin, int kh, int kw, float beta, void* stream);
 /* General forms: operands are channel-strided views (element (pixel p, channel c < valid) at ptr[p*cstride + coff + c], as in
  * egm_copy_slice).  Cin / Cout are the padded (multiple-of-16) channel counts of the packed weight; channels >= *_valid read
  * as zero through TMA out-of-bounds fill and are never written, so thin (C < 16), odd and channel-sliced tensors -- GRFB branch
