@@ -787,6 +787,15 @@ extern "C" long long egm_conv2d_tc_workspace_bytes(int, int, int, int, int, int,
 extern "C" int egm_conv2d_tc_stats_supported(int Cin, int Cout, int kh, int kw, int dil) {
   return egm_conv2d_tc_supported(Cin, Cout, kh, kw, dil, 1) && (Cout == 16 || Cout == 32 || Cout == 64);
 }
+// ... and they pay off only where the MMA stream of a tile is long enough to hide the extra epilogue work (2 FP ops per accumulator):
+// measured on cfg2 (profiles/conv_epilogue_stats_r2.txt) 3x3 convs with >= 18 MMAs per tile win 13-40 us per layer over a separate
+// streaming statistics pass, while 1x1 convs (1-4 MMAs per tile) and the 16-channel layers LOSE 20-40 us -- their epilogue is the
+// critical path already.  MMAs per tile = taps * Cin/16; the 64-wide epilogue needs twice the cover of the 32-wide one.
+extern "C" int egm_conv2d_tc_stats_profitable(int Cin, int Cout, int kh, int kw, int dil) {
+  if (!egm_conv2d_tc_stats_supported(Cin, Cout, kh, kw, dil)) return 0;
+  const int mmas = kh * kw * ((Cin + 15) / 16);
+  return mmas >= (Cout > 32 ? 36 : 18) ? 1 : 0;
+}
 // Extended form.  relu != 0: y = relu(conv + bias) (inference with BatchNorm folded into weights / bias).  stats != NULL: in addition to
 // writing y, atomically add the per-channel sum and sum of squares of the fp32 results (conv + bias, before rounding) over all N*H*W
 // pixels into stats[0 .. cout_valid) and stats[cout_valid .. 2*cout_valid) (doubles, zeroed by the caller) -- the batch statistics of

@@ -193,7 +193,13 @@ extern "C" long long egm_loss_workspace_bytes(int N, int C, int H, int W) {
 // (66 x 6) halo of x0 / target-0 (pass 1) or of the sign map (pass 2) is staged in shared memory once, everything else is one coalesced
 // load per pixel.  Same arithmetic, same accumulator layout.
 constexpr int LT_W = 64, LT_H = 4, LT_HW = LT_W + 2, LT_HH = LT_H + 2;
+// The per-class register arrays are sized by the template parameter (2 / 4 / 16 classes): with the fixed 16 the passes needed 125-140
+// registers per thread and ran at 12-24 % occupancy (ncu, profiles/membound_r2_ncu.txt) for a 2-class problem.
+#pragma push_macro("EGM_MAXC")
+#undef EGM_MAXC
+#define EGM_MAXC MAXC
 
+template <int MAXC>
 __global__ void __launch_bounds__(256) k_loss_pass1_t(const float* __restrict__ logits, const long long* __restrict__ target, const float* __restrict__ weight,
                                                       int N, int C, int H, int W, int ignore_index, double* __restrict__ acc, unsigned char* __restrict__ smap) {
   __shared__ float red[32];
@@ -277,6 +283,7 @@ __global__ void __launch_bounds__(256) k_loss_pass1_t(const float* __restrict__ 
   }
 }
 
+template <int MAXC>
 __global__ void __launch_bounds__(256) k_loss_pass2_t(const float* __restrict__ logits, const long long* __restrict__ target, const float* __restrict__ weight,
                                                       int N, int C, int H, int W, int ignore_index, const double* __restrict__ acc,
                                                       const unsigned char* __restrict__ smap, float gscale, int with_dice, float* __restrict__ dlogits) {
@@ -354,6 +361,8 @@ __global__ void __launch_bounds__(256) k_loss_pass2_t(const float* __restrict__ 
   }
 }
 
+#pragma pop_macro("EGM_MAXC")
+
 // logits fp32 NCHW, target int64 [N,H,W]; loss_out[8] (total, ce, dice, laplace, lap, sobel, #out-of-range labels, unused); dlogits may be null (forward only).
 extern "C" int egm_loss_fwd_bwd(const float* logits, const long long* target, const float* class_weight, int N, int C, int H, int W, int ignore_index,
                                 int with_dice, float grad_scale, float* loss_out, float* dlogits, void* workspace, long long workspace_bytes, void* stream) {
@@ -381,9 +390,14 @@ extern "C" int egm_loss_fwd_bwd(const float* logits, const long long* target, co
   const int tilesX = (W + LT_W - 1) / LT_W, tilesY = (H + LT_H - 1) / LT_H;
   long long gy = (long long)egm_num_sms() * 8 / ((long long)N * tilesX); if (gy < 1) gy = 1; if (gy > tilesY) gy = tilesY;
   dim3 grid(tilesX, (unsigned)gy, N);
-  k_loss_pass1_t<<<grid, 256, 0, st>>>(logits, target, class_weight, N, C, H, W, ignore_index, acc, smap);
-  k_loss_finalize<<<1, 32, 0, st>>>(acc, N, C, (double)N * (double)HW, with_dice, loss_out);
-  if (dlogits) k_loss_pass2_t<<<grid, 256, 0, st>>>(logits, target, class_weight, N, C, H, W, ignore_index, acc, smap, grad_scale, with_dice, dlogits);
+#define EGM_LOSS_LAUNCH(MC)                                                                                                                    \
+  {                                                                                                                                            \
+    k_loss_pass1_t<MC><<<grid, 256, 0, st>>>(logits, target, class_weight, N, C, H, W, ignore_index, acc, smap);                               \
+    k_loss_finalize<<<1, 32, 0, st>>>(acc, N, C, (double)N * (double)HW, with_dice, loss_out);                                                 \
+    if (dlogits) k_loss_pass2_t<MC><<<grid, 256, 0, st>>>(logits, target, class_weight, N, C, H, W, ignore_index, acc, smap, grad_scale, with_dice, dlogits); \
+  }
+  if (C <= 2) EGM_LOSS_LAUNCH(2) else if (C <= 4) EGM_LOSS_LAUNCH(4) else EGM_LOSS_LAUNCH(16)
+#undef EGM_LOSS_LAUNCH
   EGM_LAUNCH_CHECK("loss_fwd_bwd"); return EGM_OK;
 }
 

@@ -77,6 +77,7 @@ class Ctx:
         self.f32 = dict(dtype=torch.float32, device=device)
         self.wplan: Optional["WeightPlan"] = None   # batched weight preparation (Trainer); None = per-conv pack kernels
         self.fuse_bn = os.environ.get("EGM_NO_BN_FUSE", "0") != "1"   # BN statistics / inference BN+ReLU in the conv epilogue
+        self.stats_all = os.environ.get("EGM_BN_STATS_ALL", "0") == "1"   # epilogue statistics wherever supported, not only where they win
         self._arena, self._arena_off = None, 0
 
     ARENA_DOUBLES = 1 << 16
@@ -597,7 +598,7 @@ def conv_bn_act(ctx: Ctx, x: Var, conv: nn.Conv2d, bn: nn.BatchNorm2d, act: int,
             wfold = torch.empty_like(_p(conv.weight))
             call("scale_rows", _p(conv.weight), scale, wfold, co, cig * kh * kw)
             return conv2d(ctx, x, wfold, shift, groups=conv.groups, dilation=d, epi=Epi(relu=(act == ACT_RELU), out=out, out_coff=out_coff))
-        if training and x.M > 0 and abi.query("conv2d_tc_stats_supported", cinp, cop, kh, kw, d):
+        if training and x.M > 0 and abi.query("conv2d_tc_stats_supported" if ctx.stats_all else "conv2d_tc_stats_profitable", cinp, cop, kh, kw, d):
             epi = Epi(stats=True)
             z = conv2d(ctx, x, conv.weight, conv.bias, groups=conv.groups, dilation=d, epi=epi)
             return bn_act(ctx, z, bn, act, mode, aux, alpha, out=out, out_coff=out_coff, sums=epi.sums)

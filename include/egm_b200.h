@@ -86,6 +86,7 @@ int egm_conv2d_tc_view(const void* x, long long x_cstride, long long x_coff, int
  *               caller); egm_bn_finalize turns them into scale / shift / running statistics.  Available where
  *               egm_conv2d_tc_stats_supported (padded Cout of 16 / 32 / 64: the layers with the large pre-BN maps). */
 int egm_conv2d_tc_stats_supported(int Cin, int Cout, int kh, int kw, int dil);
+int egm_conv2d_tc_stats_profitable(int Cin, int Cout, int kh, int kw, int dil);   /* supported AND faster than a separate statistics pass (measured) */
 int egm_conv2d_tc_ex(const void* x, long long x_cstride, long long x_coff, int cin_valid, const void* w_packed_bf16, const float* bias,
                      void* y, long long y_cstride, long long y_coff, int cout_valid, int accumulate, int N, int H, int W, int Cin,
                      int Cout, int kh, int kw, int dil, int relu, double* stats, void* stream);

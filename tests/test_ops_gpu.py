@@ -402,6 +402,7 @@ def test_conv_bn_act_train_stats_in_epilogue(case):
     for fuse in (True, False):
         hs = Harness(torch.bfloat16, use_tc=True)
         hs.ctx.fuse_bn = fuse
+        hs.ctx.stats_all = True           # every shape the epilogue supports, not only the ones the profitability rule selects
         cc, bb = nn.Conv2d(cin, cout, k, padding=dil * (k - 1) // 2, dilation=dil, groups=groups, bias=bias), nn.BatchNorm2d(cout, momentum=0.01)
         cc.load_state_dict(conv.state_dict()); bb.load_state_dict(bn.state_dict())
         cc, bb = cc.cuda(), bb.cuda()
