@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 HEADER = os.path.join(_ROOT, "include", "egm_b200.h")
-LIB_PATH = os.path.join(_HERE, "libegm_b200.so")
+LIB_PATH = os.environ.get("EGM_LIB") or os.path.join(_HERE, "libegm_b200.so")   # EGM_LIB: a tuning-variant build of the same library
 
 F32, BF16 = 0, 1
 DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16}

@@ -7,7 +7,7 @@
 
 // ------------------------------------------------------------------ out (+)= in - avgpool3x3(in)   (zero pad, /9; self-adjoint)
 template <typename T, int V>
-__global__ void k_highpass3(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int CV, int accumulate) {
+__global__ void k_highpass3(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int CV, int accumulate) { egm_pdl_enter();
   const int C = CV * V; long long total = (long long)N * H * W * CV;
   const NhwcIndexer ix(CV, W, H, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -48,7 +48,7 @@ extern "C" int egm_highpass3(const void* in, void* out, int accumulate, int dtyp
   if (walk < 0) { const char* e = getenv("EGM_NO_STENCIL_WALK"); walk = (e && e[0] == '1') ? 0 : 1; }
   if (walk && egm_highpass3_walk_launch(in, out, accumulate, dtype, N, H, W, C, (cudaStream_t)stream)) { EGM_LAUNCH_CHECK("highpass3(walk)"); return EGM_OK; }
   int v = egm_pick_vec(C);
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_highpass3<T, V><<<egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream>>>((const T*)in, (T*)out, N, H, W, C / V, accumulate))));
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_highpass3<T, V>, egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream, (const T*)in, (T*)out, N, H, W, C / V, accumulate))));
   EGM_LAUNCH_CHECK("highpass3"); return EGM_OK;
 }
 
@@ -56,7 +56,7 @@ extern "C" int egm_highpass3(const void* in, void* out, int accumulate, int dtyp
 // G threads (power of two <= 32) cooperate on one pixel.
 template <typename T, int V>
 __global__ void __launch_bounds__(256) k_pixel_dot(const T* __restrict__ a, const T* __restrict__ b, const float* __restrict__ cvec, float* __restrict__ out,
-                                                   long long M, long long HW, int C, int G) {
+                                                   long long M, long long HW, int C, int G) { egm_pdl_enter();
   const int CV = C / V;
   const int lane = threadIdx.x % G;
   const long long gpb = blockDim.x / G;
@@ -80,13 +80,13 @@ extern "C" int egm_pixel_dot(const void* a, const void* b, const float* cvec, fl
   long long M = (long long)N * HW;
   if (M == 0) return EGM_OK;
   int v = egm_pick_vec(C); int CV = C / v; int G = 1; while (G < CV && G < 32) G <<= 1;
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_pixel_dot<T, V><<<egm_grid_for(M * G, 256), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, cvec, out, M, HW, C, G))));
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_pixel_dot<T, V>, egm_grid_for(M * G, 256), 256, 0, (cudaStream_t)stream, (const T*)a, (const T*)b, cvec, out, M, HW, C, G))));
   EGM_LAUNCH_CHECK("pixel_dot"); return EGM_OK;
 }
 
 // ------------------------------------------------------------------ per-(sample, channel) dot over pixels: out[n][c] = sum_p a*b*pvec[p]
 template <typename T, int V>
-__global__ void k_sample_chan_dot(const T* __restrict__ a, const T* __restrict__ b, const float* __restrict__ pvec, float* __restrict__ out, long long HW, int C) {
+__global__ void k_sample_chan_dot(const T* __restrict__ a, const T* __restrict__ b, const float* __restrict__ pvec, float* __restrict__ out, long long HW, int C) { egm_pdl_enter();
   extern __shared__ float sm[];
   const int CV = C / V, rpi = blockDim.x / CV, cv = threadIdx.x % CV, r = threadIdx.x / CV, n = blockIdx.y;
   float acc[V];
@@ -119,7 +119,7 @@ extern "C" int egm_sample_chan_dot(const void* a, const void* b, const float* pv
   int v = egm_pick_vec(C); int CV = C / v; EGM_REQUIRE(CV <= 256, EGM_E_SHAPE, "sample_chan_dot: C too large");
   int rpi = 256 / CV; int threads = CV * rpi;
   long long bx = (HW + (long long)rpi * 16 - 1) / ((long long)rpi * 16); long long cap = egm_num_sms() * 4 / N + 1; if (bx > cap) bx = cap; if (bx < 1) bx = 1;
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_sample_chan_dot<T, V><<<dim3((unsigned)bx, N), threads, (size_t)rpi * C * sizeof(float), st>>>(
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_sample_chan_dot<T, V>, dim3((unsigned)bx, N), threads, (size_t)rpi * C * sizeof(float), st, 
       (const T*)a, (const T*)b, pvec, out, HW, C))));
   EGM_LAUNCH_CHECK("sample_chan_dot"); return EGM_OK;
 }
@@ -135,7 +135,7 @@ __device__ __forceinline__ float pixel_phi(const T* g, long long m, int Gc, int 
   return 1.f + s / (float)Gc;
 }
 template <typename T, int V>
-__global__ void k_mul_pixel_gate(const T* __restrict__ a, const T* __restrict__ g, T* __restrict__ y, long long M, int CV, int Gc, int mode) {
+__global__ void k_mul_pixel_gate(const T* __restrict__ a, const T* __restrict__ g, T* __restrict__ y, long long M, int CV, int Gc, int mode) { egm_pdl_enter();
   const int C = CV * V; long long total = M * CV;
   const RowIndexer rix(CV, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -150,12 +150,12 @@ __global__ void k_mul_pixel_gate(const T* __restrict__ a, const T* __restrict__ 
 extern "C" int egm_mul_pixel_gate(const void* a, const void* g, void* y, int dtype, long long M, int C, int Gc, int mode, void* stream) {
   if (M * C == 0) return EGM_OK;
   int v = egm_pick_vec(C);
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_mul_pixel_gate<T, V><<<egm_grid_for(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)g, (T*)y, M, C / V, Gc, mode))));
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_mul_pixel_gate<T, V>, egm_grid_for(M * (C / V), 256), 256, 0, (cudaStream_t)stream, (const T*)a, (const T*)g, (T*)y, M, C / V, Gc, mode))));
   EGM_LAUNCH_CHECK("mul_pixel_gate"); return EGM_OK;
 }
 // dg[m][j] = dot[m] * d phi / d g_j
 template <typename T>
-__global__ void k_pixel_gate_bwd(const float* __restrict__ dot, const T* __restrict__ g, T* __restrict__ dg, long long M, int Gc, int mode) {
+__global__ void k_pixel_gate_bwd(const float* __restrict__ dot, const T* __restrict__ g, T* __restrict__ dg, long long M, int Gc, int mode) { egm_pdl_enter();
   long long total = M * Gc;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long m = i / Gc;
@@ -167,14 +167,14 @@ __global__ void k_pixel_gate_bwd(const float* __restrict__ dot, const T* __restr
 }
 extern "C" int egm_pixel_gate_bwd(const float* dot, const void* g, void* dg, int dtype, long long M, int Gc, int mode, void* stream) {
   if (M * Gc == 0) return EGM_OK;
-  EGM_DISPATCH_DTYPE(dtype, (k_pixel_gate_bwd<T><<<egm_grid_for(M * Gc, 256), 256, 0, (cudaStream_t)stream>>>(dot, (const T*)g, (T*)dg, M, Gc, mode)));
+  EGM_DISPATCH_DTYPE(dtype, (egm_launch(k_pixel_gate_bwd<T>, egm_grid_for(M * Gc, 256), 256, 0, (cudaStream_t)stream, dot, (const T*)g, (T*)dg, M, Gc, mode)));
   EGM_LAUNCH_CHECK("pixel_gate_bwd"); return EGM_OK;
 }
 
 // ------------------------------------------------------------------ unary elementwise (flat): gelu fwd/bwd, scale by a device scalar
 //   op 0: y = gelu(x) (exact erf)      op 1: y = dy * gelu'(x)   (a = dy, b = x)       op 2: y = a * (*scalar)
 template <typename T, int V>
-__global__ void k_unary(const T* __restrict__ a, const T* __restrict__ b, const float* __restrict__ scalar, T* __restrict__ y, long long nv, int op) {
+__global__ void k_unary(const T* __restrict__ a, const T* __restrict__ b, const float* __restrict__ scalar, T* __restrict__ y, long long nv, int op) { egm_pdl_enter();
   const float sc = (op == 2) ? *scalar : 1.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
     FVec<V> x = ldv<V>(a + i * V), o, z;
@@ -191,12 +191,12 @@ __global__ void k_unary(const T* __restrict__ a, const T* __restrict__ b, const 
 extern "C" int egm_unary(const void* a, const void* b, const float* scalar_dev, void* y, int dtype, long long n, int op, void* stream) {
   if (n == 0) return EGM_OK;
   int v = egm_pick_vec(n);
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_unary<T, V><<<egm_grid_for(n / V, 256), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, scalar_dev, (T*)y, n / V, op))));
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_unary<T, V>, egm_grid_for(n / V, 256), 256, 0, (cudaStream_t)stream, (const T*)a, (const T*)b, scalar_dev, (T*)y, n / V, op))));
   EGM_LAUNCH_CHECK("unary"); return EGM_OK;
 }
 // out[0] = sum_i a[i]*b[i]
 template <typename T>
-__global__ void k_dot_all(const T* __restrict__ a, const T* __restrict__ b, long long n, float* out) {
+__global__ void k_dot_all(const T* __restrict__ a, const T* __restrict__ b, long long n, float* out) { egm_pdl_enter();
   __shared__ float red[32];
   float s = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += ldf(a + i) * ldf(b + i);
@@ -207,14 +207,14 @@ extern "C" int egm_dot_all(const void* a, const void* b, float* out, int dtype, 
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(out, 0, sizeof(float), st);
   if (n == 0) return EGM_OK;
-  EGM_DISPATCH_DTYPE(dtype, (k_dot_all<T><<<egm_grid_for(n, 256, 2), 256, 0, st>>>((const T*)a, (const T*)b, n, out)));
+  EGM_DISPATCH_DTYPE(dtype, (egm_launch(k_dot_all<T>, egm_grid_for(n, 256, 2), 256, 0, st, (const T*)a, (const T*)b, n, out)));
   EGM_LAUNCH_CHECK("dot_all"); return EGM_OK;
 }
 
 // ------------------------------------------------------------------ FusionConv spatial attention
 // mm[m] = (mean_c s, max_c s) fp32; amax[m] = first arg-max channel
 template <typename T>
-__global__ void k_chan_meanmax(const T* __restrict__ s, float* __restrict__ mm, unsigned char* __restrict__ amax, long long M, int C) {
+__global__ void k_chan_meanmax(const T* __restrict__ s, float* __restrict__ mm, unsigned char* __restrict__ amax, long long M, int C) { egm_pdl_enter();
   for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
     float sum = 0.f, mx = -INFINITY; int am = 0;
     for (int c = 0; c < C; ++c) { float v = ldf(s + m * C + c); sum += v; if (v > mx) { mx = v; am = c; } }
@@ -224,11 +224,11 @@ __global__ void k_chan_meanmax(const T* __restrict__ s, float* __restrict__ mm, 
 extern "C" int egm_chan_meanmax(const void* s, float* mm, unsigned char* amax, int dtype, long long M, int C, void* stream) {
   EGM_REQUIRE(C <= 256, EGM_E_SHAPE, "chan_meanmax: C > 256");
   if (M == 0) return EGM_OK;
-  EGM_DISPATCH_DTYPE(dtype, (k_chan_meanmax<T><<<egm_grid_for(M, 128), 128, 0, (cudaStream_t)stream>>>((const T*)s, mm, amax, M, C)));
+  EGM_DISPATCH_DTYPE(dtype, (egm_launch(k_chan_meanmax<T>, egm_grid_for(M, 128), 128, 0, (cudaStream_t)stream, (const T*)s, mm, amax, M, C)));
   EGM_LAUNCH_CHECK("chan_meanmax"); return EGM_OK;
 }
 // sa[m] = sigmoid(conv7x7(mm; w[1][2][7][7], pad 3, no bias))
-__global__ void k_sa_conv_fwd(const float* __restrict__ mm, const float* __restrict__ w, float* __restrict__ sa, int N, int H, int W) {
+__global__ void k_sa_conv_fwd(const float* __restrict__ mm, const float* __restrict__ w, float* __restrict__ sa, int N, int H, int W) { egm_pdl_enter();
   __shared__ float ws[98];
   for (int i = threadIdx.x; i < 98; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
@@ -245,11 +245,11 @@ __global__ void k_sa_conv_fwd(const float* __restrict__ mm, const float* __restr
 }
 extern "C" int egm_sa_conv_fwd(const float* mm, const float* w, float* sa, int N, int H, int W, void* stream) {
   long long M = (long long)N * H * W; if (M == 0) return EGM_OK;
-  k_sa_conv_fwd<<<egm_grid_for(M, 128), 128, 0, (cudaStream_t)stream>>>(mm, w, sa, N, H, W);
+  egm_launch(k_sa_conv_fwd, egm_grid_for(M, 128), 128, 0, (cudaStream_t)stream, mm, w, sa, N, H, W);
   EGM_LAUNCH_CHECK("sa_conv_fwd"); return EGM_OK;
 }
 // dpre = dsa * sa (1-sa);  dmm[q][ch] = sum_{r,s} w[ch][r][s] dpre[q-(r-3,s-3)];  dw[ch][r][s] = sum_p dpre[p] mm[p+(r-3,s-3)][ch]
-__global__ void k_sa_conv_bwd_dmm(const float* __restrict__ dsa, const float* __restrict__ sa, const float* __restrict__ w, float* __restrict__ dmm, int N, int H, int W) {
+__global__ void k_sa_conv_bwd_dmm(const float* __restrict__ dsa, const float* __restrict__ sa, const float* __restrict__ w, float* __restrict__ dmm, int N, int H, int W) { egm_pdl_enter();
   __shared__ float ws[98];
   for (int i = threadIdx.x; i < 98; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
@@ -266,7 +266,7 @@ __global__ void k_sa_conv_bwd_dmm(const float* __restrict__ dsa, const float* __
   }
 }
 __global__ void __launch_bounds__(256) k_sa_conv_bwd_dw(const float* __restrict__ dsa, const float* __restrict__ sa, const float* __restrict__ mm,
-                                                        float* __restrict__ dw, int N, int H, int W) {
+                                                        float* __restrict__ dw, int N, int H, int W) { egm_pdl_enter();
   __shared__ float red[32];
   const int ch = blockIdx.y / 7, r = blockIdx.y % 7;
   long long M = (long long)N * H * W;
@@ -288,9 +288,9 @@ extern "C" int egm_sa_conv_bwd(const float* dsa, const float* sa, const float* m
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(dw, 0, sizeof(float) * 98, st);
   long long M = (long long)N * H * W; if (M == 0) return EGM_OK;
-  k_sa_conv_bwd_dmm<<<egm_grid_for(M, 128), 128, 0, st>>>(dsa, sa, w, dmm, N, H, W);
+  egm_launch(k_sa_conv_bwd_dmm, egm_grid_for(M, 128), 128, 0, st, dsa, sa, w, dmm, N, H, W);
   int bx = egm_grid_for(M, 256, 2) / 14 + 1;
-  k_sa_conv_bwd_dw<<<dim3(bx, 14), 256, 0, st>>>(dsa, sa, mm, dw, N, H, W);
+  egm_launch(k_sa_conv_bwd_dw, dim3(bx, 14), 256, 0, st, dsa, sa, mm, dw, N, H, W);
   EGM_LAUNCH_CHECK("sa_conv_bwd"); return EGM_OK;
 }
 
@@ -299,7 +299,7 @@ __device__ __forceinline__ unsigned int f2ord(float f) { unsigned int u = __floa
 __device__ __forceinline__ float ord2f(unsigned int u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
 // global avg / max (+ FIRST arg-max pixel) per (n, c).  keys: packed (ordered value << 32 | ~pixel) combined with 64-bit atomicMax.
 template <typename T, int V>
-__global__ void k_gap_gmp(const T* __restrict__ f, float* __restrict__ sum, unsigned long long* __restrict__ keys, long long HW, int C) {
+__global__ void k_gap_gmp(const T* __restrict__ f, float* __restrict__ sum, unsigned long long* __restrict__ keys, long long HW, int C) { egm_pdl_enter();
   const int CV = C / V, rpi = blockDim.x / CV, cv = threadIdx.x % CV, r = threadIdx.x / CV, n = blockIdx.y;
   float acc[V], mx[V]; unsigned int am[V];
 #pragma unroll
@@ -327,7 +327,7 @@ __global__ void k_gap_gmp(const T* __restrict__ f, float* __restrict__ sum, unsi
     if (k) atomicMax(keys + (long long)n * C + c, k);
   }
 }
-__global__ void k_gap_gmp_fin(const float* sum, const unsigned long long* keys, float* avg, float* mx, int* arg, long long NC, float inv_hw) {
+__global__ void k_gap_gmp_fin(const float* sum, const unsigned long long* keys, float* avg, float* mx, int* arg, long long NC, float inv_hw) { egm_pdl_enter();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= NC) return;
   unsigned long long k = keys[i];
@@ -343,13 +343,13 @@ extern "C" int egm_gap_gmp(const void* f, float* avg, float* mx, int* arg, void*
   int v = egm_pick_vec(C); int CV = C / v; EGM_REQUIRE(CV <= 256, EGM_E_SHAPE, "gap_gmp: C too large");
   int rpi = 256 / CV; int threads = CV * rpi;
   long long bx = (HW + (long long)rpi * 16 - 1) / ((long long)rpi * 16); long long cap = egm_num_sms() * 4 / N + 1; if (bx > cap) bx = cap; if (bx < 1) bx = 1;
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_gap_gmp<T, V><<<dim3((unsigned)bx, N), threads, 0, st>>>((const T*)f, sum, keys, HW, C))));
-  k_gap_gmp_fin<<<cdiv(NC, 128), 128, 0, st>>>(sum, keys, avg, mx, arg, NC, 1.f / (float)HW);
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_gap_gmp<T, V>, dim3((unsigned)bx, N), threads, 0, st, (const T*)f, sum, keys, HW, C))));
+  egm_launch(k_gap_gmp_fin, cdiv(NC, 128), 128, 0, st, sum, keys, avg, mx, arg, NC, 1.f / (float)HW);
   EGM_LAUNCH_CHECK("gap_gmp"); return EGM_OK;
 }
 // ca[n][c] = sigmoid(W2 relu(W0 avg) + W2 relu(W0 max));  hid[2][N][Cr] keeps the pre-ReLU hidden activations.  One block per sample.
 __global__ void k_ca_mlp_fwd(const float* __restrict__ avg, const float* __restrict__ mx, const float* __restrict__ w0, const float* __restrict__ w2,
-                             float* __restrict__ ca, float* __restrict__ hid, int N, int C, int Cr) {
+                             float* __restrict__ ca, float* __restrict__ hid, int N, int C, int Cr) { egm_pdl_enter();
   extern __shared__ float sh[];   // ha[Cr] hm[Cr]
   const int n = blockIdx.x;
   for (int j = threadIdx.x; j < Cr; j += blockDim.x) {
@@ -365,14 +365,14 @@ __global__ void k_ca_mlp_fwd(const float* __restrict__ avg, const float* __restr
   }
 }
 extern "C" int egm_ca_mlp_fwd(const float* avg, const float* mx, const float* w0, const float* w2, float* ca, float* hid, int N, int C, int Cr, void* stream) {
-  k_ca_mlp_fwd<<<N, 128, 2 * Cr * sizeof(float), (cudaStream_t)stream>>>(avg, mx, w0, w2, ca, hid, N, C, Cr);
+  egm_launch(k_ca_mlp_fwd, N, 128, 2 * Cr * sizeof(float), (cudaStream_t)stream, avg, mx, w0, w2, ca, hid, N, C, Cr);
   EGM_LAUNCH_CHECK("ca_mlp_fwd"); return EGM_OK;
 }
 // single block: parameter grads need sums over samples
 __global__ void __launch_bounds__(256) k_ca_mlp_bwd(const float* __restrict__ dca, const float* __restrict__ ca, const float* __restrict__ avg,
                                                     const float* __restrict__ mx, const float* __restrict__ hid, const float* __restrict__ w0,
                                                     const float* __restrict__ w2, float* __restrict__ dw0, float* __restrict__ dw2,
-                                                    float* __restrict__ davg, float* __restrict__ dmx, int N, int C, int Cr) {
+                                                    float* __restrict__ davg, float* __restrict__ dmx, int N, int C, int Cr) { egm_pdl_enter();
   extern __shared__ float sh[];   // dpre[N*C] | dha[N*Cr] | dhm[N*Cr]
   float* dpre = sh; float* dha = sh + N * C; float* dhm = dha + N * Cr;
   for (int i = threadIdx.x; i < N * C; i += blockDim.x) { float s = ca[i]; dpre[i] = dca[i] * s * (1.f - s); }
@@ -403,14 +403,14 @@ extern "C" int egm_ca_mlp_bwd(const float* dca, const float* ca, const float* av
                               float* dw0, float* dw2, float* davg, float* dmx, int N, int C, int Cr, void* stream) {
   size_t smb = (size_t)(N * C + 2 * N * Cr) * sizeof(float);
   EGM_REQUIRE(smb <= 48 * 1024, EGM_E_SHAPE, "ca_mlp_bwd: N*C too large for one block");
-  k_ca_mlp_bwd<<<1, 256, smb, (cudaStream_t)stream>>>(dca, ca, avg, mx, hid, w0, w2, dw0, dw2, davg, dmx, N, C, Cr);
+  egm_launch(k_ca_mlp_bwd, 1, 256, smb, (cudaStream_t)stream, dca, ca, avg, mx, hid, w0, w2, dw0, dw2, davg, dmx, N, C, Cr);
   EGM_LAUNCH_CHECK("ca_mlp_bwd"); return EGM_OK;
 }
 
 // t = f + s * sa[m] * ca[n][c]
 template <typename T, int V>
 __global__ void k_fuse_mix_fwd(const T* __restrict__ f, const T* __restrict__ s, const float* __restrict__ sa, const float* __restrict__ ca, T* __restrict__ t,
-                               long long M, long long HW, int CV) {
+                               long long M, long long HW, int CV) { egm_pdl_enter();
   const int C = CV * V; long long total = M * CV;
   const RowIndexer rix(CV, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -425,13 +425,13 @@ __global__ void k_fuse_mix_fwd(const T* __restrict__ f, const T* __restrict__ s,
 extern "C" int egm_fuse_mix_fwd(const void* f, const void* s, const float* sa, const float* ca, void* t, int dtype, int N, long long HW, int C, void* stream) {
   long long M = (long long)N * HW; if (M * C == 0) return EGM_OK;
   int v = egm_pick_vec(C);
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_fuse_mix_fwd<T, V><<<egm_grid_for(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>((const T*)f, (const T*)s, sa, ca, (T*)t, M, HW, C / V))));
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_fuse_mix_fwd<T, V>, egm_grid_for(M * (C / V), 256), 256, 0, (cudaStream_t)stream, (const T*)f, (const T*)s, sa, ca, (T*)t, M, HW, C / V))));
   EGM_LAUNCH_CHECK("fuse_mix_fwd"); return EGM_OK;
 }
 // ds = dt*sa*ca + dmm[m][0]/C + [c == amax[m]] * dmm[m][1]
 template <typename T, int V>
 __global__ void k_fuse_mix_bwd_s(const T* __restrict__ dt, const float* __restrict__ sa, const float* __restrict__ ca, const float* __restrict__ dmm,
-                                 const unsigned char* __restrict__ amax, T* __restrict__ ds, long long M, long long HW, int CV) {
+                                 const unsigned char* __restrict__ amax, T* __restrict__ ds, long long M, long long HW, int CV) { egm_pdl_enter();
   const int C = CV * V; long long total = M * CV;
   const RowIndexer rix(CV, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -447,13 +447,13 @@ extern "C" int egm_fuse_mix_bwd_s(const void* dt, const float* sa, const float* 
                                   long long HW, int C, void* stream) {
   long long M = (long long)N * HW; if (M * C == 0) return EGM_OK;
   int v = egm_pick_vec(C);
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_fuse_mix_bwd_s<T, V><<<egm_grid_for(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>((const T*)dt, sa, ca, dmm, amax, (T*)ds, M, HW, C / V))));
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_fuse_mix_bwd_s<T, V>, egm_grid_for(M * (C / V), 256), 256, 0, (cudaStream_t)stream, (const T*)dt, sa, ca, dmm, amax, (T*)ds, M, HW, C / V))));
   EGM_LAUNCH_CHECK("fuse_mix_bwd_s"); return EGM_OK;
 }
 // df (+)= dt + davg[n][c]/HW + [p == arg[n][c]] * dmx[n][c]
 template <typename T, int V>
 __global__ void k_fuse_df_finish(T* __restrict__ df, const T* __restrict__ dt, const float* __restrict__ davg, const float* __restrict__ dmx,
-                                 const int* __restrict__ arg, int accumulate, long long M, long long HW, int CV) {
+                                 const int* __restrict__ arg, int accumulate, long long M, long long HW, int CV) { egm_pdl_enter();
   const int C = CV * V; long long total = M * CV; const float ih = 1.f / (float)HW;
   const RowIndexer rix(CV, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -468,6 +468,6 @@ __global__ void k_fuse_df_finish(T* __restrict__ df, const T* __restrict__ dt, c
 extern "C" int egm_fuse_df_finish(void* df, const void* dt, const float* davg, const float* dmx, const int* arg, int accumulate, int dtype, int N, long long HW, int C, void* stream) {
   long long M = (long long)N * HW; if (M * C == 0) return EGM_OK;
   int v = egm_pick_vec(C);
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_fuse_df_finish<T, V><<<egm_grid_for(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>((T*)df, (const T*)dt, davg, dmx, arg, accumulate, M, HW, C / V))));
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_fuse_df_finish<T, V>, egm_grid_for(M * (C / V), 256), 256, 0, (cudaStream_t)stream, (T*)df, (const T*)dt, davg, dmx, arg, accumulate, M, HW, C / V))));
   EGM_LAUNCH_CHECK("fuse_df_finish"); return EGM_OK;
 }

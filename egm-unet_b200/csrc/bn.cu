@@ -106,7 +106,7 @@ struct StatsF {
   }
 };
 template <typename T, int V>
-__global__ void k_bn_stats(StatsF<T, V> f, long long M, int C, double* out, BnTail tl) {
+__global__ void k_bn_stats(StatsF<T, V> f, long long M, int C, double* out, BnTail tl) { egm_pdl_enter();
   extern __shared__ float smem[];
   chan_reduce<V, 2>(f, M, C, out, smem);
   bn_tail_run(tl, out, C, threadIdx.x, blockDim.x, false);
@@ -121,7 +121,7 @@ static int bn_stats_impl(const void* x, int dtype, long long M, int C, long long
   if (bn_stats_stream_launch(x, dtype, M, C, cstride, coff, sums, tl, st)) { EGM_LAUNCH_CHECK("bn_stats(stream)"); return EGM_OK; }
   int v = egm_pick_vec(C, cstride, coff);
   int threads = reduce_threads(C, v); size_t sm = (size_t)(threads / (C / v)) * 2 * C * sizeof(float);
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_stats<T, V><<<reduce_blocks(M, threads, C, v), threads, sm, st>>>(
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_bn_stats<T, V>, reduce_blocks(M, threads, C, v), threads, sm, st, 
       StatsF<T, V>{(const T*)x, cstride, coff}, M, C, sums, tl))));
   EGM_LAUNCH_CHECK("bn_stats"); return EGM_OK;
 }
@@ -143,7 +143,7 @@ extern "C" int egm_bn_stats_finalize(const void* x, int dtype, long long M, int 
 // sums [2][C] -> scale/shift/mean/rstd (+ running-stat update).  training=0: use the running stats.
 __global__ void k_bn_finalize(const double* __restrict__ sums, double M, const float* __restrict__ gamma, const float* __restrict__ beta,
                               float* running_mean, float* running_var, long long* nbt, float momentum, float eps, int training, int C,
-                              float* scale, float* shift, float* mean_o, float* rstd_o) {
+                              float* scale, float* shift, float* mean_o, float* rstd_o) { egm_pdl_enter();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && training && nbt) *nbt += 1;
   if (c >= C) return;
@@ -165,7 +165,7 @@ __global__ void k_bn_finalize(const double* __restrict__ sums, double M, const f
 extern "C" int egm_bn_finalize(const double* sums, long long M, const float* gamma, const float* beta, float* running_mean, float* running_var,
                                long long* num_batches_tracked, float momentum, float eps, int training, int C,
                                float* scale, float* shift, float* mean, float* rstd, void* stream) {
-  k_bn_finalize<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, (double)M, gamma, beta, running_mean, running_var, num_batches_tracked,
+  egm_launch(k_bn_finalize, cdiv(C, 128), 128, 0, (cudaStream_t)stream, sums, (double)M, gamma, beta, running_mean, running_var, num_batches_tracked,
                                                                 momentum, eps, training, C, scale, shift, mean, rstd);
   EGM_LAUNCH_CHECK("bn_finalize"); return EGM_OK;
 }
@@ -173,7 +173,7 @@ extern "C" int egm_bn_finalize(const double* sums, long long M, const float* gam
 // ---------------------------------------------------------------- apply (+activation / gate / residual)
 template <typename T, int V>
 __global__ void k_bn_act_fwd(const T* __restrict__ z, long long zcs, long long zco, BnArgs a, const T* __restrict__ aux, T* __restrict__ y,
-                             long long ycs, long long yco, long long M, int CV) {
+                             long long ycs, long long yco, long long M, int CV) { egm_pdl_enter();
   // blockDim.x = CV * rpb: every thread keeps ONE channel vector, so scale/shift are loaded once
   const int rpb = blockDim.x / CV, cv = threadIdx.x % CV, r = threadIdx.x / CV, c = cv * V;
   const FVec<V> sc = ldv<V>(a.scale + c), sh = ldv<V>(a.shift + c);
@@ -205,7 +205,7 @@ extern "C" int egm_bn_act_fwd(const void* z, long long z_cstride, long long z_co
   BnArgs a{scale, shift, nullptr, nullptr, nullptr, act, mode, alpha};
   if (bn_fwd_stream_launch(z, z_cstride, z_coff, a, aux, y, y_cstride, y_coff, dtype, M, C, (cudaStream_t)stream)) { EGM_LAUNCH_CHECK("bn_act_fwd(stream)"); return EGM_OK; }
   const int threads = reduce_threads(C, v);
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_act_fwd<T, V><<<ew_blocks(M, threads, C, V), threads, 0, (cudaStream_t)stream>>>(
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_bn_act_fwd<T, V>, ew_blocks(M, threads, C, V), threads, 0, (cudaStream_t)stream, 
       (const T*)z, z_cstride, z_coff, a, (const T*)aux, (T*)y, y_cstride, y_coff, M, C / V))));
   EGM_LAUNCH_CHECK("bn_act_fwd"); return EGM_OK;
 }
@@ -243,7 +243,7 @@ struct BwdRedF {
   }
 };
 template <typename T, int V>
-__global__ void k_bn_bwd_reduce(BwdRedF<T, V> f, long long M, int C, double* out, BnTail tl) {
+__global__ void k_bn_bwd_reduce(BwdRedF<T, V> f, long long M, int C, double* out, BnTail tl) { egm_pdl_enter();
   extern __shared__ float smem[];
   chan_reduce<V, 2>(f, M, C, out, smem);
   bn_tail_run(tl, out, C, threadIdx.x, blockDim.x, false);
@@ -260,18 +260,18 @@ static int bn_bwd_reduce_impl(const void* dy, long long dy_cstride, long long dy
       if (mode == 0) {
         const size_t smb = bs::ring_bytes<2>(tail);
         static bool attr[64] = {}; egm_ensure_smem(k_bn_bwd_reduce_stream<T, false>, (int)smb, attr);
-        k_bn_bwd_reduce_stream<T, false><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st>>>((const T*)dy, (const T*)z, nullptr, a, M * C, C, sums, tl);
+        egm_launch(k_bn_bwd_reduce_stream<T, false>, bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st, (const T*)dy, (const T*)z, nullptr, a, M * C, C, sums, tl);
       } else {
         const size_t smb = bs::ring_bytes<3>(tail);
         static bool attr[64] = {}; egm_ensure_smem(k_bn_bwd_reduce_stream<T, true>, (int)smb, attr);
-        k_bn_bwd_reduce_stream<T, true><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st>>>((const T*)dy, (const T*)z, (const T*)aux, a, M * C, C, sums, tl);
+        egm_launch(k_bn_bwd_reduce_stream<T, true>, bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st, (const T*)dy, (const T*)z, (const T*)aux, a, M * C, C, sums, tl);
       }
     });
     EGM_LAUNCH_CHECK("bn_act_bwd_reduce(stream)"); return EGM_OK;
   }
   int v = egm_pick_vec(C, dy_cstride, dy_coff); if (v > 4) v = 4;      // 4-wide: fewer live registers -> more warps in flight
   int threads = reduce_threads(C, v); size_t sm = (size_t)(threads / (C / v)) * 2 * C * sizeof(float);
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_bwd_reduce<T, V><<<reduce_blocks(M, threads, C, v), threads, sm, st>>>(
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_bn_bwd_reduce<T, V>, reduce_blocks(M, threads, C, v), threads, sm, st, 
       BwdRedF<T, V>{(const T*)dy, dy_cstride, dy_coff, (const T*)z, (const T*)aux, a, C, {}, {}, {}, {}}, M, C, sums, tl))));
   EGM_LAUNCH_CHECK("bn_act_bwd_reduce"); return EGM_OK;
 }
@@ -294,7 +294,7 @@ extern "C" int egm_bn_act_bwd_reduce_finalize(const void* dy, long long dy_cstri
 
 // sums -> coef[0][c] = gamma*rstd, coef[1][c] = sum(g)/M, coef[2][c] = sum(g*xhat)/M ; dgamma, dbeta
 __global__ void k_bn_bwd_finalize(const double* __restrict__ sums, double M, const float* __restrict__ gamma, const float* __restrict__ rstd, int C,
-                                  float* coef, float* dgamma, float* dbeta, int training) {
+                                  float* coef, float* dgamma, float* dbeta, int training) { egm_pdl_enter();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double sg = sums[c], sgx = sums[C + c];
@@ -306,13 +306,13 @@ __global__ void k_bn_bwd_finalize(const double* __restrict__ sums, double M, con
 }
 extern "C" int egm_bn_bwd_finalize(const double* sums, long long M, const float* gamma, const float* rstd, int C, float* coef, float* dgamma,
                                    float* dbeta, int training, void* stream) {
-  k_bn_bwd_finalize<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, (double)M, gamma, rstd, C, coef, dgamma, dbeta, training);
+  egm_launch(k_bn_bwd_finalize, cdiv(C, 128), 128, 0, (cudaStream_t)stream, sums, (double)M, gamma, rstd, C, coef, dgamma, dbeta, training);
   EGM_LAUNCH_CHECK("bn_bwd_finalize"); return EGM_OK;
 }
 
 template <typename T, int V>
 __global__ void k_bn_bwd_apply(const T* __restrict__ dy, long long dcs, long long dco, const T* __restrict__ z, const T* __restrict__ aux, BnArgs a,
-                               T* __restrict__ dz, T* __restrict__ daux, int daux_acc, long long M, int CV) {
+                               T* __restrict__ dz, T* __restrict__ daux, int daux_acc, long long M, int CV) { egm_pdl_enter();
   const int C = CV * V;
   const int rpb = blockDim.x / CV, cv = threadIdx.x % CV, r = threadIdx.x / CV, c = cv * V;
   const FVec<V> sc = ldv<V>(a.scale + c), sh = ldv<V>(a.shift + c), mu = ldv<V>(a.mean + c), rs = ldv<V>(a.rstd + c),
@@ -343,12 +343,12 @@ extern "C" int egm_bn_act_bwd_apply(const void* dy, long long dy_cstride, long l
       if (mode == 0) {
         const size_t smb = bs::ring_bytes<2>(0);
         static bool attr[64] = {}; egm_ensure_smem(k_bn_bwd_apply_stream<T, false>, (int)smb, attr);
-        k_bn_bwd_apply_stream<T, false><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, (cudaStream_t)stream>>>(
+        egm_launch(k_bn_bwd_apply_stream<T, false>, bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, (cudaStream_t)stream, 
             (const T*)dy, (const T*)z, nullptr, a, (T*)dz, nullptr, 0, M * C, C);
       } else {
         const size_t smb = bs::ring_bytes<3>(0);
         static bool attr[64] = {}; egm_ensure_smem(k_bn_bwd_apply_stream<T, true>, (int)smb, attr);
-        k_bn_bwd_apply_stream<T, true><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, (cudaStream_t)stream>>>(
+        egm_launch(k_bn_bwd_apply_stream<T, true>, bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, (cudaStream_t)stream, 
             (const T*)dy, (const T*)z, (const T*)aux, a, (T*)dz, (T*)daux, daux_accumulate, M * C, C);
       }
     });
@@ -356,7 +356,7 @@ extern "C" int egm_bn_act_bwd_apply(const void* dy, long long dy_cstride, long l
   }
   int v = egm_pick_vec(C, dy_cstride, dy_coff); if (v > 4) v = 4;
   const int threads = reduce_threads(C, v);
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_bn_bwd_apply<T, V><<<ew_blocks(M, threads, C, V), threads, 0, (cudaStream_t)stream>>>(
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_bn_bwd_apply<T, V>, ew_blocks(M, threads, C, V), threads, 0, (cudaStream_t)stream, 
       (const T*)dy, dy_cstride, dy_coff, (const T*)z, (const T*)aux, a, (T*)dz, (T*)daux, daux_accumulate, M, C / V))));
   EGM_LAUNCH_CHECK("bn_act_bwd_apply"); return EGM_OK;
 }
@@ -373,11 +373,11 @@ struct SumF {
   }
 };
 template <typename T, int V>
-__global__ void k_chan_sum(SumF<T, V> f, long long M, int C, double* out) {
+__global__ void k_chan_sum(SumF<T, V> f, long long M, int C, double* out) { egm_pdl_enter();
   extern __shared__ float smem[];
   chan_reduce<V, 1>(f, M, C, out, smem);
 }
-__global__ void k_d2f(const double* s, float* d, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) d[i] = (float)s[i]; }
+__global__ void k_d2f(const double* s, float* d, int n) { egm_pdl_enter(); int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) d[i] = (float)s[i]; }
 extern "C" int egm_channel_sum(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* scratch, float* out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st);
@@ -386,10 +386,10 @@ extern "C" int egm_channel_sum(const void* x, int dtype, long long M, int C, lon
   } else if (M > 0) {
     int v = egm_pick_vec(C, cstride, coff);
     int threads = reduce_threads(C, v); size_t sm = (size_t)(threads / (C / v)) * C * sizeof(float);
-    EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_chan_sum<T, V><<<reduce_blocks(M, threads, C, v), threads, sm, st>>>(
+    EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_chan_sum<T, V>, reduce_blocks(M, threads, C, v), threads, sm, st, 
         SumF<T, V>{(const T*)x, cstride, coff}, M, C, scratch))));
   }
-  k_d2f<<<cdiv(C, 128), 128, 0, st>>>(scratch, out, C);
+  egm_launch(k_d2f, cdiv(C, 128), 128, 0, st, scratch, out, C);
   EGM_LAUNCH_CHECK("channel_sum"); return EGM_OK;
 }
 
@@ -399,10 +399,10 @@ static bool bn_stats_stream_launch(const void* x, int dtype, long long M, int C,
   const size_t smb = bs::ring_bytes<1>(2 * bs::CONSUMERS * bs::V * sizeof(float));
   if (dtype == EGM_F32) {
     static bool attr[64] = {}; egm_ensure_smem(k_bn_stats_stream<float>, (int)smb, attr);
-    k_bn_stats_stream<float><<<bn_stream_grid(M * C, 4), bs::THREADS, smb, st>>>((const float*)x, M * C, C, sums, tl);
+    egm_launch(k_bn_stats_stream<float>, bn_stream_grid(M * C, 4), bs::THREADS, smb, st, (const float*)x, M * C, C, sums, tl);
   } else {
     static bool attr[64] = {}; egm_ensure_smem(k_bn_stats_stream<__nv_bfloat16>, (int)smb, attr);
-    k_bn_stats_stream<__nv_bfloat16><<<bn_stream_grid(M * C, 2), bs::THREADS, smb, st>>>((const __nv_bfloat16*)x, M * C, C, sums, tl);
+    egm_launch(k_bn_stats_stream<__nv_bfloat16>, bn_stream_grid(M * C, 2), bs::THREADS, smb, st, (const __nv_bfloat16*)x, M * C, C, sums, tl);
   }
   return true;
 }
@@ -414,11 +414,11 @@ static bool bn_fwd_stream_launch(const void* z, long long zcs, long long zco, co
     if (a.mode == 0) {
       const size_t smb = bs::ring_bytes<1>(0);
       static bool attr[64] = {}; egm_ensure_smem(k_bn_act_fwd_stream<T, false>, (int)smb, attr);
-      k_bn_act_fwd_stream<T, false><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st>>>((const T*)z, nullptr, a, (T*)y, M * C, C);
+      egm_launch(k_bn_act_fwd_stream<T, false>, bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st, (const T*)z, nullptr, a, (T*)y, M * C, C);
     } else {
       const size_t smb = bs::ring_bytes<2>(0);
       static bool attr[64] = {}; egm_ensure_smem(k_bn_act_fwd_stream<T, true>, (int)smb, attr);
-      k_bn_act_fwd_stream<T, true><<<bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st>>>((const T*)z, (const T*)aux, a, (T*)y, M * C, C);
+      egm_launch(k_bn_act_fwd_stream<T, true>, bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st, (const T*)z, (const T*)aux, a, (T*)y, M * C, C);
     }
   });
   return true;

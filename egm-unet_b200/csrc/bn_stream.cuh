@@ -67,7 +67,7 @@ __device__ __forceinline__ void produce(const Ring& r, const T* const* src, long
 // ------------------------------------------------------------------ sum(g), sum(g*xhat) per channel   (AUX: gate / residual modes read `aux` too)
 template <typename T, bool AUX>
 __global__ void __launch_bounds__(bs::THREADS, 1) k_bn_bwd_reduce_stream(const T* __restrict__ dy, const T* __restrict__ z, const T* __restrict__ aux, BnArgs a,
-                                                                        long long total, int C, double* __restrict__ out, BnTail tl) {
+                                                                        long long total, int C, double* __restrict__ out, BnTail tl) { egm_pdl_enter();
   using namespace bs;
   constexpr int NT = AUX ? 3 : 2;
   extern __shared__ uint8_t smem_raw[];
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(bs::THREADS, 1) k_bn_bwd_reduce_stream(const T
 // ------------------------------------------------------------------ dz = k0 * (g - k1 - xhat*k2)   (AUX: also daux (+)= the gate / residual branch)
 template <typename T, bool AUX>
 __global__ void __launch_bounds__(bs::THREADS, 1) k_bn_bwd_apply_stream(const T* __restrict__ dy, const T* __restrict__ z, const T* __restrict__ aux, BnArgs a,
-                                                                       T* __restrict__ dz, T* __restrict__ daux, int daux_acc, long long total, int C) {
+                                                                       T* __restrict__ dz, T* __restrict__ daux, int daux_acc, long long total, int C) { egm_pdl_enter();
   using namespace bs;
   constexpr int NT = AUX ? 3 : 2;
   extern __shared__ uint8_t smem_raw[];
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(bs::THREADS, 1) k_bn_bwd_apply_stream(const T*
 
 // ------------------------------------------------------------------ forward statistics sum(x), sum(x^2) per channel
 template <typename T>
-__global__ void __launch_bounds__(bs::THREADS, 1) k_bn_stats_stream(const T* __restrict__ x, long long total, int C, double* __restrict__ out, BnTail tl) {
+__global__ void __launch_bounds__(bs::THREADS, 1) k_bn_stats_stream(const T* __restrict__ x, long long total, int C, double* __restrict__ out, BnTail tl) { egm_pdl_enter();
   using namespace bs;
   extern __shared__ uint8_t smem_raw[];
   float* red;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(bs::THREADS, 1) k_bn_stats_stream(const T* __r
 // ------------------------------------------------------------------ y = act(z*scale + shift) | gate | residual   (dense in and out)
 template <typename T, bool AUX>
 __global__ void __launch_bounds__(bs::THREADS, 1) k_bn_act_fwd_stream(const T* __restrict__ z, const T* __restrict__ aux, BnArgs a, T* __restrict__ y,
-                                                                     long long total, int C) {
+                                                                     long long total, int C) { egm_pdl_enter();
   using namespace bs;
   constexpr int NT = AUX ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];

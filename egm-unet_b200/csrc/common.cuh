@@ -42,6 +42,38 @@ static inline void egm_ensure_smem(K kernel, int bytes, bool (&done)[64]) {
   int dev = 0; cudaGetDevice(&dev); dev &= 63;
   if (!done[dev]) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); done[dev] = true; }
 }
+// ---------------------------------------------------------------- launches with programmatic dependent launch (PDL)
+// A training step is ~820 dependent kernels, most of them 5-30 us long: with plain stream order every boundary pays the full
+// "last CTA retires -> grid completes -> next grid is scheduled -> its CTAs start up" latency, and the last partial wave of a grid
+// leaves SMs idle.  Every kernel of this library therefore (a) starts with egm_pdl_enter(): it lets the NEXT grid of the stream be
+// scheduled as soon as all CTAs of this one have started (so its CTAs fill the SMs this grid's tail frees and run their start-up),
+// then waits until the PREVIOUS grid has completed and its memory is visible before touching anything; and (b) is launched through
+// egm_launch() with cudaLaunchAttributeProgrammaticStreamSerialization.  Because every kernel executes the wait before its first
+// global access, "kernel k+1 complete" still implies "kernel k complete": ordering is transitive and results are unchanged.
+// Stream capture turns these into programmatic edges of the CUDA graph.  egm_set_launch_overlap(0) / EGM_NO_PDL=1 launch with plain
+// stream order (the A/B switch of bench.py --no-pdl).
+#ifndef EGM_PDL_MODE
+#define EGM_PDL_MODE 2      // 2: early trigger + wait; 1: wait only (successor scheduled when this grid's CTAs exit); 0: no PDL instructions
+#endif
+__device__ __forceinline__ void egm_pdl_enter() {
+#if EGM_PDL_MODE >= 2
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+#if EGM_PDL_MODE >= 1
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+int egm_launch_overlap_enabled();
+template <typename... P, typename... A>
+static inline void egm_launch(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = egm_launch_overlap_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------- dtype dispatch

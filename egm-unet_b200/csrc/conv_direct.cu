@@ -16,7 +16,7 @@ struct ConvGeom {
 
 template <typename T, int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(256) k_conv_tiled(const T* __restrict__ x, const float* __restrict__ wf, const float* __restrict__ bias,
-                                                    T* __restrict__ y, ConvGeom g, int accumulate) {
+                                                    T* __restrict__ y, ConvGeom g, int accumulate) { egm_pdl_enter();
   constexpr int BK = 16;
   constexpr int NJ = BM / 16;
   __shared__ float As[BK][BM + 1];
@@ -106,16 +106,16 @@ static int launch_conv_tiled(const T* x, const float* wf, const float* bias, T* 
   int cg = g.Cout_g;
   if (cg > 32) {
     dim3 grid(cdiv(M, 64), cdiv(cg, 64), g.groups);
-    k_conv_tiled<T, 64, 64, 4, 4><<<grid, 256, 0, st>>>(x, wf, bias, y, g, accumulate);
+    egm_launch(k_conv_tiled<T, 64, 64, 4, 4>, grid, 256, 0, st, x, wf, bias, y, g, accumulate);
   } else if (cg > 16) {
     dim3 grid(cdiv(M, 64), 1, g.groups);
-    k_conv_tiled<T, 64, 32, 4, 2><<<grid, 256, 0, st>>>(x, wf, bias, y, g, accumulate);
+    egm_launch(k_conv_tiled<T, 64, 32, 4, 2>, grid, 256, 0, st, x, wf, bias, y, g, accumulate);
   } else if (cg > 8) {
     dim3 grid(cdiv(M, 128), 1, g.groups);
-    k_conv_tiled<T, 128, 16, 4, 2><<<grid, 256, 0, st>>>(x, wf, bias, y, g, accumulate);
+    egm_launch(k_conv_tiled<T, 128, 16, 4, 2>, grid, 256, 0, st, x, wf, bias, y, g, accumulate);
   } else {
     dim3 grid(cdiv(M, 128), 1, g.groups);
-    k_conv_tiled<T, 128, 8, 4, 1><<<grid, 256, 0, st>>>(x, wf, bias, y, g, accumulate);
+    egm_launch(k_conv_tiled<T, 128, 8, 4, 1>, grid, 256, 0, st, x, wf, bias, y, g, accumulate);
   }
   return egm_check_launch("conv_tiled");
 }
@@ -135,7 +135,7 @@ extern "C" int egm_conv2d_direct(const void* x, long long x_cstride, long long x
 // dwf[t][ci][co] (+)= sum_m x[m+off(t), g*Cin_g+ci] * dy[m, g*Cout_g+co]; split over m with fp32 atomics.
 template <typename T, int BN, int TN>
 __global__ void __launch_bounds__(256) k_conv_wgrad_tiled(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dwf, ConvGeom g,
-                                                          int ktiles, int splits, long long m_per_split) {
+                                                          int ktiles, int splits, long long m_per_split) { egm_pdl_enter();
   constexpr int BKT = 64, BMC = 16, TK = 4;
   __shared__ float As[BMC][BKT + 1];
   __shared__ float Bs[BMC][BN];
@@ -245,16 +245,16 @@ extern "C" int egm_conv2d_wgrad_direct(const void* x, long long x_cstride, long 
   splits = (int)((M + mps - 1) / mps);
   dim3 grid(ktiles * splits, ntiles, groups);
   EGM_DISPATCH_DTYPE(dtype, {
-    if (BN == 64) k_conv_wgrad_tiled<T, 64, 4><<<grid, 256, 0, st>>>((const T*)x, (const T*)dy, dw_packed, g, ktiles, splits, mps);
-    else if (BN == 32) k_conv_wgrad_tiled<T, 32, 2><<<grid, 256, 0, st>>>((const T*)x, (const T*)dy, dw_packed, g, ktiles, splits, mps);
-    else k_conv_wgrad_tiled<T, 16, 1><<<grid, 256, 0, st>>>((const T*)x, (const T*)dy, dw_packed, g, ktiles, splits, mps);
+    if (BN == 64) egm_launch(k_conv_wgrad_tiled<T, 64, 4>, grid, 256, 0, st, (const T*)x, (const T*)dy, dw_packed, g, ktiles, splits, mps);
+    else if (BN == 32) egm_launch(k_conv_wgrad_tiled<T, 32, 2>, grid, 256, 0, st, (const T*)x, (const T*)dy, dw_packed, g, ktiles, splits, mps);
+    else egm_launch(k_conv_wgrad_tiled<T, 16, 1>, grid, 256, 0, st, (const T*)x, (const T*)dy, dw_packed, g, ktiles, splits, mps);
   });
   EGM_LAUNCH_CHECK("conv_wgrad_tiled"); return EGM_OK;
 }
 
 // ------------------------------------------------------------------ weight packing / unpacking
 // w [Cout][Cin_g][kh][kw] fp32 (reference layout) -> wf [taps][Cin_g][Cout], wd [taps][Cout_g][Cin] (flipped taps); either may be null.
-__global__ void k_pack_w(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wd, int Cout, int Cin_g, int kh, int kw, int groups) {
+__global__ void k_pack_w(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wd, int Cout, int Cin_g, int kh, int kw, int groups) { egm_pdl_enter();
   int taps = kh * kw, Cout_g = Cout / groups, Cin = Cin_g * groups;
   long long total = (long long)Cout * Cin_g * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -268,11 +268,11 @@ __global__ void k_pack_w(const float* __restrict__ w, float* __restrict__ wf, fl
 extern "C" int egm_pack_conv_weight(const float* w, float* wf, float* wd, int Cout, int Cin_g, int kh, int kw, int groups, void* stream) {
   long long total = (long long)Cout * Cin_g * kh * kw;
   if (total == 0) return EGM_OK;
-  k_pack_w<<<egm_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, wf, wd, Cout, Cin_g, kh, kw, groups);
+  egm_launch(k_pack_w, egm_grid_for(total, 256), 256, 0, (cudaStream_t)stream, w, wf, wd, Cout, Cin_g, kh, kw, groups);
   EGM_LAUNCH_CHECK("pack_conv_weight"); return EGM_OK;
 }
 // dwf [taps][Cin_g][Cout] -> dw [Cout][Cin_g][kh][kw]  (dw = beta*dw + dwf^T)
-__global__ void k_unpack_dw(const float* __restrict__ dwf, float* __restrict__ dw, int Cout, int Cin_g, int taps, float beta) {
+__global__ void k_unpack_dw(const float* __restrict__ dwf, float* __restrict__ dw, int Cout, int Cin_g, int taps, float beta) { egm_pdl_enter();
   long long total = (long long)Cout * Cin_g * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int t = (int)(i % taps); long long q = i / taps; int ci = (int)(q % Cin_g); int co = (int)(q / Cin_g);
@@ -283,12 +283,12 @@ __global__ void k_unpack_dw(const float* __restrict__ dwf, float* __restrict__ d
 extern "C" int egm_unpack_conv_wgrad(const float* dw_packed, float* dw, int Cout, int Cin_g, int kh, int kw, float beta, void* stream) {
   long long total = (long long)Cout * Cin_g * kh * kw;
   if (total == 0) return EGM_OK;
-  k_unpack_dw<<<egm_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dw_packed, dw, Cout, Cin_g, kh * kw, beta);
+  egm_launch(k_unpack_dw, egm_grid_for(total, 256), 256, 0, (cudaStream_t)stream, dw_packed, dw, Cout, Cin_g, kh * kw, beta);
   EGM_LAUNCH_CHECK("unpack_conv_wgrad"); return EGM_OK;
 }
 
 // Embed a [Co][Ci][ks][ks] kernel into the centre of a [Co][Ci][kb][kb] one (big (+)= small), or crop back (small = centre(big)).
-__global__ void k_embed(float* big, float* small_, long long CoCi, int kb, int ks, int mode, int accumulate) {
+__global__ void k_embed(float* big, float* small_, long long CoCi, int kb, int ks, int mode, int accumulate) { egm_pdl_enter();
   long long total = CoCi * ks * ks; int o = (kb - ks) / 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int s = (int)(i % ks); long long q = i / ks; int r = (int)(q % ks); long long cc = q / ks;
@@ -300,14 +300,46 @@ __global__ void k_embed(float* big, float* small_, long long CoCi, int kb, int k
 extern "C" int egm_kernel_embed(float* big, float* small_, long long CoCi, int kb, int ks, int mode, int accumulate, void* stream) {
   long long total = CoCi * ks * ks;
   if (total == 0) return EGM_OK;
-  k_embed<<<egm_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(big, small_, CoCi, kb, ks, mode, accumulate);
+  egm_launch(k_embed, egm_grid_for(total, 256), 256, 0, (cudaStream_t)stream, big, small_, CoCi, kb, ks, mode, accumulate);
   EGM_LAUNCH_CHECK("kernel_embed"); return EGM_OK;
+}
+
+// EdgeAwareFeatureEnhancer (src/EGM-UNet.py:872-886): conv1x1(x - AvgPool2d(3, 1, 1)(x)).  AvgPool2d with count_include_pad divides by 9
+// everywhere, i.e. x - avg3(x) IS a zero-padded depthwise 3x3 filter k = delta - 1/9, so high-pass + 1x1 conv == ONE dense 3x3 conv with
+// W3[co][ci][t] = W1[co][ci] * k[t].  That conv runs on the tcgen05 halo kernel (the smem-staged halo tile feeds the MMAs directly, BN
+// statistics in its epilogue); the high-pass tensor and both of its HBM round trips (forward and transposed backward) disappear.
+//   mode 0: w3 <- w1.  round_bf16: the off-centre weight is wn = bf16(-w1/9) and the centre is -8*wn (exact in bf16), so the bf16 operand
+//           is EXACTLY W1' (x - avg3 x) with W1' = -9*wn within bf16 rounding of W1 -- a constant input still maps to exactly zero.
+//   mode 1: dw1 <- sum_t k[t] * dw3[co][ci][t]   (gradient of the composition)
+__device__ __forceinline__ float hp_tap(float w1, int t, int round_bf16) {
+  float wn = -w1 * (1.f / 9.f);
+  if (round_bf16) wn = __bfloat162float(__float2bfloat16_rn(wn));
+  return t == 4 ? -8.f * wn : wn;
+}
+__global__ void k_highpass_compose(float* __restrict__ w1, float* __restrict__ w3, long long CoCi, int mode, int round_bf16) { egm_pdl_enter();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < CoCi; i += (long long)gridDim.x * blockDim.x) {
+    if (mode == 0) {
+      const float w = w1[i];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) w3[i * 9 + t] = hp_tap(w, t, round_bf16);
+    } else {
+      float s = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) s += w3[i * 9 + t] * (t == 4 ? 8.f / 9.f : -1.f / 9.f);
+      w1[i] = s;
+    }
+  }
+}
+extern "C" int egm_highpass_compose(float* w1, float* w3, long long CoCi, int mode, int round_bf16, void* stream) {
+  if (CoCi == 0) return EGM_OK;
+  egm_launch(k_highpass_compose, egm_grid_for(CoCi, 256), 256, 0, (cudaStream_t)stream, w1, w3, CoCi, mode, round_bf16);
+  EGM_LAUNCH_CHECK("highpass_compose"); return EGM_OK;
 }
 
 // Lift a (possibly grouped, possibly thin) conv weight to a dense zero-padded one so it can run on the tcgen05 path:
 //   mode 0: wp[CoutP][CinP][taps] (zeroed here) <- w[Cout][Cin_g][taps] placed on the block diagonal (ci = group*Cin_g + cil)
 //   mode 1: w <- the same entries read back out of wp (gradient extraction)
-__global__ void k_weight_lift(float* __restrict__ w, float* __restrict__ wp, int Cout, int Cin_g, int groups, int taps, int CinP, int mode) {
+__global__ void k_weight_lift(float* __restrict__ w, float* __restrict__ wp, int Cout, int Cin_g, int groups, int taps, int CinP, int mode) { egm_pdl_enter();
   const int Cout_g = Cout / groups;
   long long total = (long long)Cout * Cin_g * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -322,6 +354,6 @@ extern "C" int egm_conv_weight_lift(float* w, float* wp, int Cout, int Cin_g, in
   if (mode == 0) cudaMemsetAsync(wp, 0, sizeof(float) * (size_t)CoutP * CinP * taps, st);
   long long total = (long long)Cout * Cin_g * taps;
   if (total == 0) return EGM_OK;
-  k_weight_lift<<<egm_grid_for(total, 256), 256, 0, st>>>(w, wp, Cout, Cin_g, groups, taps, CinP, mode);
+  egm_launch(k_weight_lift, egm_grid_for(total, 256), 256, 0, st, w, wp, Cout, Cin_g, groups, taps, CinP, mode);
   EGM_LAUNCH_CHECK("conv_weight_lift"); return EGM_OK;
 }

@@ -159,7 +159,9 @@ __device__ __forceinline__ void stats_accum16(float (&s1)[NC], float (&s2)[NC], 
 }
 // red: shared [4 warps][2][NC] floats; out: global [2][cvalid] doubles (atomically accumulated); ew = epilogue warp 0..3
 template <int NC>
-__device__ __forceinline__ void stats_flush(const float (&s1)[NC], const float (&s2)[NC], float* red, double* __restrict__ out, int cvalid, int ew, int lane) {
+__device__ __forceinline__ void stats_flush(const float (&s1)[NC], const float (&s2)[NC], float* red, double* __restrict__ out, int cvalid, int ew, int lane,
+                                            int group = 0) {
+  red += group * 8 * NC;                                 // each epilogue group of 4 warps reduces on its own (named barrier 1 + group)
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     float a = s1[c], b = s2[c];
@@ -167,7 +169,7 @@ __device__ __forceinline__ void stats_flush(const float (&s1)[NC], const float (
     for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
     if (lane == 0) { red[ew * 2 * NC + c] = a; red[ew * 2 * NC + NC + c] = b; }
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
   for (int i = ew * 32 + lane; i < 2 * NC; i += 128) {
     const int k = i / NC, c = i - k * NC;
     if (c < cvalid) atomicAdd(out + (long long)k * cvalid + c, (double)red[i] + (double)red[2 * NC + i] + (double)red[4 * NC + i] + (double)red[6 * NC + i]);
@@ -253,6 +255,30 @@ static int make_map_w(CUtensorMap* tm, const void* ptr, int taps, int Cout, int 
   return EGM_OK;
 }
 
+// Persistent CTAs visit tile = blockIdx.x + k * gridDim.x.  Decomposing every tile index into (image, tile row, tile column, Cout slice)
+// costs three integer divisions (~100 dependent instructions) per tile in EVERY role warp -- on the thin layers, whose tile needs one
+// MMA, that was a third of the epilogue's per-tile critical path (ncu source view: the IABS/MUFU.RCP division sequences right behind
+// the accumulator wait).  The walk below divides once and then advances by the constant stride with carries.
+struct TileWalk {
+  int n, th, tw, ck;            // image, tile row, tile column, Cout slice
+  int dn, dth, dtw, dck;        // the grid stride in the same mixed radix
+  __device__ __forceinline__ TileWalk(int tile0, int step, int tilesH, int tilesW, int chunks) {
+    split(tile0, tilesH, tilesW, chunks, n, th, tw, ck);
+    split(step, tilesH, tilesW, chunks, dn, dth, dtw, dck);
+  }
+  static __device__ __forceinline__ void split(int t, int tilesH, int tilesW, int chunks, int& a, int& b, int& c, int& d) {
+    d = t % chunks; t /= chunks;
+    c = t % tilesW; t /= tilesW;
+    b = t % tilesH; a = t / tilesH;
+  }
+  __device__ __forceinline__ void next(int tilesH, int tilesW, int chunks) {
+    ck += dck; tw += dtw; th += dth; n += dn;
+    if (ck >= chunks) { ck -= chunks; ++tw; }
+    if (tw >= tilesW) { tw -= tilesW; ++th; }
+    if (th >= tilesH) { th -= tilesH; ++n; }
+  }
+};
+
 constexpr int TILE_H = 8, TILE_W = 16, TILE_PIX = 128;
 constexpr int TC_THREADS = 192;
 
@@ -280,9 +306,9 @@ __device__ __forceinline__ void issue_group(uint32_t d, uint64_t ad, uint64_t bd
   }
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                                                          __nv_bfloat16* __restrict__ y, const float* __restrict__ bias, ConvTcParams p) {
+template <int EPI, int NG>      // NG epilogue groups, see k_conv_tc_halo
+__global__ void __launch_bounds__(64 + 128 * NG, 1) k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                                                          __nv_bfloat16* __restrict__ y, const float* __restrict__ bias, ConvTcParams p) { egm_pdl_enter();
   constexpr bool RELU = EPI == EPI_RELU;
   constexpr int NSTAT = EPI >= 16 ? EPI : 1;
   extern __shared__ uint8_t smem_raw[];
@@ -303,7 +329,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }       // tempty: one arrival per epilogue WARP
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -324,10 +350,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     }
     const uint32_t txBytes = (uint32_t)p.aBytes + (p.wres ? 0u : bBytes);
     int s = 0; uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
-      const int chunk = tile % p.coChunks, sp_t = tile / p.coChunks;
-      const int n = sp_t / tilesPerImg, r = sp_t - n * tilesPerImg;
-      const int h0 = (r / p.tilesW) * TILE_H, w0 = (r % p.tilesW) * TILE_W, co0 = chunk * p.nChunk;
+    TileWalk tw_(blockIdx.x, gridDim.x, p.tilesH, p.tilesW, p.coChunks);
+    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x, tw_.next(p.tilesH, p.tilesW, p.coChunks)) {
+      const int n = tw_.n;
+      const int h0 = tw_.th * TILE_H, w0 = tw_.tw * TILE_W, co0 = tw_.ck * p.nChunk;
       if (p.kps == 9) {
         // thin 3x3 layer: the per-tap loop below costs ~150 dependent instructions per tap in this single warp (ncu: the producer
         // was the busiest warp) -- here one wait, one expect_tx and nine back-to-back TMA issues with compile-time tap offsets
@@ -407,15 +433,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     }
   } else {
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;                     // epilogue group: tiles grp, grp + NG, ... of this CTA
     const int row = q * 32 + lane;                       // pixel index inside the 8x16 patch
-    int acc = 0; uint32_t aph = 0;
+    int acc = grp; uint32_t aph = 0;                     // two accumulator buffers: with NG == 2 each group owns one
     float s1[NSTAT], s2[NSTAT];
 #pragma unroll
     for (int c = 0; c < NSTAT; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
-    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
-      const int chunk = tile % p.coChunks, sp_t = tile / p.coChunks;
-      const int n = sp_t / tilesPerImg, r = sp_t - n * tilesPerImg;
-      const int h = (r / p.tilesW) * TILE_H + row / TILE_W, w = (r % p.tilesW) * TILE_W + row % TILE_W;
+    TileWalk tw_(blockIdx.x + grp * gridDim.x, NG * gridDim.x, p.tilesH, p.tilesW, p.coChunks);
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.numTiles; tile += NG * gridDim.x, tw_.next(p.tilesH, p.tilesW, p.coChunks)) {
+      const int chunk = tw_.ck, n = tw_.n;
+      const int h = tw_.th * TILE_H + row / TILE_W, w = tw_.tw * TILE_W + row % TILE_W;
       const bool valid = h < p.H && w < p.W;
       __nv_bfloat16* yp = y + (((long long)n * p.H + h) * p.W + w) * p.out.cs + p.out.coff + chunk * p.nChunk;
       const float* bp = bias ? bias + chunk * p.nChunk : nullptr;
@@ -461,10 +488,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);
-      if (++acc == 2) { acc = 0; aph ^= 1; }
+      __syncwarp();                                      // every lane's tcgen05.ld has retired (wait::ld above) before the warp releases the accumulator
+      if (lane == 0) mbar_arrive(&tempty[acc]);          // 4 arrivals per tile instead of 128 serialised shared-memory atomics
+      acc += NG; if (acc >= 2) { acc -= 2; aph ^= 1; }
     }
-    if constexpr (EPI >= 16) stats_flush<NSTAT>(s1, s2, (float*)(tmem_slot + 4), p.stats, p.out.valid, q, lane);
+    if constexpr (EPI >= 16) stats_flush<NSTAT>(s1, s2, (float*)(tmem_slot + 4), p.stats, p.out.valid, q, lane, grp);
   }
   tc_fence_before();
   __syncthreads();
@@ -501,9 +529,14 @@ constexpr int HT_H = 16, HT_W = 8;
 #define EGM_EXPBIT(b) (0)
 #endif
 
-template <int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                                                               __nv_bfloat16* __restrict__ y, const float* __restrict__ bias, ConvHaloParams p) {
+// NG = epilogue warp GROUPS (4 warps each = the four TMEM lane quarters).  The epilogue of a tile is one dependent chain per warp
+// (accumulator wait -> tcgen05.ld -> convert -> store -> release: ~115 instructions at ~8 cycles each, ncu source view of the
+// 16->16 1x1 layer: the four epilogue warps were busy 80 % of the time while the TMA and MMA warps idled), so thin layers -- one to
+// nine MMAs per tile -- were bound by it.  With NG groups, group g takes the tiles g, g + NG, ... of its CTA (accumulator buffers
+// are handed out round-robin, so consecutive tiles are in different buffers anyway) and NG epilogues overlap.
+template <int EPI, int NG>
+__global__ void __launch_bounds__(64 + 128 * NG, 1) k_conv_tc_halo(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                                                               __nv_bfloat16* __restrict__ y, const float* __restrict__ bias, ConvHaloParams p) { egm_pdl_enter();
   constexpr bool RELU = EPI == EPI_RELU;
   constexpr int NSTAT = EPI >= 16 ? EPI : 1;
   extern __shared__ uint8_t smem_raw[];
@@ -521,7 +554,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < p.nacc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    for (int i = 0; i < p.nacc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }  // tempty: one arrival per epilogue WARP
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -538,11 +571,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
       mbar_expect_tx(wfull, (uint32_t)(taps * p.Cout * p.rowB));
       for (int t = 0; t < taps; ++t) tma_load_3d(sW + (size_t)t * p.wTapStride, &tmW, wfull, 0, 0, t);
     }
-    const int tilesPerImg = p.tilesH * p.tilesW;
     int s = 0; uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
-      const int n = tile / tilesPerImg, r = tile - n * tilesPerImg;
-      const int h0 = (r / p.tilesW) * HT_H, w0 = (r % p.tilesW) * HT_W;
+    TileWalk tw_(blockIdx.x, gridDim.x, p.tilesH, p.tilesW, 1);
+    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x, tw_.next(p.tilesH, p.tilesW, 1)) {
+      const int n = tw_.n;
+      const int h0 = tw_.th * HT_H, w0 = tw_.tw * HT_W;
       mbar_wait(&empty[s], ph ^ 1);
       if (leader) {
         if (EGM_EXPBIT(8)) mbar_arrive(&full[s]);
@@ -662,14 +695,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
     }
   } else {
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;                     // epilogue group: tiles grp, grp + NG, ... of this CTA
     const int row = q * 32 + lane;                       // pixel index inside the 16x8 patch (row-major, 8 wide)
-    int acc = 0; uint32_t aph = 0;
+    int acc = grp; uint32_t aph = 0;                     // p.nacc >= NG (host), so the first NG tiles sit in buffers 0 .. NG-1
     float s1[NSTAT], s2[NSTAT];
 #pragma unroll
     for (int c = 0; c < NSTAT; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
-    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
-      int n = tile / (p.tilesH * p.tilesW); int r = tile - n * p.tilesH * p.tilesW;
-      int h = (r / p.tilesW) * HT_H + row / HT_W, w = (r % p.tilesW) * HT_W + row % HT_W;
+    TileWalk tw_(blockIdx.x + grp * gridDim.x, NG * gridDim.x, p.tilesH, p.tilesW, 1);
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.numTiles; tile += NG * gridDim.x, tw_.next(p.tilesH, p.tilesW, 1)) {
+      const int n = tw_.n;
+      const int h = tw_.th * HT_H + row / HT_W, w = tw_.tw * HT_W + row % HT_W;
       const bool valid = h < p.H && w < p.W;
       __nv_bfloat16* yp = y + (((long long)n * p.H + h) * p.W + w) * p.out.cs + p.out.coff;
       const int nv = p.out.valid, cend = nv < p.Cout ? nv : p.Cout;
@@ -713,10 +748,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);
-      if (++acc == p.nacc) { acc = 0; aph ^= 1; }
+      __syncwarp();                                      // every lane's tcgen05.ld has retired (wait::ld above) before the warp releases the accumulator
+      if (lane == 0) mbar_arrive(&tempty[acc]);          // 4 arrivals per tile instead of 128 serialised shared-memory atomics
+      acc += NG; if (acc >= p.nacc) { acc -= p.nacc; aph ^= 1; }
     }
-    if constexpr (EPI >= 16) stats_flush<NSTAT>(s1, s2, (float*)(tmem_slot + 4), p.stats, p.out.valid, q, lane);
+    if constexpr (EPI >= 16) stats_flush<NSTAT>(s1, s2, (float*)(tmem_slot + 4), p.stats, p.out.valid, q, lane, grp);
   }
   tc_fence_before();
   __syncthreads();
@@ -743,7 +779,9 @@ static int launch_conv_halo(const NhwcView& xv, const void* wpk, const float* bi
   p.haloBytes = p.haloW * p.haloH * p.rowB; p.haloStride = (p.haloBytes + 1023) / 1024 * 1024;
   p.wTapStride = (Cout * p.rowB + 1023) / 1024 * 1024;
   size_t wres = (size_t)kh * kw * p.wTapStride;
-  p.stages = (int)((198 * 1024 - wres) / p.haloStride); if (p.stages > 8) p.stages = 8; if (p.stages < 2) p.stages = 2;
+  static int stage_cap = 0;                          // tuning knob (EGM_HALO_STAGES, read once): ring depth cap; the barrier block holds up to 32 stages
+  if (!stage_cap) { const char* e = getenv("EGM_HALO_STAGES"); stage_cap = e ? atoi(e) : 8; if (stage_cap < 2 || stage_cap > 32) stage_cap = 8; }
+  p.stages = (int)((198 * 1024 - wres) / p.haloStride); if (p.stages > stage_cap) p.stages = stage_cap; if (p.stages < 2) p.stages = 2;
   p.accCols = (Cout + 31) / 32 * 32;
   p.nacc = 512 / p.accCols; if (p.nacc > 8) p.nacc = 8; if (p.nacc < 2) p.nacc = 2;
   p.exp = 0;
@@ -755,18 +793,25 @@ static int launch_conv_halo(const NhwcView& xv, const void* wpk, const float* bi
   p.out = ov;
   int e = make_map_nhwc(&tmX, xv, N, H, W, p.rowB / 2, p.haloW, p.haloH); if (e) return e;
   e = make_map_w(&tmW, wpk, kh * kw, Cout, Cin, p.rowB / 2, Cout); if (e) return e;
-  size_t smem = wres + (size_t)p.stages * p.haloStride + 1024 + 1408 + (epi >= 16 ? 2048 : 0);
+  size_t smem = wres + (size_t)p.stages * p.haloStride + 1024 + 1408 + (epi >= 16 ? 2 * 2048 : 0);
   int grid = p.numTiles < egm_num_sms() ? p.numTiles : egm_num_sms();
   p.stats = stats;
-#define EGM_LAUNCH_HALO(E)                                                                                 \
+  // two epilogue groups wherever the register file allows (320 threads x <= 204 registers); the 64-channel statistics epilogue keeps
+  // 128 running sums per thread and stays at one group.  EGM_EPI_GROUPS=1 forces one group (A/B measurements).
+  static int ng_max = 0;
+  if (!ng_max) { const char* e = getenv("EGM_EPI_GROUPS"); ng_max = e ? atoi(e) : 2; if (ng_max < 1 || ng_max > 2) ng_max = 2; }
+  const int ng = (epi == 64 || p.nacc < 2) ? 1 : ng_max;
+#define EGM_LAUNCH_HALO_(E, G)                                                                             \
   {                                                                                                        \
     static bool attr_set[64] = {};                                                                         \
-    egm_ensure_smem(k_conv_tc_halo<E>, 227 * 1024, attr_set);                                              \
-    k_conv_tc_halo<E><<<grid, TC_THREADS, smem, st>>>(tmX, tmW, (__nv_bfloat16*)y, bias, p);               \
+    egm_ensure_smem(k_conv_tc_halo<E, G>, 227 * 1024, attr_set);                                           \
+    egm_launch(k_conv_tc_halo<E, G>, grid, 64 + 128 * G, smem, st, tmX, tmW, (__nv_bfloat16*)y, bias, p);  \
   }
+#define EGM_LAUNCH_HALO(E) { if (ng == 2) EGM_LAUNCH_HALO_(E, 2) else EGM_LAUNCH_HALO_(E, 1) }
   if (epi == EPI_PLAIN) EGM_LAUNCH_HALO(EPI_PLAIN) else if (epi == EPI_RELU) EGM_LAUNCH_HALO(EPI_RELU)
-  else if (epi == 16) EGM_LAUNCH_HALO(16) else if (epi == 32) EGM_LAUNCH_HALO(32) else EGM_LAUNCH_HALO(64)
+  else if (epi == 16) EGM_LAUNCH_HALO(16) else if (epi == 32) EGM_LAUNCH_HALO(32) else EGM_LAUNCH_HALO_(64, 1)
 #undef EGM_LAUNCH_HALO
+#undef EGM_LAUNCH_HALO_
   return egm_check_launch("conv2d_tc_halo");
 }
 
@@ -832,18 +877,23 @@ extern "C" int egm_conv2d_tc_ex(const void* x, long long x_cstride, long long x_
   p.out = ov;
   int e = make_map_nhwc(&tmX, xv, N, H, W, p.bkc, TILE_W, TILE_H); if (e) return e;
   e = make_map_w(&tmW, w_packed_bf16, kh * kw, Cout, Cin, p.bkc, p.nChunk); if (e) return e;
-  size_t smem = (size_t)p.stages * per + (p.wres ? (size_t)wresBytes : 0) + 1024 + 1024 + (epi >= 16 ? 2048 : 0);
+  size_t smem = (size_t)p.stages * per + (p.wres ? (size_t)wresBytes : 0) + 1024 + 1024 + (epi >= 16 ? 2 * 2048 : 0);
   int grid = p.numTiles < egm_num_sms() ? p.numTiles : egm_num_sms();
   p.stats = stats;
-#define EGM_LAUNCH_TC(E)                                                                                          \
+  static int ng_max = 0;                              // epilogue groups (see k_conv_tc_halo); EGM_EPI_GROUPS=1 forces one
+  if (!ng_max) { const char* e = getenv("EGM_EPI_GROUPS"); ng_max = e ? atoi(e) : 2; if (ng_max < 1 || ng_max > 2) ng_max = 2; }
+  const int ng = epi == 64 ? 1 : ng_max;
+#define EGM_LAUNCH_TC_(E, G)                                                                                      \
   {                                                                                                               \
     static bool attr_set[64] = {};                                                                                \
-    egm_ensure_smem(k_conv_tc<E>, 227 * 1024, attr_set);                                                          \
-    k_conv_tc<E><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmX, tmW, (__nv_bfloat16*)y, bias, p);         \
+    egm_ensure_smem(k_conv_tc<E, G>, 227 * 1024, attr_set);                                                       \
+    egm_launch(k_conv_tc<E, G>, grid, 64 + 128 * G, smem, (cudaStream_t)stream, tmX, tmW, (__nv_bfloat16*)y, bias, p);  \
   }
+#define EGM_LAUNCH_TC(E) { if (ng == 2) EGM_LAUNCH_TC_(E, 2) else EGM_LAUNCH_TC_(E, 1) }
   if (epi == EPI_PLAIN) EGM_LAUNCH_TC(EPI_PLAIN) else if (epi == EPI_RELU) EGM_LAUNCH_TC(EPI_RELU)
-  else if (epi == 16) EGM_LAUNCH_TC(16) else if (epi == 32) EGM_LAUNCH_TC(32) else EGM_LAUNCH_TC(64)
+  else if (epi == 16) EGM_LAUNCH_TC(16) else if (epi == 32) EGM_LAUNCH_TC(32) else EGM_LAUNCH_TC_(64, 1)
 #undef EGM_LAUNCH_TC
+#undef EGM_LAUNCH_TC_
   EGM_LAUNCH_CHECK("conv2d_tc"); return EGM_OK;
 }
 extern "C" int egm_conv2d_tc_view(const void* x, long long x_cstride, long long x_coff, int cin_valid, const void* w_packed_bf16, const float* bias,
@@ -858,7 +908,7 @@ extern "C" int egm_conv2d_tc(const void* x, const void* w_packed_bf16, const flo
 }
 
 // weights fp32 [Cout][Cin][kh][kw] -> bf16 wf [taps][Cout][Cin] (forward) and wd [taps_flipped][Cin][Cout] (dgrad: roles swapped)
-__global__ void k_pack_w_tc(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int taps) {
+__global__ void k_pack_w_tc(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int taps) { egm_pdl_enter();
   long long total = (long long)Cout * Cin * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int t = (int)(i % taps); long long q = i / taps; int ci = (int)(q % Cin); int co = (int)(q / Cin);
@@ -870,7 +920,7 @@ __global__ void k_pack_w_tc(const float* __restrict__ w, __nv_bfloat16* __restri
 extern "C" int egm_pack_conv_weight_tc(const float* w, void* wf_bf16, void* wd_bf16, int Cout, int Cin, int kh, int kw, void* stream) {
   long long total = (long long)Cout * Cin * kh * kw;
   if (total == 0) return EGM_OK;
-  k_pack_w_tc<<<egm_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wf_bf16, (__nv_bfloat16*)wd_bf16, Cout, Cin, kh * kw);
+  egm_launch(k_pack_w_tc, egm_grid_for(total, 256), 256, 0, (cudaStream_t)stream, w, (__nv_bfloat16*)wf_bf16, (__nv_bfloat16*)wd_bf16, Cout, Cin, kh * kw);
   EGM_LAUNCH_CHECK("pack_conv_weight_tc"); return EGM_OK;
 }
 
@@ -885,7 +935,7 @@ struct WgradParams {
 constexpr int WG_TAPS = 3;
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
-                                                           float* __restrict__ dwp, WgradParams p) {
+                                                           float* __restrict__ dwp, WgradParams p) { egm_pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + (size_t)p.stages * p.stageBytes);
@@ -1019,7 +1069,7 @@ struct WgradHaloParams {
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
-                                                                float* __restrict__ dwp, WgradHaloParams p) {
+                                                                float* __restrict__ dwp, WgradHaloParams p) { egm_pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + (size_t)p.stages * p.stageBytes);
@@ -1250,7 +1300,7 @@ static int launch_wgrad_halo(const NhwcView& xv, const NhwcView& dyv, float* dwp
   egm_ensure_smem(k_wgrad_tc_halo, 227 * 1024, attr_set);
   long long grid = units * p.splits;
   EGM_REQUIRE(grid < (1ll << 31), EGM_E_SHAPE, "wgrad_tc: grid too large");
-  k_wgrad_tc_halo<<<(unsigned)grid, TC_THREADS, smem, st>>>(tmDY, tmX, dwp, p);
+  egm_launch(k_wgrad_tc_halo, (unsigned)grid, TC_THREADS, smem, st, tmDY, tmX, dwp, p);
   return egm_check_launch("conv2d_wgrad_tc_halo");
 }
 
@@ -1295,11 +1345,11 @@ extern "C" int egm_conv2d_wgrad_tc_view(const void* x, long long x_cstride, long
   egm_ensure_smem(k_wgrad_tc, 227 * 1024, attr_set);
   long long grid = units * p.splits;
   EGM_REQUIRE(grid < (1ll << 31), EGM_E_SHAPE, "wgrad_tc: grid too large");
-  k_wgrad_tc<<<(unsigned)grid, TC_THREADS, smem, st>>>(tmDY, tmX, dw_packed, p);
+  egm_launch(k_wgrad_tc, (unsigned)grid, TC_THREADS, smem, st, tmDY, tmX, dw_packed, p);
   EGM_LAUNCH_CHECK("conv2d_wgrad_tc"); return EGM_OK;
 }
 // dw_packed [taps][Cout][Cin] (tcgen05 wgrad layout) -> dw [Cout][Cin][kh][kw]   (dw = beta*dw + unpacked)
-__global__ void k_unpack_dw_tc(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin, int taps, float beta) {
+__global__ void k_unpack_dw_tc(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin, int taps, float beta) { egm_pdl_enter();
   long long total = (long long)Cout * Cin * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int t = (int)(i % taps); long long q = i / taps;        // q = co*Cin + ci
@@ -1310,7 +1360,7 @@ __global__ void k_unpack_dw_tc(const float* __restrict__ dwp, float* __restrict_
 extern "C" int egm_unpack_conv_wgrad_tc(const float* dw_packed, float* dw, int Cout, int Cin, int kh, int kw, float beta, void* stream) {
   long long total = (long long)Cout * Cin * kh * kw;
   if (total == 0) return EGM_OK;
-  k_unpack_dw_tc<<<egm_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dw_packed, dw, Cout, Cin, kh * kw, beta);
+  egm_launch(k_unpack_dw_tc, egm_grid_for(total, 256), 256, 0, (cudaStream_t)stream, dw_packed, dw, Cout, Cin, kh * kw, beta);
   EGM_LAUNCH_CHECK("unpack_conv_wgrad_tc"); return EGM_OK;
 }
 extern "C" int egm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_packed, int N, int H, int W, int Cin, int Cout, int kh, int kw, int dil,

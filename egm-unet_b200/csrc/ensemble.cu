@@ -59,7 +59,7 @@ __device__ __forceinline__ int fused_argmax(const float (&cu)[ENS_MAXC], const f
 
 // confusion[a][label][pred] += ...   for one image; label pixels at (Ho, Wo) = label size
 __global__ void __launch_bounds__(256) k_ens_confusion(const float* __restrict__ clip, const float* __restrict__ unet, const unsigned char* __restrict__ label,
-                                                       EnsGeom g, const double* __restrict__ alphas, int n_alpha, unsigned long long* __restrict__ conf) {
+                                                       EnsGeom g, const double* __restrict__ alphas, int n_alpha, unsigned long long* __restrict__ conf) { egm_pdl_enter();
   extern __shared__ unsigned int s_cnt[];                 // [n_alpha][C*C]
   const int CC = g.C * g.C;
   for (int i = threadIdx.x; i < n_alpha * CC; i += blockDim.x) s_cnt[i] = 0;
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) k_ens_confusion(const float* __restrict__
 
 // mIoU per alpha (float32, ConfusionMatrix.compute) and the FIRST alpha whose mIoU is strictly larger than everything before it
 __global__ void k_ens_best(const unsigned long long* __restrict__ conf, const double* __restrict__ alphas, int n_alpha, int C, float* __restrict__ miou,
-                           double* __restrict__ best) {
+                           double* __restrict__ best) { egm_pdl_enter();
   for (int a = threadIdx.x; a < n_alpha; a += blockDim.x) {
     const unsigned long long* m = conf + (size_t)a * C * C;
     float acc = 0.f;
@@ -128,7 +128,7 @@ __global__ void k_ens_best(const unsigned long long* __restrict__ conf, const do
 }
 
 // final mask at (Ho, Wo): uint8(argmax(clip_up + alpha*unet)) resized INTER_NEAREST
-__global__ void k_ens_predict(const float* __restrict__ clip, const float* __restrict__ unet, EnsGeom g, float alpha, unsigned char* __restrict__ out) {
+__global__ void k_ens_predict(const float* __restrict__ clip, const float* __restrict__ unet, EnsGeom g, float alpha, unsigned char* __restrict__ out) { egm_pdl_enter();
   const long long total = (long long)g.Ho * g.Wo;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int yo = (int)(i / g.Wo), xo = (int)(i - (long long)yo * g.Wo);
@@ -147,13 +147,13 @@ extern "C" int egm_ensemble_confusion(const float* clip_logits, int hc, int wc, 
   if ((long long)Hl * Wl == 0) return EGM_OK;
   EnsGeom g{hc, wc, H, W, Hl, Wl, num_classes};
   const size_t sm = (size_t)n_alpha * num_classes * num_classes * sizeof(unsigned int);
-  k_ens_confusion<<<egm_grid_for((long long)Hl * Wl, 256, 4), 256, sm, (cudaStream_t)stream>>>(clip_logits, unet_logits, label, g, alphas, n_alpha, confusion);
+  egm_launch(k_ens_confusion, egm_grid_for((long long)Hl * Wl, 256, 4), 256, sm, (cudaStream_t)stream, clip_logits, unet_logits, label, g, alphas, n_alpha, confusion);
   EGM_LAUNCH_CHECK("ensemble_confusion"); return EGM_OK;
 }
 extern "C" int egm_ensemble_best_alpha(const unsigned long long* confusion, const double* alphas, int n_alpha, int num_classes, float* miou, double* best,
                                        void* stream) {
   EGM_REQUIRE(num_classes >= 2 && num_classes <= ENS_MAXC && n_alpha >= 1, EGM_E_SHAPE, "ensemble_best_alpha: bad shape");
-  k_ens_best<<<1, 128, 0, (cudaStream_t)stream>>>(confusion, alphas, n_alpha, num_classes, miou, best);
+  egm_launch(k_ens_best, 1, 128, 0, (cudaStream_t)stream, confusion, alphas, n_alpha, num_classes, miou, best);
   EGM_LAUNCH_CHECK("ensemble_best_alpha"); return EGM_OK;
 }
 extern "C" int egm_ensemble_predict(const float* clip_logits, int hc, int wc, const float* unet_logits, int H, int W, int num_classes, float alpha,
@@ -161,6 +161,6 @@ extern "C" int egm_ensemble_predict(const float* clip_logits, int hc, int wc, co
   EGM_REQUIRE(num_classes >= 2 && num_classes <= ENS_MAXC, EGM_E_SHAPE, "ensemble: 2..%d classes", ENS_MAXC);
   if ((long long)Ho * Wo == 0) return EGM_OK;
   EnsGeom g{hc, wc, H, W, Ho, Wo, num_classes};
-  k_ens_predict<<<egm_grid_for((long long)Ho * Wo, 256, 8), 256, 0, (cudaStream_t)stream>>>(clip_logits, unet_logits, g, alpha, mask);
+  egm_launch(k_ens_predict, egm_grid_for((long long)Ho * Wo, 256, 8), 256, 0, (cudaStream_t)stream, clip_logits, unet_logits, g, alpha, mask);
   EGM_LAUNCH_CHECK("ensemble_predict"); return EGM_OK;
 }

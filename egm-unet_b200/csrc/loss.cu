@@ -40,7 +40,7 @@ __device__ __forceinline__ void stencils(const float* x0, const long long* t0, i
 }
 
 __global__ void __launch_bounds__(256) k_loss_pass1(const float* __restrict__ logits, const long long* __restrict__ target, const float* __restrict__ weight,
-                                                    int N, int C, int H, int W, int ignore_index, double* __restrict__ acc, unsigned char* __restrict__ smap) {
+                                                    int N, int C, int H, int W, int ignore_index, double* __restrict__ acc, unsigned char* __restrict__ smap) { egm_pdl_enter();
   __shared__ float red[32];
   const int n = blockIdx.y;
   const long long HW = (long long)H * W;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) k_loss_pass1(const float* __restrict__ lo
 }
 
 // out[0] = total, out[1..5] = ce, dice, laplace, lap, sobel, out[6] = number of out-of-range labels (0 for valid input)
-__global__ void k_loss_finalize(const double* __restrict__ acc, int N, int C, double NHW, int with_dice, float* __restrict__ out) {
+__global__ void k_loss_finalize(const double* __restrict__ acc, int N, int C, double NHW, int with_dice, float* __restrict__ out) { egm_pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double eps = 1e-6;
   double ce = acc[0] / acc[1];
@@ -111,7 +111,7 @@ __global__ void k_loss_finalize(const double* __restrict__ acc, int N, int C, do
 
 __global__ void __launch_bounds__(256) k_loss_pass2(const float* __restrict__ logits, const long long* __restrict__ target, const float* __restrict__ weight,
                                                     int N, int C, int H, int W, int ignore_index, const double* __restrict__ acc,
-                                                    const unsigned char* __restrict__ smap, float gscale, int with_dice, float* __restrict__ dlogits) {
+                                                    const unsigned char* __restrict__ smap, float gscale, int with_dice, float* __restrict__ dlogits) { egm_pdl_enter();
   const int n = blockIdx.y;
   const long long HW = (long long)H * W;
   const float* lg = logits + (long long)n * C * HW;
@@ -201,7 +201,7 @@ constexpr int LT_W = 64, LT_H = 4, LT_HW = LT_W + 2, LT_HH = LT_H + 2;
 
 template <int MAXC>
 __global__ void __launch_bounds__(256) k_loss_pass1_t(const float* __restrict__ logits, const long long* __restrict__ target, const float* __restrict__ weight,
-                                                      int N, int C, int H, int W, int ignore_index, double* __restrict__ acc, unsigned char* __restrict__ smap) {
+                                                      int N, int C, int H, int W, int ignore_index, double* __restrict__ acc, unsigned char* __restrict__ smap) { egm_pdl_enter();
   __shared__ float red[32];
   __shared__ float sx[LT_HH][LT_HW], st0[LT_HH][LT_HW];
   const int n = blockIdx.z;
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(256) k_loss_pass1_t(const float* __restrict__ 
 template <int MAXC>
 __global__ void __launch_bounds__(256) k_loss_pass2_t(const float* __restrict__ logits, const long long* __restrict__ target, const float* __restrict__ weight,
                                                       int N, int C, int H, int W, int ignore_index, const double* __restrict__ acc,
-                                                      const unsigned char* __restrict__ smap, float gscale, int with_dice, float* __restrict__ dlogits) {
+                                                      const unsigned char* __restrict__ smap, float gscale, int with_dice, float* __restrict__ dlogits) { egm_pdl_enter();
   __shared__ unsigned char sb[LT_HH][LT_HW + 2];
   const int n = blockIdx.z;
   const long long HW = (long long)H * W;
@@ -382,9 +382,9 @@ extern "C" int egm_loss_fwd_bwd(const float* logits, const long long* target, co
   if (flat) {                                            // round-1 kernels (diagnostic switch)
     int bx = (int)((HW + 255) / 256); int cap = egm_num_sms() * 8 / N + 1; if (bx > cap) bx = cap; if (bx < 1) bx = 1;
     dim3 grid(bx, N);
-    k_loss_pass1<<<grid, 256, 0, st>>>(logits, target, class_weight, N, C, H, W, ignore_index, acc, smap);
-    k_loss_finalize<<<1, 32, 0, st>>>(acc, N, C, (double)N * (double)HW, with_dice, loss_out);
-    if (dlogits) k_loss_pass2<<<grid, 256, 0, st>>>(logits, target, class_weight, N, C, H, W, ignore_index, acc, smap, grad_scale, with_dice, dlogits);
+    egm_launch(k_loss_pass1, grid, 256, 0, st, logits, target, class_weight, N, C, H, W, ignore_index, acc, smap);
+    egm_launch(k_loss_finalize, 1, 32, 0, st, acc, N, C, (double)N * (double)HW, with_dice, loss_out);
+    if (dlogits) egm_launch(k_loss_pass2, grid, 256, 0, st, logits, target, class_weight, N, C, H, W, ignore_index, acc, smap, grad_scale, with_dice, dlogits);
     EGM_LAUNCH_CHECK("loss_fwd_bwd"); return EGM_OK;
   }
   const int tilesX = (W + LT_W - 1) / LT_W, tilesY = (H + LT_H - 1) / LT_H;
@@ -392,9 +392,9 @@ extern "C" int egm_loss_fwd_bwd(const float* logits, const long long* target, co
   dim3 grid(tilesX, (unsigned)gy, N);
 #define EGM_LOSS_LAUNCH(MC)                                                                                                                    \
   {                                                                                                                                            \
-    k_loss_pass1_t<MC><<<grid, 256, 0, st>>>(logits, target, class_weight, N, C, H, W, ignore_index, acc, smap);                               \
-    k_loss_finalize<<<1, 32, 0, st>>>(acc, N, C, (double)N * (double)HW, with_dice, loss_out);                                                 \
-    if (dlogits) k_loss_pass2_t<MC><<<grid, 256, 0, st>>>(logits, target, class_weight, N, C, H, W, ignore_index, acc, smap, grad_scale, with_dice, dlogits); \
+    egm_launch(k_loss_pass1_t<MC>, grid, 256, 0, st, logits, target, class_weight, N, C, H, W, ignore_index, acc, smap);                               \
+    egm_launch(k_loss_finalize, 1, 32, 0, st, acc, N, C, (double)N * (double)HW, with_dice, loss_out);                                                 \
+    if (dlogits) egm_launch(k_loss_pass2_t<MC>, grid, 256, 0, st, logits, target, class_weight, N, C, H, W, ignore_index, acc, smap, grad_scale, with_dice, dlogits); \
   }
   if (C <= 2) EGM_LOSS_LAUNCH(2) else if (C <= 4) EGM_LOSS_LAUNCH(4) else EGM_LOSS_LAUNCH(16)
 #undef EGM_LOSS_LAUNCH
@@ -403,7 +403,7 @@ extern "C" int egm_loss_fwd_bwd(const float* logits, const long long* target, co
 
 // ------------------------------------------------------------------ fused SGD (torch.optim.SGD semantics, dampening 0, no nesterov)
 // hp (device or host-mapped): hp[0]=lr hp[1]=momentum hp[2]=weight_decay hp[3]=grad_scale (e.g. 1/world_size)
-__global__ void k_sgd(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n, const float* __restrict__ hp) {
+__global__ void k_sgd(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n, const float* __restrict__ hp) { egm_pdl_enter();
   const float lr = hp[0], mom = hp[1], wd = hp[2], gs = hp[3];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float w = p[i];
@@ -415,7 +415,7 @@ __global__ void k_sgd(float* __restrict__ p, const float* __restrict__ g, float*
 }
 extern "C" int egm_sgd_step(float* params, const float* grads, float* momentum_buf, long long n, const float* hyper_dev, void* stream) {
   if (n == 0) return EGM_OK;
-  k_sgd<<<egm_grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, momentum_buf, n, hyper_dev);
+  egm_launch(k_sgd, egm_grid_for(n, 256), 256, 0, (cudaStream_t)stream, params, grads, momentum_buf, n, hyper_dev);
   EGM_LAUNCH_CHECK("sgd_step"); return EGM_OK;
 }
 
@@ -423,7 +423,7 @@ extern "C" int egm_sgd_step(float* params, const float* grads, float* momentum_b
 // mat[n_cls*n_cls] int64 += bincount(n_cls*t + argmax) over valid (0 <= t < n_cls) pixels (distributed_utils.py:81-91)
 // dice_acc[N][C][3] double += (inter, pred_sum, tgt_sum) over t != ignore_index pixels of one-hot argmax vs one-hot target (:135-144)
 __global__ void k_eval_metrics(const float* __restrict__ logits, const long long* __restrict__ target, int N, int C, long long HW, int ignore_index,
-                               unsigned long long* __restrict__ mat, double* __restrict__ dice_acc) {
+                               unsigned long long* __restrict__ mat, double* __restrict__ dice_acc) { egm_pdl_enter();
   extern __shared__ unsigned int sh[];     // [C*C] confusion + [C*3] dice
   const int n = blockIdx.y;
   for (int i = threadIdx.x; i < C * C + C * 3; i += blockDim.x) sh[i] = 0;
@@ -450,7 +450,7 @@ extern "C" int egm_eval_metrics(const float* logits, const long long* target, in
   long long HW = (long long)H * W;
   if (HW == 0) return EGM_OK;
   int bx = (int)((HW + 255) / 256); int cap = egm_num_sms() * 8 / N + 1; if (bx > cap) bx = cap;
-  k_eval_metrics<<<dim3(bx, N), 256, (C * C + C * 3) * sizeof(unsigned int), (cudaStream_t)stream>>>(logits, target, N, C, HW, ignore_index,
+  egm_launch(k_eval_metrics, dim3(bx, N), 256, (C * C + C * 3) * sizeof(unsigned int), (cudaStream_t)stream, logits, target, N, C, HW, ignore_index,
                                                                                                     (unsigned long long*)confmat, dice_acc);
   EGM_LAUNCH_CHECK("eval_metrics"); return EGM_OK;
 }

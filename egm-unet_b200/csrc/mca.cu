@@ -4,6 +4,7 @@
 // frequency_enhancement is the identity scaled by 1.1, so the blend is
 //   y = 0.51*u + 0.2*(max3x3 u - min3x3 u) + 0.2*avg3x3((u - avg3x3 u)^2) + 0.1*shuffle4(u),   u = x*(g_c+g_h+g_w)/3
 #include "common.cuh"
+#include <stdlib.h>
 
 // Per-axis vectors are packed [h: N*H | w: N*W | c: N*C], each segment padded to 4 entries so the
 // channel segment stays 16-byte aligned for vector loads.
@@ -17,7 +18,7 @@ static inline long long mca_total(int N, int H, int W, int C) { return mca_oc(N,
 // K=2: (sum x, sum x^2);  K=1 with b != null: sum a*b.
 template <typename T, int V, int K>
 __global__ void k_axis_sums(const T* __restrict__ a, const T* __restrict__ b, int H, int W, int C, double* __restrict__ rowS, double* __restrict__ colS,
-                            double* __restrict__ chS) {
+                            double* __restrict__ chS) { egm_pdl_enter();
   extern __shared__ float sm[];           // col[W][K] | ch[rows][K][C] | red[32]
   const int CV = C / V;
   const int rows = blockDim.x / CV;
@@ -80,11 +81,118 @@ __global__ void k_axis_sums(const T* __restrict__ a, const T* __restrict__ b, in
     atomicAdd(chS + ((long long)n * C + c) * K + k, (double)s);
   }
 }
+// Banded variant (the production shapes): the kernel above launches one block per image ROW and ends every block with W*K + C*K
+// fp64 global atomics -- 2.3 M atomics for the 240^2 x 64 map -- and funnels the per-pixel sums through contended shared-memory
+// atomics; it ran at 0.2-1.2 TB/s (137 us for the 29 MB 60^2 x 256 map).  Here a block owns a band of TH rows of one image, every
+// thread keeps ONE 16-byte channel vector position (threads = PX pixels x CV vectors, 256 % CV == 0) and walks the band with fixed
+// pixel slots, so the channel sums (chacc) and the column sums (colacc, one slot per pass over the row) live in registers for the
+// whole band and the row sums are reduced once per row inside the warp; global fp64 atomics drop by the band height.
+constexpr int AS_MAXP = 16;     // passes over one row: ceil(W / PX)
+constexpr int AS_MAXTH = 8;
+template <typename T, int K>
+__global__ void __launch_bounds__(256) k_axis_sums_band(const T* __restrict__ a, const T* __restrict__ b, int H, int W, int C, int TH, int bands,
+                                                        double* __restrict__ rowS, double* __restrict__ colS, double* __restrict__ chS) { egm_pdl_enter();
+  constexpr int VE = 16 / (int)sizeof(T);
+  extern __shared__ float sm[];           // col[W][K] | rowp[AS_MAXTH][8 warps][K] | chp[PX][K][C]
+  const int CV = C / VE, PX = 256 / CV;
+  const int cg = threadIdx.x % CV, px = threadIdx.x / CV, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* col = sm; float* rowp = col + (size_t)W * K; float* chp = rowp + AS_MAXTH * 8 * K;
+  const int n = blockIdx.x / bands, h0 = (blockIdx.x - n * bands) * TH, h1 = min(h0 + TH, H);
+  for (int i = threadIdx.x; i < W * K; i += 256) col[i] = 0.f;
+  float chacc[K][VE], colacc[AS_MAXP][K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int j = 0; j < VE; ++j) chacc[k][j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < AS_MAXP; ++i) colacc[i][k] = 0.f;
+  }
+  const int np = (W + PX - 1) / PX;
+  for (int h = h0; h < h1; ++h) {
+    const long long base = ((long long)n * H + h) * W * C + cg * VE;
+    float rs[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) rs[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < AS_MAXP; ++i) {
+      const int w = i * PX + px;
+      if (i < np && w < W) {
+        FVec<VE> x = ldv<VE>(a + base + (long long)w * C);
+        if (b) { const FVec<VE> y = ldv<VE>(b + base + (long long)w * C);
+#pragma unroll
+          for (int j = 0; j < VE; ++j) x.v[j] *= y.v[j]; }
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < VE; ++j) {
+          s0 += x.v[j]; chacc[0][j] += x.v[j];
+          if (K == 2) { const float q = x.v[j] * x.v[j]; s1 += q; chacc[K - 1][j] += q; }
+        }
+        colacc[i][0] += s0; rs[0] += s0;
+        if (K == 2) { colacc[i][K - 1] += s1; rs[K - 1] += s1; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) { const float v = warp_sum(rs[k]); if (lane == 0) rowp[((h - h0) * 8 + wid) * K + k] = v; }
+  }
+  __syncthreads();                                      // col zeroed, rowp complete
+  // column sums: the CV threads of one pixel are consecutive lanes (CV <= 32: one aligned lane group; CV == 64: two warps)
+  const int grp = CV < 32 ? CV : 32;
+#pragma unroll
+  for (int i = 0; i < AS_MAXP; ++i) {
+    if (i < np) {                                       // block-uniform
+      const int w = i * PX + px;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        float v = colacc[i][k];
+        for (int o = grp >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((cg & (grp - 1)) == 0 && w < W) { if (CV > 32) atomicAdd(&col[w * K + k], v); else col[w * K + k] = v; }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < VE; ++j) chp[((size_t)px * K + k) * C + cg * VE + j] = chacc[k][j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < (h1 - h0) * K; i += 256) {
+    const int hr = i / K, k = i - hr * K; float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += rowp[(hr * 8 + q) * K + k];
+    rowS[((long long)n * H + h0 + hr) * K + k] = (double)v;
+  }
+  for (int i = threadIdx.x; i < W * K; i += 256) atomicAdd(colS + (long long)n * W * K + i, (double)col[i]);
+  for (int i = threadIdx.x; i < K * C; i += 256) {
+    const int k = i / C, c = i - k * C; float v = 0.f;
+    for (int q = 0; q < PX; ++q) v += chp[((size_t)q * K + k) * C + c];
+    atomicAdd(chS + ((long long)n * C + c) * K + k, (double)v);
+  }
+}
+template <typename T, int K>
+static bool launch_axis_sums_band(const T* a, const T* b, int N, int H, int W, int C, double* rowS, double* colS, double* chS, cudaStream_t st) {
+  constexpr int VE = 16 / (int)sizeof(T);
+  if (C % VE != 0 || ((uintptr_t)a & 15) || ((uintptr_t)b & 15)) return false;
+  const int CV = C / VE;
+  if (CV < 1 || CV > 64 || 256 % CV != 0) return false;
+  const int PX = 256 / CV;
+  if ((W + PX - 1) / PX > AS_MAXP) return false;
+  const size_t smb = ((size_t)W * K + AS_MAXTH * 8 * K + (size_t)PX * K * C) * sizeof(float);
+  if (smb > 48 * 1024) return false;
+  long long th = (long long)N * H / (4LL * egm_num_sms()); if (th < 1) th = 1; if (th > AS_MAXTH) th = AS_MAXTH;
+  const int bands = cdiv(H, th);
+  egm_launch(k_axis_sums_band<T, K>, N * bands, 256, smb, st, a, b, H, W, C, (int)th, bands, rowS, colS, chS);
+  return true;
+}
+
 template <typename T, int K>
 static int launch_axis_sums(const T* a, const T* b, int N, int H, int W, int C, double* sums, cudaStream_t st) {
   double* rowS = sums; double* colS = sums + mca_ow(N, H) * K; double* chS = sums + mca_oc(N, H, W) * K;
   cudaMemsetAsync(sums, 0, sizeof(double) * K * (size_t)mca_total(N, H, W, C), st);
   if ((long long)N * H * W * C == 0) return EGM_OK;
+  {
+    static int band_off = -1;                           // EGM_MCA_SUMS_V1=1: the row-per-block kernel everywhere (A/B measurements)
+    if (band_off < 0) { const char* e = getenv("EGM_MCA_SUMS_V1"); band_off = (e && e[0] == '1') ? 1 : 0; }
+    if (!band_off && launch_axis_sums_band<T, K>(a, b, N, H, W, C, rowS, colS, chS, st)) return egm_check_launch("mca_axis_sums(band)");
+  }
   int v = egm_pick_vec(C); if (v > 4) v = 4;
   int CV = C / v; EGM_REQUIRE(CV <= 512, EGM_E_SHAPE, "mca: C=%d too large", C);
   int rows = 256 / CV; if (rows < 1) rows = 1; int threads = CV * rows;
@@ -94,7 +202,7 @@ static int launch_axis_sums(const T* a, const T* b, int N, int H, int W, int C, 
     if (V <= 4) {
       auto kern = k_axis_sums<T, (V <= 4 ? V : 4), K>;
       if (smb > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
-      kern<<<N * H, threads, smb, st>>>(a, b, H, W, C, rowS, colS, chS);
+      egm_launch(kern, N * H, threads, smb, st, a, b, H, W, C, rowS, colS, chS);
     }
   });
   return egm_check_launch("mca_axis_sums");
@@ -124,7 +232,7 @@ __device__ __forceinline__ void gate_stat(const GateDesc& d, int n, int i, float
   double m = s[0] / d.n_el, var = (s[1] - s[0] * m) / (d.n_el - 1.0);
   avg = (float)m; sd = (float)sqrt(var > 0.0 ? var : 0.0);
 }
-__global__ void k_mca_gates(GateDesc g0, GateDesc g1, GateDesc g2, int N) {
+__global__ void k_mca_gates(GateDesc g0, GateDesc g1, GateDesc g2, int N) { egm_pdl_enter();
   GateDesc d = blockIdx.y == 0 ? g0 : (blockIdx.y == 1 ? g1 : g2);
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * d.L) return;
@@ -147,7 +255,7 @@ extern "C" int egm_mca_gates(const double* sums, int N, int H, int W, int C, con
   GateDesc gw{sums + 2 * ow, W, (double)H * C, w_w, k_w, ks_w, gates + ow, avg + ow, stdv + ow};
   GateDesc gc{sums + 2 * oc, C, (double)H * W, w_c, k_c, ks_c, gates + oc, avg + oc, stdv + oc};
   int mx = H > W ? H : W; if (C > mx) mx = C;
-  k_mca_gates<<<dim3(cdiv((long long)N * mx, 128), 3), 128, 0, (cudaStream_t)stream>>>(gh, gw, gc, N);
+  egm_launch(k_mca_gates, dim3(cdiv((long long)N * mx, 128), 3), 128, 0, (cudaStream_t)stream, gh, gw, gc, N);
   EGM_LAUNCH_CHECK("mca_gates"); return EGM_OK;
 }
 
@@ -167,7 +275,7 @@ __device__ __forceinline__ FVec<V> mca_u(const T* x, const McaGeom& g, int n, in
 //   D : d2 = (u - avg3x3(u))^2                                          (9 cached reads, 1 write)
 //   O : y  = 0.51 u + 0.2 (max3x3 u - min3x3 u) + 0.2 avg3x3(d2) + 0.1 shuffle4(u)  (+ arg-max/min byte map)
 template <typename T, int V>
-__global__ void k_mca_u(const T* __restrict__ x, T* __restrict__ u, McaGeom g) {
+__global__ void k_mca_u(const T* __restrict__ x, T* __restrict__ u, McaGeom g) { egm_pdl_enter();
   const int CV = g.C / V;
   long long total = (long long)g.N * g.H * g.W * CV;
   const NhwcIndexer ix(CV, g.W, g.H, total);
@@ -179,7 +287,7 @@ __global__ void k_mca_u(const T* __restrict__ x, T* __restrict__ u, McaGeom g) {
   }
 }
 template <typename T, int V>
-__global__ void k_mca_d2(const T* __restrict__ u, T* __restrict__ d2, int N, int H, int W, int CV) {
+__global__ void k_mca_d2(const T* __restrict__ u, T* __restrict__ d2, int N, int H, int W, int CV) { egm_pdl_enter();
   const int C = CV * V; long long total = (long long)N * H * W * CV;
   const NhwcIndexer ix(CV, W, H, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -210,7 +318,7 @@ __global__ void k_mca_d2(const T* __restrict__ u, T* __restrict__ d2, int N, int
   }
 }
 template <typename T, int V>
-__global__ void k_mca_out(const T* __restrict__ u, const T* __restrict__ d2, T* __restrict__ y, unsigned char* __restrict__ idx, int N, int H, int W, int CV) {
+__global__ void k_mca_out(const T* __restrict__ u, const T* __restrict__ d2, T* __restrict__ y, unsigned char* __restrict__ idx, int N, int H, int W, int CV) { egm_pdl_enter();
   const int C = CV * V; long long total = (long long)N * H * W * CV;
   const NhwcIndexer ix(CV, W, H, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -265,13 +373,13 @@ extern "C" int egm_mca_apply(const void* x, const float* gates, void* y, unsigne
   int v = egm_pick_vec(C); if (v > 8) v = 8; if (v < 4) v = 4;
   EGM_DISPATCH_DTYPE(dtype, {
     if (v == 8) {
-      k_mca_u<T, 8><<<egm_grid_for(total / 8, 256), 256, 0, st>>>((const T*)x, (T*)u_scratch, g);
-      k_mca_d2<T, 8><<<egm_grid_for(total / 8, 256), 256, 0, st>>>((const T*)u_scratch, (T*)d2_scratch, N, H, W, C / 8);
-      k_mca_out<T, 8><<<egm_grid_for(total / 8, 256), 256, 0, st>>>((const T*)u_scratch, (const T*)d2_scratch, (T*)y, argidx, N, H, W, C / 8);
+      egm_launch(k_mca_u<T, 8>, egm_grid_for(total / 8, 256), 256, 0, st, (const T*)x, (T*)u_scratch, g);
+      egm_launch(k_mca_d2<T, 8>, egm_grid_for(total / 8, 256), 256, 0, st, (const T*)u_scratch, (T*)d2_scratch, N, H, W, C / 8);
+      egm_launch(k_mca_out<T, 8>, egm_grid_for(total / 8, 256), 256, 0, st, (const T*)u_scratch, (const T*)d2_scratch, (T*)y, argidx, N, H, W, C / 8);
     } else {
-      k_mca_u<T, 4><<<egm_grid_for(total / 4, 256), 256, 0, st>>>((const T*)x, (T*)u_scratch, g);
-      k_mca_d2<T, 4><<<egm_grid_for(total / 4, 256), 256, 0, st>>>((const T*)u_scratch, (T*)d2_scratch, N, H, W, C / 4);
-      k_mca_out<T, 4><<<egm_grid_for(total / 4, 256), 256, 0, st>>>((const T*)u_scratch, (const T*)d2_scratch, (T*)y, argidx, N, H, W, C / 4);
+      egm_launch(k_mca_u<T, 4>, egm_grid_for(total / 4, 256), 256, 0, st, (const T*)x, (T*)u_scratch, g);
+      egm_launch(k_mca_d2<T, 4>, egm_grid_for(total / 4, 256), 256, 0, st, (const T*)u_scratch, (T*)d2_scratch, N, H, W, C / 4);
+      egm_launch(k_mca_out<T, 4>, egm_grid_for(total / 4, 256), 256, 0, st, (const T*)u_scratch, (const T*)d2_scratch, (T*)y, argidx, N, H, W, C / 4);
     }
   });
   EGM_LAUNCH_CHECK("mca_apply"); return EGM_OK;
@@ -280,7 +388,7 @@ extern "C" int egm_mca_apply(const void* x, const float* gates, void* y, unsigne
 // ------------------------------------------------------------------ backward
 // pass E:  E[q] = 2*(u[q]-avg3(u)[q]) * (0.2/9) * sum_{p in N(q)} dy[p]
 template <typename T, int V>
-__global__ void __launch_bounds__(256) k_mca_bwd_e(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ E, McaGeom g) {
+__global__ void __launch_bounds__(256) k_mca_bwd_e(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ E, McaGeom g) { egm_pdl_enter();
   const int CV = g.C / V;
   long long total = (long long)g.N * g.H * g.W * CV;
   const NhwcIndexer ix(CV, g.W, g.H, total);
@@ -320,7 +428,7 @@ __global__ void __launch_bounds__(256) k_mca_bwd_e(const T* __restrict__ x, cons
 // pass U: du[q] = 0.51 dy[q] + 0.1 unshuffle(dy)[q] + 0.2 (sum_p dy[p][argmax_p==q] - sum_p dy[p][argmin_p==q]) + E[q] - avg3(E)[q]
 template <typename T, int V>
 __global__ void __launch_bounds__(256) k_mca_bwd_du(const T* __restrict__ dy, const unsigned char* __restrict__ idx, const T* __restrict__ E,
-                                                    T* __restrict__ du, McaGeom g) {
+                                                    T* __restrict__ du, McaGeom g) { egm_pdl_enter();
   const int CV = g.C / V;
   long long total = (long long)g.N * g.H * g.W * CV;
   const NhwcIndexer ix(CV, g.W, g.H, total);
@@ -373,11 +481,11 @@ extern "C" int egm_mca_bwd_du(const void* x, const float* gates, const void* dy,
   cudaStream_t st = (cudaStream_t)stream;
   EGM_DISPATCH_DTYPE(dtype, {
     if (C % 8 == 0) {
-      k_mca_bwd_e<T, 8><<<egm_grid_for(total / 8, 256, 16), 256, 0, st>>>((const T*)x, (const T*)dy, (T*)E_scratch, g);
-      k_mca_bwd_du<T, 8><<<egm_grid_for(total / 8, 256, 16), 256, 0, st>>>((const T*)dy, argidx, (const T*)E_scratch, (T*)du, g);
+      egm_launch(k_mca_bwd_e<T, 8>, egm_grid_for(total / 8, 256, 16), 256, 0, st, (const T*)x, (const T*)dy, (T*)E_scratch, g);
+      egm_launch(k_mca_bwd_du<T, 8>, egm_grid_for(total / 8, 256, 16), 256, 0, st, (const T*)dy, argidx, (const T*)E_scratch, (T*)du, g);
     } else {
-      k_mca_bwd_e<T, 4><<<egm_grid_for(total / 4, 256, 16), 256, 0, st>>>((const T*)x, (const T*)dy, (T*)E_scratch, g);
-      k_mca_bwd_du<T, 4><<<egm_grid_for(total / 4, 256, 16), 256, 0, st>>>((const T*)dy, argidx, (const T*)E_scratch, (T*)du, g);
+      egm_launch(k_mca_bwd_e<T, 4>, egm_grid_for(total / 4, 256, 16), 256, 0, st, (const T*)x, (const T*)dy, (T*)E_scratch, g);
+      egm_launch(k_mca_bwd_du<T, 4>, egm_grid_for(total / 4, 256, 16), 256, 0, st, (const T*)dy, argidx, (const T*)E_scratch, (T*)du, g);
     }
   });
   EGM_LAUNCH_CHECK("mca_bwd_du"); return EGM_OK;
@@ -388,7 +496,7 @@ extern "C" int egm_mca_bwd_du(const void* x, const float* gates, const void* dy,
 //   a_i = davg/n - dstd*avg/((n-1) std),  b_i = dstd/((n-1) std)    (d std / d x = (x-avg)/((n-1) std))
 struct GateBwd { const double* dG; int L; double n_el; const float* w2; const float* kw; int ks; const float* gate; const float* avg; const float* stdv;
                  float* a; float* b; float* dw2; float* dkw; };
-__global__ void __launch_bounds__(256) k_mca_gates_bwd(GateBwd g0, GateBwd g1, GateBwd g2, int N) {
+__global__ void __launch_bounds__(256) k_mca_gates_bwd(GateBwd g0, GateBwd g1, GateBwd g2, int N) { egm_pdl_enter();
   __shared__ float red[32];
   GateBwd d = blockIdx.x == 0 ? g0 : (blockIdx.x == 1 ? g1 : g2);
   const int pad = (d.ks - 1) / 2, tot = N * d.L;
@@ -432,14 +540,14 @@ extern "C" int egm_mca_gates_bwd(const double* dG, int N, int H, int W, int C, c
   GateBwd gh{dG + oh, H, (double)W * C, w_h, k_h, ks_h, gates + oh, avg + oh, stdv + oh, coef_a + oh, coef_b + oh, dw_h, dk_h};
   GateBwd gw{dG + ow, W, (double)H * C, w_w, k_w, ks_w, gates + ow, avg + ow, stdv + ow, coef_a + ow, coef_b + ow, dw_w, dk_w};
   GateBwd gc{dG + oc, C, (double)H * W, w_c, k_c, ks_c, gates + oc, avg + oc, stdv + oc, coef_a + oc, coef_b + oc, dw_c, dk_c};
-  k_mca_gates_bwd<<<3, 256, 0, (cudaStream_t)stream>>>(gh, gw, gc, N);
+  egm_launch(k_mca_gates_bwd, 3, 256, 0, (cudaStream_t)stream, gh, gw, gc, N);
   EGM_LAUNCH_CHECK("mca_gates_bwd"); return EGM_OK;
 }
 
 // final: dx = du * s/3 + (a_h + a_w + a_c) + (b_h + b_w + b_c) * x
 template <typename T, int V>
 __global__ void k_mca_bwd_dx(const T* __restrict__ du, const T* __restrict__ x, const float* __restrict__ gates, const float* __restrict__ ca,
-                             const float* __restrict__ cb, T* __restrict__ dx, int N, int H, int W, int CV, long long ow, long long oc) {
+                             const float* __restrict__ cb, T* __restrict__ dx, int N, int H, int W, int CV, long long ow, long long oc) { egm_pdl_enter();
   const int C = CV * V; long long total = (long long)N * H * W * CV;
   const NhwcIndexer ix(CV, W, H, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -457,7 +565,7 @@ extern "C" int egm_mca_bwd_dx(const void* du, const void* x, const float* gates,
   long long total = (long long)N * H * W * C;
   if (total == 0) return EGM_OK;
   int v = egm_pick_vec(C); if (v > 4) v = 4;
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_mca_bwd_dx<T, (V > 4 ? 4 : V)><<<egm_grid_for(total / v, 256), 256, 0, (cudaStream_t)stream>>>(
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_mca_bwd_dx<T, (V > 4 ? 4 : V)>, egm_grid_for(total / v, 256), 256, 0, (cudaStream_t)stream, 
       (const T*)du, (const T*)x, gates, coef_a, coef_b, (T*)dx, N, H, W, C / v, mca_ow(N, H), mca_oc(N, H, W)))));
   EGM_LAUNCH_CHECK("mca_bwd_dx"); return EGM_OK;
 }

@@ -68,7 +68,7 @@ __device__ __forceinline__ void st4(float* p, const float (&f)[4]) { *reinterpre
 // ===================================================================================== forward
 // smem: U[5][TX][CC] (ring over rows: r, r-1, r-2, r-3 are read while r+1 is written) | D[2][TX][CC]
 template <typename T>
-__global__ void __launch_bounds__(mf::THREADS, MF_MINB_FWD) k_mca_fwd(const T* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ idx, McaFusedParams g) {
+__global__ void __launch_bounds__(mf::THREADS, MF_MINB_FWD) k_mca_fwd(const T* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ idx, McaFusedParams g) { egm_pdl_enter();
   using namespace mf;
   extern __shared__ float sm[];
   float* U = sm;
@@ -235,7 +235,7 @@ extern "C" int egm_mca_fwd(const void* x, const float* gates, void* y, unsigned 
   EGM_DISPATCH_DTYPE(dtype, {
     static bool attr[64] = {};
     egm_ensure_smem(k_mca_fwd<T>, (int)smb, attr);
-    k_mca_fwd<T><<<grid, mf::THREADS, smb, (cudaStream_t)stream>>>((const T*)x, (T*)y, argidx, g);
+    egm_launch(k_mca_fwd<T>, grid, mf::THREADS, smb, (cudaStream_t)stream, (const T*)x, (T*)y, argidx, g);
   });
   EGM_LAUNCH_CHECK("mca_fwd"); return EGM_OK;
 }
@@ -248,7 +248,7 @@ extern "C" int egm_mca_fwd(const void* x, const float* gates, void* y, unsigned 
 //   IX [6][TX][CV] u32    arg codes of the same rows
 template <typename T>
 __global__ void __launch_bounds__(mf::THREADS, MF_MINB_BWD) k_mca_bwd(const T* __restrict__ x, const T* __restrict__ dy, const unsigned char* __restrict__ idx,
-                                                           T* __restrict__ du, McaFusedParams g) {
+                                                           T* __restrict__ du, McaFusedParams g) { egm_pdl_enter();
   using namespace mf;
   extern __shared__ float sm[];
   float* U = sm;
@@ -397,7 +397,7 @@ extern "C" int egm_mca_bwd(const void* x, const float* gates, const void* dy, co
   EGM_DISPATCH_DTYPE(dtype, {
     static bool attr[64] = {};
     egm_ensure_smem(k_mca_bwd<T>, (int)smb, attr);
-    k_mca_bwd<T><<<grid, mf::THREADS, smb, (cudaStream_t)stream>>>((const T*)x, (const T*)dy, argidx, (T*)du, g);
+    egm_launch(k_mca_bwd<T>, grid, mf::THREADS, smb, (cudaStream_t)stream, (const T*)x, (const T*)dy, argidx, (T*)du, g);
   });
   EGM_LAUNCH_CHECK("mca_bwd"); return EGM_OK;
 }
@@ -411,7 +411,7 @@ constexpr int TX = 32, HALO = 1, TW = TX - 2 * HALO, PF = 4;
 }
 template <typename T>
 __global__ void __launch_bounds__(mf::THREADS, 2) k_highpass3_walk(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C, int TH,
-                                                                  int accumulate) {
+                                                                  int accumulate) { egm_pdl_enter();
   using mf::CC; using mf::V; using mf::CV; using mf::ROW;
   using namespace hp;
   extern __shared__ float sm[];
@@ -488,8 +488,8 @@ int egm_highpass3_walk_launch(const void* in, void* out, int accumulate, int dty
   dim3 grid(cdiv(W, hp::TW), cdiv(H, TH), N * (C / mf::CC));
   if (grid.y > 65535) return 0;
   const size_t smb = (size_t)2 * mf::ROW * sizeof(float);
-  if (dtype == EGM_F32) k_highpass3_walk<float><<<grid, mf::THREADS, smb, st>>>((const float*)in, (float*)out, N, H, W, C, TH, accumulate);
-  else if (dtype == EGM_BF16) k_highpass3_walk<__nv_bfloat16><<<grid, mf::THREADS, smb, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, N, H, W, C, TH, accumulate);
+  if (dtype == EGM_F32) egm_launch(k_highpass3_walk<float>, grid, mf::THREADS, smb, st, (const float*)in, (float*)out, N, H, W, C, TH, accumulate);
+  else if (dtype == EGM_BF16) egm_launch(k_highpass3_walk<__nv_bfloat16>, grid, mf::THREADS, smb, st, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, N, H, W, C, TH, accumulate);
   else return 0;
   return 1;
 }

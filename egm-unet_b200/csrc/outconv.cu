@@ -11,7 +11,7 @@ constexpr int OC_MAXK = 4;
 
 template <typename T, int C, int K>
 __global__ void __launch_bounds__(256) k_outconv_fwd(const T* __restrict__ y, const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ logits,
-                                                     long long HW, long long total) {
+                                                     long long HW, long long total) { egm_pdl_enter();
   __shared__ float sw[K * C + K];
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < K) sw[K * C + threadIdx.x] = b ? b[threadIdx.x] : 0.f;
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) k_outconv_fwd(const T* __restrict__ y, co
 // dy[p][c] = sum_k dl[k][p] w[k][c];  dw[k][c] += sum_p dl[k][p] y[p][c];  db[k] += sum_p dl[k][p]     (dw / db zeroed by the launcher)
 template <typename T, int C, int K>
 __global__ void __launch_bounds__(256) k_outconv_bwd(const T* __restrict__ y, const float* __restrict__ w, const float* __restrict__ dl, T* __restrict__ dy,
-                                                     float* __restrict__ dw, float* __restrict__ db, long long HW, long long total) {
+                                                     float* __restrict__ dw, float* __restrict__ db, long long HW, long long total) { egm_pdl_enter();
   __shared__ float sw[K * C];
   __shared__ float red[8][K * C + K];
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) sw[i] = w[i];
@@ -104,7 +104,7 @@ extern "C" int egm_outconv_fwd(const void* y, const float* w, const float* bias,
   const long long total = (long long)N * HW;
   if (total == 0) return EGM_OK;
   const int grid = egm_grid_for(total, 256);
-  EGM_DISPATCH_DTYPE(dtype, EGM_OC_DISPATCH(C, K, (k_outconv_fwd<T, CC, KK><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)y, w, bias, logits, HW, total))));
+  EGM_DISPATCH_DTYPE(dtype, EGM_OC_DISPATCH(C, K, (egm_launch(k_outconv_fwd<T, CC, KK>, grid, 256, 0, (cudaStream_t)stream, (const T*)y, w, bias, logits, HW, total))));
   EGM_LAUNCH_CHECK("outconv_fwd"); return EGM_OK;
 }
 // dlogits [N,K,H,W] fp32 -> dy [N,H,W,C] (dtype; NULL to skip), dw [K][C] fp32, dbias [K] fp32 (NULL to skip); dw / dbias are overwritten
@@ -117,6 +117,6 @@ extern "C" int egm_outconv_bwd(const void* y, const float* w, const float* dlogi
   const long long total = (long long)N * HW;
   if (total == 0) return EGM_OK;
   const int grid = egm_grid_for(total, 256, 4);
-  EGM_DISPATCH_DTYPE(dtype, EGM_OC_DISPATCH(C, K, (k_outconv_bwd<T, CC, KK><<<grid, 256, 0, st>>>((const T*)y, w, dlogits, (T*)dy, dw, dbias, HW, total))));
+  EGM_DISPATCH_DTYPE(dtype, EGM_OC_DISPATCH(C, K, (egm_launch(k_outconv_bwd<T, CC, KK>, grid, 256, 0, st, (const T*)y, w, dlogits, (T*)dy, dw, dbias, HW, total))));
   EGM_LAUNCH_CHECK("outconv_bwd"); return EGM_OK;
 }

@@ -37,7 +37,7 @@ __device__ __forceinline__ int hpass(const PipeArgs& a, int row, int fx, int c) 
   return clip8(acc);
 }
 
-__global__ void __launch_bounds__(256) k_input_transform(PipeArgs a) {
+__global__ void __launch_bounds__(256) k_input_transform(PipeArgs a) { egm_pdl_enter();
   const long long total = (long long)a.OH * a.OW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int oy = (int)(i / a.OW), ox = (int)(i - (long long)oy * a.OW);
@@ -81,6 +81,6 @@ extern "C" int egm_input_transform(const unsigned char* img, const unsigned char
   if ((long long)out_h * out_w == 0) return EGM_OK;
   PipeArgs a{img, mask, H, W, rh, rw, hmin, hcnt, hk, hks, vmin, vcnt, vk, vks, nnx, nny, hflip, vflip, top, left, valid_h, valid_w, out_h, out_w,
              {mean_std_host[0], mean_std_host[1], mean_std_host[2]}, {mean_std_host[3], mean_std_host[4], mean_std_host[5]}, out_img, out_tgt};
-  k_input_transform<<<egm_grid_for((long long)out_h * out_w, 256, 8), 256, 0, (cudaStream_t)stream>>>(a);
+  egm_launch(k_input_transform, egm_grid_for((long long)out_h * out_w, 256, 8), 256, 0, (cudaStream_t)stream, a);
   EGM_LAUNCH_CHECK("input_transform"); return EGM_OK;
 }

@@ -6,14 +6,14 @@
 
 // ------------------------------------------------------------------ max pool 2x2 s2
 template <typename T, int V>
-__global__ void k_maxpool2_fwd(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int CV) {
+__global__ void k_maxpool2_fwd(const T* __restrict__ x, long long xcs, long long xco, T* __restrict__ y, int N, int H, int W, int CV) { egm_pdl_enter();
   const int Ho = H / 2, Wo = W / 2, C = CV * V;
   long long total = (long long)N * Ho * Wo * CV;
   const NhwcIndexer ix(CV, Wo, Ho, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const Nhwc4 e = ix(i); const int cv = e.cv, wo = e.w, ho = e.h, n = e.n; const long long p = e.p;
-    const T* b = x + (((long long)n * H + 2 * ho) * W + 2 * wo) * C + cv * V;
-    FVec<V> a = ldv<V>(b), c1 = ldv<V>(b + C), c2 = ldv<V>(b + (long long)W * C), c3 = ldv<V>(b + (long long)W * C + C), o;
+    const T* b = x + (((long long)n * H + 2 * ho) * W + 2 * wo) * xcs + xco + cv * V;
+    FVec<V> a = ldv<V>(b), c1 = ldv<V>(b + xcs), c2 = ldv<V>(b + (long long)W * xcs), c3 = ldv<V>(b + (long long)W * xcs + xcs), o;
 #pragma unroll
     for (int j = 0; j < V; ++j) o.v[j] = fmaxf(fmaxf(a.v[j], c1.v[j]), fmaxf(c2.v[j], c3.v[j]));
     stv<V>(y + p * C + cv * V, o);
@@ -21,17 +21,18 @@ __global__ void k_maxpool2_fwd(const T* __restrict__ x, T* __restrict__ y, int N
 }
 // gradient goes to the FIRST maximum in (h, w) scan order (ATen tie rule)
 template <typename T, int V>
-__global__ void k_maxpool2_bwd(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W, int CV, int accumulate) {
+__global__ void k_maxpool2_bwd(const T* __restrict__ x, long long xcs, long long xco, const T* __restrict__ dy, T* __restrict__ dx, long long dcs, long long dco,
+                               int N, int H, int W, int CV, int accumulate) { egm_pdl_enter();
   const int Ho = H / 2, Wo = W / 2, C = CV * V;
   long long total = (long long)N * Ho * Wo * CV;
   const NhwcIndexer ix(CV, Wo, Ho, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const Nhwc4 e = ix(i); const int cv = e.cv, wo = e.w, ho = e.h, n = e.n; const long long p = e.p;
-    long long base = (((long long)n * H + 2 * ho) * W + 2 * wo) * C + cv * V;
-    long long off[4] = {0, C, (long long)W * C, (long long)W * C + C};
+    const long long pix = ((long long)n * H + 2 * ho) * W + 2 * wo;
+    const long long pofs[4] = {0, 1, (long long)W, (long long)W + 1};
     FVec<V> v[4], g = ldv<V>(dy + p * C + cv * V);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) v[t] = ldv<V>(x + base + off[t]);
+    for (int t = 0; t < 4; ++t) v[t] = ldv<V>(x + (pix + pofs[t]) * xcs + xco + cv * V);
     int arg[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -43,29 +44,43 @@ __global__ void k_maxpool2_bwd(const T* __restrict__ x, const T* __restrict__ dy
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       FVec<V> o;
-      if (accumulate) o = ldv<V>(dx + base + off[t]);
+      T* dp = dx + (pix + pofs[t]) * dcs + dco + cv * V;
+      if (accumulate) o = ldv<V>(dp);
 #pragma unroll
       for (int j = 0; j < V; ++j) o.v[j] = (accumulate ? o.v[j] : 0.f) + (arg[j] == t ? g.v[j] : 0.f);
-      stv<V>(dx + base + off[t], o);
+      stv<V>(dp, o);
     }
   }
 }
-extern "C" int egm_maxpool2x2_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream) {
+// x may be a channel-strided view (element (pixel, c) at x[pixel * x_cstride + x_coff + c]): the first skip connection of the U lives
+// inside the Up level's concat buffer (egm_upsample_concat_fwd with skip == NULL) and is pooled from there.
+extern "C" int egm_maxpool2x2_fwd_view(const void* x, long long x_cstride, long long x_coff, void* y, int dtype, int N, int H, int W, int C, void* stream) {
   long long total = (long long)N * (H / 2) * (W / 2) * C;
   if (total == 0) return EGM_OK;
-  int v = egm_pick_vec(C);
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_maxpool2_fwd<T, V><<<egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, N, H, W, C / V))));
+  int v = egm_pick_vec(C, x_cstride, x_coff);
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_maxpool2_fwd<T, V>, egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream,
+      (const T*)x, x_cstride, x_coff, (T*)y, N, H, W, C / V))));
   EGM_LAUNCH_CHECK("maxpool2x2_fwd"); return EGM_OK;
 }
-extern "C" int egm_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int accumulate, int dtype, int N, int H, int W, int C, void* stream) {
+extern "C" int egm_maxpool2x2_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream) {
+  return egm_maxpool2x2_fwd_view(x, C, 0, y, dtype, N, H, W, C, stream);
+}
+// dx may be a channel-strided view as well (the gradient of the concat buffer); accumulate = 0 needs a dense dx.
+extern "C" int egm_maxpool2x2_bwd_view(const void* x, long long x_cstride, long long x_coff, const void* dy, void* dx, long long dx_cstride, long long dx_coff,
+                                       int accumulate, int dtype, int N, int H, int W, int C, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   size_t es = dtype == EGM_F32 ? 4 : 2;
+  EGM_REQUIRE(accumulate || (dx_cstride == C && dx_coff == 0), EGM_E_BADARG, "maxpool2x2_bwd: a strided dx must be accumulated into");
   if (!accumulate && ((H & 1) || (W & 1))) cudaMemsetAsync(dx, 0, (size_t)N * H * W * C * es, st);   // dropped trailing row/col gets no gradient
   long long total = (long long)N * (H / 2) * (W / 2) * C;
   if (total == 0) return EGM_OK;
-  int v = egm_pick_vec(C);
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_maxpool2_bwd<T, V><<<egm_grid_for(total / V, 256), 256, 0, st>>>((const T*)x, (const T*)dy, (T*)dx, N, H, W, C / V, accumulate))));
+  int v = egm_pick_vec(C, x_cstride, x_coff), v2 = egm_pick_vec(C, dx_cstride, dx_coff); if (v2 < v) v = v2;
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_maxpool2_bwd<T, V>, egm_grid_for(total / V, 256), 256, 0, st,
+      (const T*)x, x_cstride, x_coff, (const T*)dy, (T*)dx, dx_cstride, dx_coff, N, H, W, C / V, accumulate))));
   EGM_LAUNCH_CHECK("maxpool2x2_bwd"); return EGM_OK;
+}
+extern "C" int egm_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int accumulate, int dtype, int N, int H, int W, int C, void* stream) {
+  return egm_maxpool2x2_bwd_view(x, C, 0, dy, dx, C, 0, accumulate, dtype, N, H, W, C, stream);
 }
 
 // ------------------------------------------------------------------ bilinear x2 (align_corners=True) + pad + concat
@@ -76,12 +91,13 @@ __device__ __forceinline__ void up_src(int o, int in, float scale, int& i0, int&
   i0 = (int)src; ip = (i0 < in - 1) ? 1 : 0; l1 = src - (float)i0; l0 = 1.f - l1;
 }
 template <typename T, int V>
-__global__ void k_upcat_fwd(const T* __restrict__ skip, const T* __restrict__ low, T* __restrict__ out, UpGeom g) {
-  const int C = g.Cs + g.Cu, CV = C / V;
+__global__ void k_upcat_fwd(const T* __restrict__ skip, const T* __restrict__ low, T* __restrict__ out, UpGeom g) { egm_pdl_enter();
+  // skip == nullptr: the skip half of `out` was written in place by its producer; only the up-sampled channels are produced here
+  const int C = g.Cs + g.Cu, c_begin = skip ? 0 : g.Cs, CV = (C - c_begin) / V;
   long long total = (long long)g.N * g.H * g.W * CV;
   const NhwcIndexer ix(CV, g.W, g.H, total);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const Nhwc4 e = ix(i); const int c = e.cv * V, w = e.w, h = e.h, n = e.n; const long long p = e.p;
+    const Nhwc4 e = ix(i); const int c = c_begin + e.cv * V, w = e.w, h = e.h, n = e.n; const long long p = e.p;
     FVec<V> o;
     if (c < g.Cs) o = ldv<V>(skip + p * g.Cs + c);
     else {
@@ -104,7 +120,7 @@ __global__ void k_upcat_fwd(const T* __restrict__ skip, const T* __restrict__ lo
 }
 // gather form of the transpose: each low-res pixel sums the (<= 6x6) high-res pixels that read it
 template <typename T, int V>
-__global__ void k_upcat_bwd_low(const T* __restrict__ dcat, T* __restrict__ dlow, UpGeom g) {
+__global__ void k_upcat_bwd_low(const T* __restrict__ dcat, T* __restrict__ dlow, UpGeom g) { egm_pdl_enter();
   const int C = g.Cs + g.Cu, CV = g.Cu / V;
   long long total = (long long)g.N * g.Hl * g.Wl * CV;
   const NhwcIndexer ix(CV, g.Wl, g.Hl, total);
@@ -151,13 +167,14 @@ static int up_geom(UpGeom& g, int N, int Hl, int Wl, int H, int W, int Cs, int C
              2 * Hl > 1 ? (float)(Hl - 1) / (float)(2 * Hl - 1) : 0.f, 2 * Wl > 1 ? (float)(Wl - 1) / (float)(2 * Wl - 1) : 0.f};
   return EGM_OK;
 }
-// out[N,H,W,Cs+Cu] = cat([skip[N,H,W,Cs], pad(upsample2x(low[N,Hl,Wl,Cu]))])
+// out[N,H,W,Cs+Cu] = cat([skip[N,H,W,Cs], pad(upsample2x(low[N,Hl,Wl,Cu]))]);  skip == NULL: out[..., :Cs] already holds the skip
+// (its producer wrote it in place -- the concat is virtual) and only out[..., Cs:] is written
 extern "C" int egm_upsample_concat_fwd(const void* skip, const void* low, void* out, int dtype, int N, int Hl, int Wl, int H, int W, int Cs, int Cu, void* stream) {
   UpGeom g; int e = up_geom(g, N, Hl, Wl, H, W, Cs, Cu); if (e) return e;
-  long long total = (long long)N * H * W * (Cs + Cu);
+  long long total = (long long)N * H * W * (skip ? Cs + Cu : Cu);
   if (total == 0) return EGM_OK;
   int v = egm_pick_vec(Cs); int v2 = egm_pick_vec(Cu); if (v2 < v) v = v2;
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_upcat_fwd<T, V><<<egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream>>>((const T*)skip, (const T*)low, (T*)out, g))));
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_upcat_fwd<T, V>, egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream, (const T*)skip, (const T*)low, (T*)out, g))));
   EGM_LAUNCH_CHECK("upsample_concat_fwd"); return EGM_OK;
 }
 // dlow[N,Hl,Wl,Cu] = transpose of the bilinear part applied to dcat[..., Cs:]; the skip part is a plain slice (egm_copy_slice).
@@ -166,7 +183,7 @@ extern "C" int egm_upsample_concat_bwd_low(const void* dcat, void* dlow, int dty
   long long total = (long long)N * Hl * Wl * Cu;
   if (total == 0) return EGM_OK;
   int v = egm_pick_vec(Cu, Cs + Cu, Cs);
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_upcat_bwd_low<T, V><<<egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dcat, (T*)dlow, g))));
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_upcat_bwd_low<T, V>, egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream, (const T*)dcat, (T*)dlow, g))));
   EGM_LAUNCH_CHECK("upsample_concat_bwd_low"); return EGM_OK;
 }
 
@@ -174,7 +191,7 @@ extern "C" int egm_upsample_concat_bwd_low(const void* dcat, void* dlow, int dty
 // (UNet(bilinear=False): src/unet.py:35-37).  The GEMM is a 1x1 conv with the re-laid-out weight
 //   wT[(a*2+b)*Cout + co][ci] = W[ci][co][a][b]        (mode 0: W -> wT,  mode 1: wT -> W, used for the gradient)
 // and the kernels below scatter / gather its [N,Hl,Wl,4*Cout] output into the up-sampled half of the concat tensor.
-__global__ void k_deconv_wpack(float* __restrict__ w, float* __restrict__ wt, int Cin, int Cout, int mode) {
+__global__ void k_deconv_wpack(float* __restrict__ w, float* __restrict__ wt, int Cin, int Cout, int mode) { egm_pdl_enter();
   long long total = (long long)Cin * Cout * 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int ab = (int)(i & 3); long long q = i >> 2; int co = (int)(q % Cout); int ci = (int)(q / Cout);
@@ -185,12 +202,12 @@ __global__ void k_deconv_wpack(float* __restrict__ w, float* __restrict__ wt, in
 extern "C" int egm_deconv_weight_pack(float* w, float* wt, int Cin, int Cout, int mode, void* stream) {
   long long total = (long long)Cin * Cout * 4;
   if (total == 0) return EGM_OK;
-  k_deconv_wpack<<<egm_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, wt, Cin, Cout, mode);
+  egm_launch(k_deconv_wpack, egm_grid_for(total, 256), 256, 0, (cudaStream_t)stream, w, wt, Cin, Cout, mode);
   EGM_LAUNCH_CHECK("deconv_weight_pack"); return EGM_OK;
 }
 // out[N,H,W,Cs+Cu] = cat([skip, pad(pixel_shuffle(z[N,Hl,Wl,4*Cu]))])
 template <typename T, int V>
-__global__ void k_shufcat_fwd(const T* __restrict__ skip, const T* __restrict__ z, T* __restrict__ out, UpGeom g) {
+__global__ void k_shufcat_fwd(const T* __restrict__ skip, const T* __restrict__ z, T* __restrict__ out, UpGeom g) { egm_pdl_enter();
   const int C = g.Cs + g.Cu, CV = C / V;
   long long total = (long long)g.N * g.H * g.W * CV;
   const NhwcIndexer ix(CV, g.W, g.H, total);
@@ -213,7 +230,7 @@ __global__ void k_shufcat_fwd(const T* __restrict__ skip, const T* __restrict__ 
 }
 // dz[N,Hl,Wl,4*Cu] gathered from dcat[..., Cs:]
 template <typename T, int V>
-__global__ void k_shufcat_bwd(const T* __restrict__ dcat, T* __restrict__ dz, UpGeom g) {
+__global__ void k_shufcat_bwd(const T* __restrict__ dcat, T* __restrict__ dz, UpGeom g) { egm_pdl_enter();
   const int C = g.Cs + g.Cu, CV = g.Cu / V;
   long long total = (long long)g.N * g.Hl * g.Wl * 4 * CV;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -226,10 +243,10 @@ __global__ void k_shufcat_bwd(const T* __restrict__ dcat, T* __restrict__ dz, Up
 }
 extern "C" int egm_pixel_shuffle_concat_fwd(const void* skip, const void* z, void* out, int dtype, int N, int Hl, int Wl, int H, int W, int Cs, int Cu, void* stream) {
   UpGeom g; int e = up_geom(g, N, Hl, Wl, H, W, Cs, Cu); if (e) return e;
-  long long total = (long long)N * H * W * (Cs + Cu);
+  long long total = (long long)N * H * W * (skip ? Cs + Cu : Cu);
   if (total == 0) return EGM_OK;
   int v = egm_pick_vec(Cs); int v2 = egm_pick_vec(Cu); if (v2 < v) v = v2;
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_shufcat_fwd<T, V><<<egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream>>>((const T*)skip, (const T*)z, (T*)out, g))));
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_shufcat_fwd<T, V>, egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream, (const T*)skip, (const T*)z, (T*)out, g))));
   EGM_LAUNCH_CHECK("pixel_shuffle_concat_fwd"); return EGM_OK;
 }
 extern "C" int egm_pixel_shuffle_concat_bwd(const void* dcat, void* dz, int dtype, int N, int Hl, int Wl, int H, int W, int Cs, int Cu, void* stream) {
@@ -237,6 +254,6 @@ extern "C" int egm_pixel_shuffle_concat_bwd(const void* dcat, void* dz, int dtyp
   long long total = (long long)N * Hl * Wl * 4 * Cu;
   if (total == 0) return EGM_OK;
   int v = egm_pick_vec(Cu, Cs + Cu, Cs);
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (k_shufcat_bwd<T, V><<<egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dcat, (T*)dz, g))));
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_shufcat_bwd<T, V>, egm_grid_for(total / V, 256), 256, 0, (cudaStream_t)stream, (const T*)dcat, (T*)dz, g))));
   EGM_LAUNCH_CHECK("pixel_shuffle_concat_bwd"); return EGM_OK;
 }

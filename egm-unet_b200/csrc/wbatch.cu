@@ -20,7 +20,8 @@ struct EgmWJob {
   float* bpad;              // [CoutP] zero-padded (summed) bias (nullable)
   const float* dwp;         // [taps][CoutP][CinP] packed fp32 weight gradient written by egm_conv2d_wgrad_tc
   float* g[3];              // gradient destinations matching src[]
-  int kind;                 // 0 = plain / grouped / zero-padded ("lifted"); 1 = 1x1 conv of cat[x,x]: W[:, :C] + W[:, C:]; 2 = 7x7+5x5+3x3 merged
+  int kind;                 // 0 = plain / grouped / zero-padded ("lifted"); 1 = 1x1 conv of cat[x,x]: W[:, :C] + W[:, C:]; 2 = 7x7+5x5+3x3 merged;
+                            // 3 = 1x1 conv of (x - avgpool3 x) as one 3x3 conv (src is [Cout][Cin_g], kh = kw = 3; egm_highpass_compose)
   int Cout, Cin_g, groups;  // reference weight [Cout][Cin_g][kh][kw] (kind 1: src is [Cout][2*Cin_g])
   int kh, kw, CoutP, CinP;
   long long prep_begin;     // prefix sums of taps*CoutP*CinP   (prep element space)
@@ -51,6 +52,10 @@ __device__ __forceinline__ float job_weight(const EgmWJob& j, int co, int ci, in
   const int g = co / (j.Cout / j.groups), cil = ci - g * j.Cin_g;
   if (cil < 0 || cil >= j.Cin_g) return 0.f;
   const long long cc = (long long)co * j.Cin_g + cil;
+  if (j.kind == 3) {                                  // off-centre taps bf16(-w/9), centre -8x that: exact zero response to constants
+    const float wn = __bfloat162float(__float2bfloat16_rn(-j.src[0][cc] * (1.f / 9.f)));
+    return t == 4 ? -8.f * wn : wn;
+  }
   float v = j.src[0][cc * taps + t];
   if (j.kind == 2) {                                  // 7x7 (+)= centre-embedded 5x5, then 3x3 (same order as the eager path)
     const int r = t / 7, s = t - r * 7;
@@ -60,7 +65,7 @@ __device__ __forceinline__ float job_weight(const EgmWJob& j, int co, int ci, in
   return v;
 }
 
-__global__ void k_weight_prep_batch(const EgmWJob* __restrict__ jobs, int n, long long total) {
+__global__ void k_weight_prep_batch(const EgmWJob* __restrict__ jobs, int n, long long total) { egm_pdl_enter();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const EgmWJob& j = jobs[find_job(jobs, n, i, false)];
     const long long l = i - j.prep_begin;
@@ -80,10 +85,18 @@ __global__ void k_weight_prep_batch(const EgmWJob* __restrict__ jobs, int n, lon
   }
 }
 
-__global__ void k_wgrad_unpack_batch(const EgmWJob* __restrict__ jobs, int n, long long total) {
+__global__ void k_wgrad_unpack_batch(const EgmWJob* __restrict__ jobs, int n, long long total) { egm_pdl_enter();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const EgmWJob& j = jobs[find_job(jobs, n, i, true)];
     const long long l = i - j.unpack_begin;
+    if (j.kind == 3) {                                // one element per (co, ci): dw1 = sum_t k[t] * dw3[t]
+      const int cil3 = (int)(l % j.Cin_g), co3 = (int)(l / j.Cin_g);
+      float s3 = 0.f;
+#pragma unroll
+      for (int t3 = 0; t3 < 9; ++t3) s3 += j.dwp[((long long)t3 * j.CoutP + co3) * j.CinP + cil3] * (t3 == 4 ? 8.f / 9.f : -1.f / 9.f);
+      j.g[0][l] = s3;
+      continue;
+    }
     const int taps = j.kh * j.kw;
     const int t = (int)(l % taps); const long long cc = l / taps; const int cil = (int)(cc % j.Cin_g); const int co = (int)(cc / j.Cin_g);
     if (j.kind == 1) {                                // both halves of the [Cout][2C] weight receive the folded gradient
@@ -108,13 +121,13 @@ extern "C" int egm_wjob_bytes(void) { return (int)sizeof(EgmWJob); }
 extern "C" int egm_weight_prep_batch(const void* jobs, int n_jobs, long long total_elems, void* stream) {
   if (n_jobs <= 0 || total_elems <= 0) return EGM_OK;
   EGM_REQUIRE(jobs && ((uintptr_t)jobs & 7) == 0, EGM_E_BADARG, "weight_prep_batch: job table must be an 8-byte aligned device pointer");
-  k_weight_prep_batch<<<egm_grid_for(total_elems, 256), 256, 0, (cudaStream_t)stream>>>((const EgmWJob*)jobs, n_jobs, total_elems);
+  egm_launch(k_weight_prep_batch, egm_grid_for(total_elems, 256), 256, 0, (cudaStream_t)stream, (const EgmWJob*)jobs, n_jobs, total_elems);
   EGM_LAUNCH_CHECK("weight_prep_batch"); return EGM_OK;
 }
 
 extern "C" int egm_wgrad_unpack_batch(const void* jobs, int n_jobs, long long total_elems, void* stream) {
   if (n_jobs <= 0 || total_elems <= 0) return EGM_OK;
   EGM_REQUIRE(jobs && ((uintptr_t)jobs & 7) == 0, EGM_E_BADARG, "wgrad_unpack_batch: job table must be an 8-byte aligned device pointer");
-  k_wgrad_unpack_batch<<<egm_grid_for(total_elems, 256), 256, 0, (cudaStream_t)stream>>>((const EgmWJob*)jobs, n_jobs, total_elems);
+  egm_launch(k_wgrad_unpack_batch, egm_grid_for(total_elems, 256), 256, 0, (cudaStream_t)stream, (const EgmWJob*)jobs, n_jobs, total_elems);
   EGM_LAUNCH_CHECK("wgrad_unpack_batch"); return EGM_OK;
 }

@@ -61,6 +61,22 @@ class Var:
             call("axpby", self.grad, g, abi.DTYPE_CODE[g.dtype], g.numel(), 1.0, 1.0)
 
 
+class SkipView:
+    """A skip connection of the U that lives in channels [0, c) of its Up level's concat buffer `cat` ([N,H,W,c + c_up]).  The reference
+    materialises torch.cat([x2, x1]) in Up.forward (src/EGM-UNet.py:938-947); here the concat is virtual: the DoubleConv's last BN+ReLU
+    writes the skip straight into the buffer, MaxPool2d reads (and back-propagates into) the channel-strided view, and Up only adds
+    the up-sampled half.  Deliberately NOT a Var: an op that has no strided form fails loudly instead of reading a wrong layout."""
+    __slots__ = ("cat", "c")
+
+    def __init__(self, cat: "Var", c: int):
+        self.cat, self.c = cat, c
+
+    @property
+    def shape(self):
+        n, h, w, _ = self.cat.t.shape
+        return (n, h, w, self.c)
+
+
 class Ctx:
     """One forward(/backward) execution."""
 
@@ -77,7 +93,11 @@ class Ctx:
         self.f32 = dict(dtype=torch.float32, device=device)
         self.wplan: Optional["WeightPlan"] = None   # batched weight preparation (Trainer); None = per-conv pack kernels
         self.fuse_bn = os.environ.get("EGM_NO_BN_FUSE", "0") != "1"   # BN statistics / inference BN+ReLU in the conv epilogue
-        self.stats_all = os.environ.get("EGM_BN_STATS_ALL", "0") == "1"   # epilogue statistics wherever supported, not only where they win
+        self.virtual_skip = os.environ.get("EGM_NO_VIRTUAL_SKIP", "0") != "1"   # skip connections produced inside the Up concat buffers
+        self.fuse_edge = os.environ.get("EGM_NO_EDGE_FUSE", "0") != "1"   # edge enhancer: high-pass + 1x1 conv as one composed 3x3 tcgen05 conv
+        # epilogue statistics wherever the kernels support them (measured: 23.54 ms/step against 24.04 with the per-layer
+        # "profitable" rule, profiles/step_variants_r2.txt); EGM_BN_STATS_PROFITABLE=1 restores the rule
+        self.stats_all = os.environ.get("EGM_BN_STATS_PROFITABLE", "0") != "1"
         self._arena, self._arena_off = None, 0
 
     ARENA_DOUBLES = 1 << 16
@@ -246,7 +266,7 @@ class WeightPlan:
             rows.append(src[:3] + bsrc[:3] + [j.wf.data_ptr(), j.wd.data_ptr(), j.bpad.data_ptr() if need_b else 0, j.dwp.data_ptr()] + g[:3]
                         + [pack(j.spec.kind, co), pack(cig, j.spec.groups), pack(kh, kw), pack(j.coutp, j.cinp), pb, ub, 0])
             pb += n
-            ub += co * cig * taps
+            ub += co * cig * (1 if j.spec.kind == 3 else taps)
         self.prep_total, self.unpack_total = pb, ub
         if rows:
             self.table = torch.from_numpy(np.array(rows, dtype=np.uint64).view(np.int64)).to(device)
@@ -264,7 +284,7 @@ class WeightPlan:
                         r2 = list(row)
                         r2[18] = u2
                         sub.append(r2)
-                        u2 += co * cig * kh * kw
+                        u2 += co * cig * (1 if j.spec.kind == 3 else kh * kw)
                     self.bucket_tables[b] = (torch.from_numpy(np.array(sub, dtype=np.uint64).view(np.int64)).to(device), len(sub), u2)
         self.ready = True
 
@@ -606,25 +626,49 @@ def conv_bn_act(ctx: Ctx, x: Var, conv: nn.Conv2d, bn: nn.BatchNorm2d, act: int,
 
 
 # =========================================================================== pooling / upsampling
-def maxpool2(ctx: Ctx, x: Var) -> Var:
+def maxpool2(ctx: Ctx, x) -> Var:
+    """MaxPool2d(2, 2); `x` may be a SkipView (read / back-propagated through the channel-strided view of the concat buffer)."""
     n, h, w, c = x.shape
+    view = isinstance(x, SkipView)
+    xt, xcs = (x.cat.t, x.cat.C) if view else (x.t, c)
     y = Var(ctx.empty(n, h // 2, w // 2, c))
-    call("maxpool2x2_fwd", x.t, y.t, ctx.code, n, h, w, c)
+    call("maxpool2x2_fwd_view", xt, xcs, 0, y.t, ctx.code, n, h, w, c)
     if ctx.record:
         def bwd():
             dy, y.grad = y.grad, None
-            if dy is None or not x.needs_grad:
+            if dy is None:
+                return
+            if view:      # the Up block's backward ran first and left the gradient of the whole concat buffer in x.cat.grad
+                assert x.cat.grad is not None, "SkipView: the concat buffer has no gradient yet"
+                call("maxpool2x2_bwd_view", xt, xcs, 0, dy, x.cat.grad, xcs, 0, 1, ctx.code, n, h, w, c)
+                return
+            if not x.needs_grad:
                 return
             gx, acc = x.grad_target()
-            call("maxpool2x2_bwd", x.t, dy, gx, acc, ctx.code, n, h, w, c)
+            call("maxpool2x2_bwd_view", xt, xcs, 0, dy, gx, c, 0, acc, ctx.code, n, h, w, c)
         ctx.push(bwd)
     return y
 
 
-def upsample_concat(ctx: Ctx, low: Var, skip: Var) -> Var:
-    """cat([skip, pad(bilinear_x2(low))], channel)  -- Up.forward of the reference up to the DoubleConv."""
+def upsample_concat(ctx: Ctx, low: Var, skip) -> Var:
+    """cat([skip, pad(bilinear_x2(low))], channel)  -- Up.forward of the reference up to the DoubleConv.  With a SkipView the skip
+    half is already in place: only the up-sampled channels are written, and the backward needs no slice copy."""
     n, hl, wl, cu = low.shape
     _, h, w, cs = skip.shape
+    if isinstance(skip, SkipView):
+        out = skip.cat
+        assert out.C == cs + cu, (out.shape, cs, cu)
+        call("upsample_concat_fwd", None, low.t, out.t, ctx.code, n, hl, wl, h, w, cs, cu)
+        if ctx.record:
+            def bwd_v():
+                d = out.grad          # stays: MaxPool and the skip's producer still add to / read channels [0, cs)
+                if d is None:
+                    return
+                gl = ctx.empty(n, hl, wl, cu)
+                call("upsample_concat_bwd_low", d, gl, ctx.code, n, hl, wl, h, w, cs, cu)
+                low.accum(gl)
+            ctx.push(bwd_v)
+        return out
     out = Var(ctx.empty(n, h, w, cs + cu))
     call("upsample_concat_fwd", skip.t, low.t, out.t, ctx.code, n, hl, wl, h, w, cs, cu)
     if ctx.record:
@@ -720,8 +764,30 @@ def release_grad(ctx: Ctx, v: Var):
 
 # =========================================================================== EdgeAwareFeatureEnhancer
 def edge_enhancer(ctx: Ctx, x: Var, m) -> Var:
-    """src/EGM-UNet.py:872-886: y = sigmoid(BN(conv1x1(x - avgpool3(x)))) * x + x."""
+    """src/EGM-UNet.py:872-886: y = sigmoid(BN(conv1x1(x - avgpool3(x)))) * x + x.
+
+    bf16 / tcgen05 path, C <= 64 (the halo kernel's range -- the large maps): x - avgpool3(x) is a zero-padded depthwise 3x3 filter, so
+    high-pass + 1x1 conv run as ONE 3x3 tcgen05 conv with the composed weight (egm_highpass_compose / WeightPlan kind 3): the TMA-staged
+    halo tile feeds the MMAs directly, the BN batch statistics come out of the conv epilogue, and the gate is applied in the second
+    (unavoidable: it needs the batch statistics) pass.  The high-pass tensor, its backward pass and 4 HBM round trips are gone.
+    Wider maps (C >= 128, 120^2 and below) keep the row-walking high-pass kernel + 1x1 conv: there a 3x3 conv costs more than it saves."""
     n, h, w, c = x.shape
+    conv, bn = m.weight_generator[0], m.weight_generator[1]
+    if ctx.use_tc and ctx.fuse_edge and c % 16 == 0 and c <= 64 and conv.groups == 1 and abi.query("conv2d_tc_supported", c, c, 3, 3, 1, 1):
+        spec = WSpec(3, (conv.weight,), (conv.bias,), (c, c, 3, 3))
+        planned = ctx.wplan is not None and ctx.wplan.ready and ctx.record and spec.key in ctx.wplan.jobs
+        training = ctx.training or bn.running_mean is None
+        epi = Epi(stats=True) if (ctx.fuse_bn and training and x.M > 0 and abi.query("conv2d_tc_stats_supported", c, c, 3, 3, 1)) else None
+        if planned:
+            z = conv2d(ctx, x, None, conv.bias, wspec=spec, epi=epi)
+        else:
+            w3 = torch.empty(c, c, 3, 3, **ctx.f32)
+            call("highpass_compose", _p(conv.weight), w3, c * c, 0, 1)
+
+            def sink(dw3):
+                call("highpass_compose", ctx.grad_slot(conv.weight), dw3, c * c, 1, 0)
+            z = conv2d(ctx, x, w3, conv.bias, wgrad_sink=sink, wspec=spec, epi=epi)
+        return bn_act(ctx, z, bn, ACT_SIGMOID, MODE_EDGE_GATE, aux=x, sums=epi.sums if epi is not None else None)
     e = Var(ctx.empty(n, h, w, c))
     call("highpass3", x.t, e.t, 0, ctx.code, n, h, w, c)
     if ctx.record:
@@ -732,7 +798,7 @@ def edge_enhancer(ctx: Ctx, x: Var, m) -> Var:
             gx, acc = x.grad_target()
             call("highpass3", d, gx, acc, ctx.code, n, h, w, c)
         ctx.push(bwd)
-    return conv_bn_act(ctx, e, m.weight_generator[0], m.weight_generator[1], ACT_SIGMOID, MODE_EDGE_GATE, aux=x)
+    return conv_bn_act(ctx, e, conv, bn, ACT_SIGMOID, MODE_EDGE_GATE, aux=x)
 
 
 # =========================================================================== MCALayer

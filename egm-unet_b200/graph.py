@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import abi
 from .abi import call
-from .engine import (ACT_NONE, ACT_RELU, ACT_SIGMOID, MODE_PLAIN, MODE_RESIDUAL, Ctx, Var, WSpec, _p, bn_act, conv2d, conv_bn_act, conv_module,
+from .engine import (ACT_NONE, ACT_RELU, ACT_SIGMOID, MODE_PLAIN, MODE_RESIDUAL, Ctx, SkipView, Var, WSpec, _p, bn_act, conv2d, conv_bn_act, conv_module,
                      copy_into, deconv_concat, edge_enhancer, from_nchw, maxpool2, mca_layer, out_conv, release_grad, slice_channels, to_nchw,
                      upsample_concat)
 
@@ -223,18 +223,22 @@ def rga(ctx: Ctx, x: Var, m) -> Var:
 
 
 # =========================================================================== skeleton
-def double_conv(ctx: Ctx, x: Var, seq, i0: int = 0, i1: int = 3) -> Var:
-    """DoubleConv, src/EGM-UNet.py:44-55 == src/unet.py:7-18."""
+def double_conv(ctx: Ctx, x: Var, seq, i0: int = 0, i1: int = 3, skip_into: Optional[Var] = None):
+    """DoubleConv, src/EGM-UNet.py:44-55 == src/unet.py:7-18.  skip_into: the Up level's concat buffer -- the result is written into its
+    first channels and returned as a SkipView (virtual concat)."""
     x = conv_bn_act(ctx, x, seq[i0], seq[i0 + 1], ACT_RELU)
-    return conv_bn_act(ctx, x, seq[i1], seq[i1 + 1], ACT_RELU)
+    if skip_into is None:
+        return conv_bn_act(ctx, x, seq[i1], seq[i1 + 1], ACT_RELU)
+    conv_bn_act(ctx, x, seq[i1], seq[i1 + 1], ACT_RELU, out=skip_into, out_coff=0)
+    return SkipView(skip_into, seq[i1].out_channels)
 
 
-def down_block(ctx: Ctx, x: Var, down, variant: str) -> Var:
+def down_block(ctx: Ctx, x, down, variant: str, skip_into: Optional[Var] = None):
     """Down: src/unet.py:21-26 ('unet'), src/EGM-UNet.py:888-912 ('egm'), src/yuanGRFBUNet.py:859-883 ('yuan')."""
     x = maxpool2(ctx, x)
     seq = down[1]
     if variant == "unet":
-        return double_conv(ctx, x, seq)
+        return double_conv(ctx, x, seq, skip_into=skip_into)
     x = conv_bn_act(ctx, x, seq[0], seq[1], ACT_RELU)
     if variant == "egm":
         x = mca_layer(ctx, x, seq[3])
@@ -245,21 +249,34 @@ def down_block(ctx: Ctx, x: Var, down, variant: str) -> Var:
     return grfb(ctx, x, seq[gi])
 
 
-def up_block(ctx: Ctx, low: Var, skip: Var, up) -> Var:
+def up_block(ctx: Ctx, low: Var, skip, up) -> Var:
     """Up (bilinear): src/EGM-UNet.py:927-949 == src/unet.py:29-51."""
     if isinstance(up.up, nn.Upsample):
         return double_conv(ctx, upsample_concat(ctx, low, skip), up.conv)
     return double_conv(ctx, deconv_concat(ctx, low, skip, up.up), up.conv)
 
 
+def _skip_buffer(ctx: Ctx, n: int, h: int, w: int, cs: int, up, producer_ok: bool) -> Optional[Var]:
+    """Concat buffer of one Up level, allocated when its skip connection is PRODUCED (virtual concat), or None where the skip's producer
+    cannot write into a channel slice (the GRFB tail of the EGM / yuan Down blocks) or Up is a transposed conv."""
+    if not (ctx.virtual_skip and producer_ok and isinstance(up.up, nn.Upsample)):
+        return None
+    cat = Var(ctx.empty(n, h, w, up.conv[0].in_channels))
+    assert cat.C > cs
+    release_grad(ctx, cat)            # pushed before every user => runs after all of them in backward
+    return cat
+
+
 def net_forward(ctx: Ctx, model, x_nchw: torch.Tensor, variant: str):
     """GRFBUNet.forward (src/EGM-UNet.py:1527-1541) / UNet.forward (src/unet.py:84-96).
     Returns (logits NCHW fp32, logits Var)."""
     x = from_nchw(ctx, x_nchw)
-    x1 = double_conv(ctx, x, model.in_conv)
-    x2 = down_block(ctx, x1, model.down1, variant)
-    x3 = down_block(ctx, x2, model.down2, variant)
-    x4 = down_block(ctx, x3, model.down3, variant)
+    n, h, w, _ = x.shape
+    plain = variant == "unet"
+    x1 = double_conv(ctx, x, model.in_conv, skip_into=_skip_buffer(ctx, n, h, w, model.in_conv[3].out_channels, model.up4, True))
+    x2 = down_block(ctx, x1, model.down1, variant, _skip_buffer(ctx, n, h // 2, w // 2, model.down1[1][3].out_channels, model.up3, plain) if plain else None)
+    x3 = down_block(ctx, x2, model.down2, variant, _skip_buffer(ctx, n, h // 4, w // 4, model.down2[1][3].out_channels, model.up2, plain) if plain else None)
+    x4 = down_block(ctx, x3, model.down3, variant, _skip_buffer(ctx, n, h // 8, w // 8, model.down3[1][3].out_channels, model.up1, plain) if plain else None)
     x5 = down_block(ctx, x4, model.down4, variant)
     if variant != "unet":
         x5 = rga(ctx, x5, model.attn1)

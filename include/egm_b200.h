@@ -26,6 +26,11 @@ enum { EGM_OK = 0, EGM_E_BADARG = -1, EGM_E_SHAPE = -2, EGM_E_ALIGN = -3, EGM_E_
 int egm_abi_version(void);
 const char* egm_last_error(void);
 int egm_device_check(void);                       /* fails unless the current device is CC 10.x */
+/* Kernel-boundary overlap: every kernel of the library is launched with programmatic stream serialization (each kernel lets its
+ * successor's CTAs be scheduled early and waits for its predecessor's completion before its first global access), which removes the
+ * grid launch / drain latency between the ~820 dependent kernels of a step.  Results are identical either way; 0 restores plain
+ * stream order (A/B measurements).  Returns the previous setting.  (The reference's eager ATen launches have no counterpart.) */
+int egm_set_launch_overlap(int enabled);
 
 /* ---- layout / glue (replaces ATen copy_/cat/split/add kernels around src/EGM-UNet.py:1527-1541) ---- */
 int egm_nchw_to_nhwc(const float* x, void* y, int dtype, int N, int C, int H, int W, void* stream);
@@ -42,6 +47,10 @@ int egm_pack_conv_weight(const float* w, float* wf, float* wd, int Cout, int Cin
 int egm_unpack_conv_wgrad(const float* dw_packed, float* dw, int Cout, int Cin_g, int kh, int kw, float beta, void* stream);
 int egm_conv_weight_lift(float* w, float* wp, int Cout, int Cin_g, int groups, int taps, int CoutP, int CinP, int mode, void* stream);
 int egm_kernel_embed(float* big, float* small_, long long CoCi, int kb, int ks, int mode, int accumulate, void* stream);
+/* EdgeAwareFeatureEnhancer (src/EGM-UNet.py:872-886): x - AvgPool2d(3,1,1)(x) followed by the 1x1 conv is ONE 3x3 conv with
+ * w3[co][ci][t] = w1[co][ci] * (delta[t] - 1/9).  mode 0 builds w3 from w1 (round_bf16: off-centre taps rounded to bf16, centre = -8 * that,
+ * so the bf16 operand keeps the exact zero response to constant inputs); mode 1 reduces a w3-shaped gradient to dw1. */
+int egm_highpass_compose(float* w1, float* w3, long long CoCi, int mode, int round_bf16, void* stream);
 /* Batched form of the per-conv weight preparation / gradient extraction above (csrc/wbatch.cu): `jobs` is a DEVICE array of
  * n_jobs 160-byte EgmWJob records (layout documented in csrc/wbatch.cu and mirrored by engine.WeightPlan); one launch packs
  * every tcgen05 conv's bf16 forward/dgrad operands (+ padded / summed bias) from the fp32 master parameters of
@@ -127,6 +136,11 @@ int egm_channel_sum(const void* x, int dtype, long long M, int C, long long cstr
 /* ---- down / up sampling (nn.MaxPool2d :908, nn.Upsample+F.pad+cat :931-947) ---- */
 int egm_maxpool2x2_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream);
 int egm_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int accumulate, int dtype, int N, int H, int W, int C, void* stream);
+/* channel-strided forms: x (and dx) may be the first Cs channels of an Up level's concat buffer -- the skip connection is produced
+ * straight into cat([skip, up]) (src/EGM-UNet.py:938-947 materialises the cat; here it is virtual) and pooled from there */
+int egm_maxpool2x2_fwd_view(const void* x, long long x_cstride, long long x_coff, void* y, int dtype, int N, int H, int W, int C, void* stream);
+int egm_maxpool2x2_bwd_view(const void* x, long long x_cstride, long long x_coff, const void* dy, void* dx, long long dx_cstride, long long dx_coff,
+                            int accumulate, int dtype, int N, int H, int W, int C, void* stream);
 int egm_upsample_concat_fwd(const void* skip, const void* low, void* out, int dtype, int N, int Hl, int Wl, int H, int W, int Cs, int Cu, void* stream);
 int egm_upsample_concat_bwd_low(const void* dcat, void* dlow, int dtype, int N, int Hl, int Wl, int H, int W, int Cs, int Cu, void* stream);
 

@@ -301,3 +301,31 @@ def test_host_fed_pipelined_loop_equals_plain_steps():
             res.append(tr.run((i.pin_memory(), t.pin_memory()) for i, t in batches))
     assert len(res[1]) == 5
     assert all(abs(a - b) <= 1e-3 * abs(a) for a, b in zip(*res)), res
+
+
+@pytest.mark.parametrize("variant,hw,dtype", [("egm", (77, 101), "bf16"), ("unet", (77, 101), "bf16"), ("unet", (64, 48), "fp32"), ("egm", (64, 48), "fp32")])
+def test_virtual_skip_concat_equals_materialised_concat(variant, hw, dtype, monkeypatch):
+    """Up.forward's torch.cat([x2, x1]) (src/EGM-UNet.py:938-947): with the skip produced inside the concat buffer (SkipView: strided
+    BN+ReLU store, strided MaxPool read / gradient accumulation, Up writing only the up-sampled half) the step must equal the
+    materialised concat (EGM_NO_VIRTUAL_SKIP=1): identical logits, gradients equal up to the split-K atomics' summation order."""
+    import egm_unet_b200 as E
+    res = []
+    for off in ("0", "1"):
+        monkeypatch.setenv("EGM_NO_VIRTUAL_SKIP", off)
+        model = build(variant)
+        model.load_state_dict(synth.fill_state_dict(model.state_dict()))
+        model = model.cuda().train()
+        if dtype == "fp32":
+            model.set_check_mode(True)
+        image, target = synth.make_inputs(2, *hw)
+        out = model(image.cuda())["out"]
+        loss = E.criterion({"out": out}, target.cuda(), torch.tensor([1.0, 2.0]).cuda(), num_classes=2, ignore_index=255)
+        loss.backward()
+        torch.cuda.synchronize()
+        res.append((out.detach().cpu(), {k: p.grad.detach().cpu().clone() for k, p in model.named_parameters()}))
+    assert torch.equal(res[0][0], res[1][0])
+    tol = 1e-5 if dtype == "fp32" else 2e-2
+    for k in res[0][1]:
+        a, b = res[0][1][k], res[1][1][k]
+        if float(b.norm()) > 1e-6:
+            assert float((a - b).norm() / b.norm()) < tol, (k, float((a - b).norm() / b.norm()))

@@ -201,11 +201,50 @@ def test_mca_layer(C, hw, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-def test_edge_enhancer(dtype):
+@pytest.mark.parametrize("C,hw", [(16, (11, 13)), (32, (35, 29)), (64, (17, 40)), (128, (9, 10))])
+def test_edge_enhancer(C, hw, dtype):
+    """src/EGM-UNet.py:872-886.  bf16, C <= 64: high-pass + 1x1 conv run as ONE composed 3x3 tcgen05 conv (statistics in its epilogue);
+    fp32 and C = 128: row-walking high-pass kernel + 1x1 conv.  Both against the oracle (forward, dx, every parameter gradient)."""
     from egm_unet_b200 import engine as E
     from egm_unet_b200.models import EdgeAwareFeatureEnhancer
-    x = _q(_rand(2, 16, 11, 13), dtype)
-    _run_block(lambda c, v, m: E.edge_enhancer(c, v, m), lambda sd, p, t: O.edge_enhancer(sd, p, t, True, None), EdgeAwareFeatureEnhancer(16), x, dtype)
+    x = _q(_rand(2, C, *hw), dtype)
+    _run_block(lambda c, v, m: E.edge_enhancer(c, v, m), lambda sd, p, t: O.edge_enhancer(sd, p, t, True, None), EdgeAwareFeatureEnhancer(C), x, dtype)
+
+
+@pytest.mark.parametrize("C,hw", [(16, (24, 19)), (64, (33, 47))])
+def test_edge_enhancer_composed_conv_equals_highpass_then_conv(C, hw):
+    """The composed 3x3 conv (egm_highpass_compose) against the unfused bf16 path on the same inputs: same function, the unfused path
+    additionally rounds the high-pass tensor to bf16, so the two agree to bf16 rounding; a constant image gives exactly zero pre-BN
+    response in the composed form (centre weight == -8 x off-centre weight in bf16)."""
+    from egm_unet_b200 import engine as E
+    from egm_unet_b200.models import EdgeAwareFeatureEnhancer
+    from egm_unet_b200.abi import call
+    torch.manual_seed(5)
+    m = EdgeAwareFeatureEnhancer(C).cuda()
+    x = _q(_rand(2, C, *hw), torch.bfloat16)
+    g = _q(_rand(2, C, *hw, seed=9), torch.bfloat16)
+    res = []
+    for fuse in (True, False):
+        hs = Harness(torch.bfloat16, use_tc=True)
+        hs.ctx.fuse_edge = fuse
+        xv = hs.var(x)
+        yv = E.edge_enhancer(hs.ctx, xv, m)
+        y = hs.out(yv)
+        hs.backward(yv, g)
+        res.append((y, hs.grad(xv), hs.pgrad(m.weight_generator[0].weight).clone(), hs.pgrad(m.weight_generator[1].weight).clone()))
+    for a, b in zip(*res):
+        assert rel_err(a, b) < 2e-2, rel_err(a, b)
+    # exact zero response of the composed weight to a constant input
+    w1 = torch.randn(C, C, device="cuda")
+    w3 = torch.empty(C, C, 3, 3, device="cuda")
+    call("highpass_compose", w1, w3, C * C, 0, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(w3.bfloat16().float(), w3) and float(w3.double().sum(dim=(2, 3)).abs().max()) == 0.0
+    dw1 = torch.empty(C, C, device="cuda")
+    call("highpass_compose", dw1, w3, C * C, 1, 0)
+    torch.cuda.synchronize()
+    k = torch.full((3, 3), -1 / 9.0, device="cuda"); k[1, 1] = 8 / 9.0
+    assert rel_err(dw1.cpu(), (w3 * k).sum(dim=(2, 3)).cpu()) < 1e-6
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
