@@ -258,7 +258,7 @@ def main():
     ap.add_argument("--check-mode", action="store_true", help="fp32 check mode (not a bench number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
-    ap.add_argument("--no-pdl", action="store_true", help="plain stream order between kernels (A/B of the programmatic-dependent-launch overlap)")
+    ap.add_argument("--pdl", action="store_true", help="launch kernels with programmatic dependent launch (A/B switch; measured slower, off by default)")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel CUDA-event breakdown of one step here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -279,8 +279,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W_ = max(args.warmup, 3)
     K = args.steps
-    if args.no_pdl:
-        abi.query("set_launch_overlap", 0)
+    if args.pdl:
+        abi.query("set_launch_overlap", 1)
 
     model = (E.GRFBUNet if args.variant == "egm" else E.UNet)(3, 2, base_c=32)
     model.load_state_dict(synth.fill_state_dict(model.state_dict()))
@@ -428,7 +428,7 @@ def main():
                                        f"batch {args.batch}/GPU, 3x{H}x{W}, 2 classes", "global_batch": gb, "parallelism": f"dp{world}",
                            "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush needed"},
                 "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
-                "gpu_launches": int(launches), "cuda_graph": not args.no_graph, "launch_overlap_pdl": not args.no_pdl, "roofline": roof, "clocks": sampler.summary()}
+                "gpu_launches": int(launches), "cuda_graph": not args.no_graph, "launch_overlap_pdl": bool(args.pdl), "roofline": roof, "clocks": sampler.summary()}
         if cb is not None:
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)

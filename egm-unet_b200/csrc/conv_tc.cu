@@ -532,8 +532,9 @@ constexpr int HT_H = 16, HT_W = 8;
 // NG = epilogue warp GROUPS (4 warps each = the four TMEM lane quarters).  The epilogue of a tile is one dependent chain per warp
 // (accumulator wait -> tcgen05.ld -> convert -> store -> release: ~115 instructions at ~8 cycles each, ncu source view of the
 // 16->16 1x1 layer: the four epilogue warps were busy 80 % of the time while the TMA and MMA warps idled), so thin layers -- one to
-// nine MMAs per tile -- were bound by it.  With NG groups, group g takes the tiles g, g + NG, ... of its CTA (accumulator buffers
-// are handed out round-robin, so consecutive tiles are in different buffers anyway) and NG epilogues overlap.
+// nine MMAs per tile -- looked bound by it.  With NG groups, group g takes the tiles g, g + NG, ... of its CTA (accumulator buffers
+// are handed out round-robin, so consecutive tiles are in different buffers anyway) and NG epilogues overlap.  Measured neutral
+// (see launch_conv_halo), kept as a tuning knob.
 template <int EPI, int NG>
 __global__ void __launch_bounds__(64 + 128 * NG, 1) k_conv_tc_halo(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                                                                __nv_bfloat16* __restrict__ y, const float* __restrict__ bias, ConvHaloParams p) { egm_pdl_enter();
@@ -796,10 +797,11 @@ static int launch_conv_halo(const NhwcView& xv, const void* wpk, const float* bi
   size_t smem = wres + (size_t)p.stages * p.haloStride + 1024 + 1408 + (epi >= 16 ? 2 * 2048 : 0);
   int grid = p.numTiles < egm_num_sms() ? p.numTiles : egm_num_sms();
   p.stats = stats;
-  // two epilogue groups wherever the register file allows (320 threads x <= 204 registers); the 64-channel statistics epilogue keeps
-  // 128 running sums per thread and stays at one group.  EGM_EPI_GROUPS=1 forces one group (A/B measurements).
+  // EGM_EPI_GROUPS=2: two epilogue groups wherever the register file allows (320 threads x <= 204 registers; the 64-channel statistics
+  // epilogue keeps 128 running sums per thread and stays at one).  MEASURED NEUTRAL (profiles/step_variants_r2.txt: thin layers +-3 %,
+  // step 23.75 vs 23.75 ms) -- the epilogue warps look busy in the stall samples but are not the limiter -- so the default is one group.
   static int ng_max = 0;
-  if (!ng_max) { const char* e = getenv("EGM_EPI_GROUPS"); ng_max = e ? atoi(e) : 2; if (ng_max < 1 || ng_max > 2) ng_max = 2; }
+  if (!ng_max) { const char* e = getenv("EGM_EPI_GROUPS"); ng_max = e ? atoi(e) : 1; if (ng_max < 1 || ng_max > 2) ng_max = 1; }
   const int ng = (epi == 64 || p.nacc < 2) ? 1 : ng_max;
 #define EGM_LAUNCH_HALO_(E, G)                                                                             \
   {                                                                                                        \
@@ -880,8 +882,8 @@ extern "C" int egm_conv2d_tc_ex(const void* x, long long x_cstride, long long x_
   size_t smem = (size_t)p.stages * per + (p.wres ? (size_t)wresBytes : 0) + 1024 + 1024 + (epi >= 16 ? 2 * 2048 : 0);
   int grid = p.numTiles < egm_num_sms() ? p.numTiles : egm_num_sms();
   p.stats = stats;
-  static int ng_max = 0;                              // epilogue groups (see k_conv_tc_halo); EGM_EPI_GROUPS=1 forces one
-  if (!ng_max) { const char* e = getenv("EGM_EPI_GROUPS"); ng_max = e ? atoi(e) : 2; if (ng_max < 1 || ng_max > 2) ng_max = 2; }
+  static int ng_max = 0;                              // epilogue groups (see launch_conv_halo): EGM_EPI_GROUPS=2, measured neutral, default 1
+  if (!ng_max) { const char* e = getenv("EGM_EPI_GROUPS"); ng_max = e ? atoi(e) : 1; if (ng_max < 1 || ng_max > 2) ng_max = 1; }
   const int ng = epi == 64 ? 1 : ng_max;
 #define EGM_LAUNCH_TC_(E, G)                                                                                      \
   {                                                                                                               \

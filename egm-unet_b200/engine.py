@@ -93,7 +93,10 @@ class Ctx:
         self.f32 = dict(dtype=torch.float32, device=device)
         self.wplan: Optional["WeightPlan"] = None   # batched weight preparation (Trainer); None = per-conv pack kernels
         self.fuse_bn = os.environ.get("EGM_NO_BN_FUSE", "0") != "1"   # BN statistics / inference BN+ReLU in the conv epilogue
-        self.virtual_skip = os.environ.get("EGM_NO_VIRTUAL_SKIP", "0") != "1"   # skip connections produced inside the Up concat buffers
+        # skip connections produced inside the Up concat buffers (SkipView).  Opt-in: measured 23.69 ms/step against 23.56 with the
+        # materialised concat (profiles/step_variants_r2.txt) -- what the Up kernel and the gradient slice copy save (0.25 ms) is lost
+        # again because BatchNorm on a channel-strided tensor falls off the cp.async.bulk streaming kernels (+0.31 ms at 480^2)
+        self.virtual_skip = os.environ.get("EGM_VIRTUAL_SKIP", "0") == "1"
         self.fuse_edge = os.environ.get("EGM_NO_EDGE_FUSE", "0") != "1"   # edge enhancer: high-pass + 1x1 conv as one composed 3x3 tcgen05 conv
         # epilogue statistics wherever the kernels support them (measured: 23.54 ms/step against 24.04 with the per-layer
         # "profitable" rule, profiles/step_variants_r2.txt); EGM_BN_STATS_PROFITABLE=1 restores the rule

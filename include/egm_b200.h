@@ -26,10 +26,10 @@ enum { EGM_OK = 0, EGM_E_BADARG = -1, EGM_E_SHAPE = -2, EGM_E_ALIGN = -3, EGM_E_
 int egm_abi_version(void);
 const char* egm_last_error(void);
 int egm_device_check(void);                       /* fails unless the current device is CC 10.x */
-/* Kernel-boundary overlap: every kernel of the library is launched with programmatic stream serialization (each kernel lets its
- * successor's CTAs be scheduled early and waits for its predecessor's completion before its first global access), which removes the
- * grid launch / drain latency between the ~820 dependent kernels of a step.  Results are identical either way; 0 restores plain
- * stream order (A/B measurements).  Returns the previous setting.  (The reference's eager ATen launches have no counterpart.) */
+/* Kernel-boundary overlap (A/B switch): launch every kernel with programmatic stream serialization (each kernel lets its successor's
+ * CTAs be scheduled early and waits for its predecessor's completion before its first global access).  Results are identical either
+ * way; measured slower than plain stream order inside the captured step graph, so it is off by default.  Returns the previous
+ * setting.  (The reference's eager ATen launches have no counterpart.) */
 int egm_set_launch_overlap(int enabled);
 
 /* ---- layout / glue (replaces ATen copy_/cat/split/add kernels around src/EGM-UNet.py:1527-1541) ---- */

@@ -307,11 +307,11 @@ def test_host_fed_pipelined_loop_equals_plain_steps():
 def test_virtual_skip_concat_equals_materialised_concat(variant, hw, dtype, monkeypatch):
     """Up.forward's torch.cat([x2, x1]) (src/EGM-UNet.py:938-947): with the skip produced inside the concat buffer (SkipView: strided
     BN+ReLU store, strided MaxPool read / gradient accumulation, Up writing only the up-sampled half) the step must equal the
-    materialised concat (EGM_NO_VIRTUAL_SKIP=1): identical logits, gradients equal up to the split-K atomics' summation order."""
+    materialised concat (the default; EGM_VIRTUAL_SKIP=1 selects the virtual form): identical logits, gradients equal up to the split-K atomics' summation order."""
     import egm_unet_b200 as E
     res = []
-    for off in ("0", "1"):
-        monkeypatch.setenv("EGM_NO_VIRTUAL_SKIP", off)
+    for on in ("1", "0"):
+        monkeypatch.setenv("EGM_VIRTUAL_SKIP", on)
         model = build(variant)
         model.load_state_dict(synth.fill_state_dict(model.state_dict()))
         model = model.cuda().train()
