@@ -227,10 +227,10 @@ def hbm_family_bytes(key, b=2):
         if name == "edge_fused":
             n_, h_, w_, c_ = iv[-4:]
             return "edge_highpass", n_ * h_ * w_ * c_ * b * 2
-        if name == "maxpool2x2_fwd":
+        if name in ("maxpool2x2_fwd", "maxpool2x2_fwd_view"):
             n_, h_, w_, c_ = iv[-4:]
             return "pool", n_ * h_ * w_ * c_ * b * 1.25
-        if name == "maxpool2x2_bwd":
+        if name in ("maxpool2x2_bwd", "maxpool2x2_bwd_view"):
             n_, h_, w_, c_ = iv[-4:]
             return "pool", n_ * h_ * w_ * c_ * b * 2.25               # read x, dy/4, write dx
         if name == "upsample_concat_fwd":
@@ -389,8 +389,11 @@ def main():
     try:        # DRAM bytes of the same launches from the committed `ncu --set full` capture (profiles/), if one exists for this round
         tj = json.load(open(os.path.join(ROOT, "profiles", "conv_dram_traffic_r2.json")))
         traffic = tj.get("doubleconv_dram_bytes_per_step")
+        traffic_info = {"unit": "bytes per step over the family's %d launches (dram__bytes_read.sum + dram__bytes_write.sum)" % tj["doubleconv"]["launches"],
+                        "algorithmic_bytes_per_step": tj.get("doubleconv_algorithmic_bytes_per_step"),
+                        "source": "profiles/conv_dram_traffic_r2.json (ncu launch list of tools/one_step.py, cached; bench.py never runs under ncu)"}
     except Exception:
-        pass
+        traffic_info = None
     if tc_ms_used > 0:
         ach = flops / (tc_ms_used * 1e-3) / 1e12
         best = max((r["tflops"] for r in layer_rows), default=0.0)
@@ -400,7 +403,7 @@ def main():
                 "timing": timing, "kernel_ms_per_step_cuda_events": round(dc_ms(ev_prof), 4),
                 "share_of_step": tc_ms_used / max(step_sum, 1e-9), "sum_of_kernel_ms_per_step": step_sum, "all_tcgen05_conv_ms_per_step": tc_all,
                 "best_layer_tflops": best, "algorithmic_flops_per_step": flops, "peak_source": peak_src, "hbm": fam,
-                "hbm_peak_gbs": peak_hbm}
+                "hbm_peak_gbs": peak_hbm, "traffic_info": traffic_info}
     else:
         # no tensor-core kernel ran (fp32 check mode): report the CUDA-core conv against the same peak
         dm = sum(v["ms"] for k, v in prof.items() if k.startswith("conv2d"))

@@ -112,6 +112,8 @@ def call(name: str, *args):
             raise RuntimeError(f"egm_{name} failed ({rc}): {L.last_error()}")
         LAUNCH_COUNTER[0] += 1
         return
+    if _CALL_LOG is not None:
+        _CALL_LOG.append(name + ":" + ",".join(str(a) for a in args if isinstance(a, int)))
     stream = torch.cuda.current_stream().cuda_stream
     prof = _PROFILE is not None
     if prof and _WINDOW is not None:
@@ -142,6 +144,7 @@ def query(name: str, *args):
     return lib().fn["egm_" + name](*args)
 
 
+_CALL_LOG = None      # list: every C-ABI call key in issue order (tools/one_step.py --call-log; matched against an ncu launch list)
 _PROFILE = None
 _PROFILE_DETAIL = bool(os.environ.get("EGM_PROFILE_DETAIL"))
 _PROFILE_DETAIL_ALL = False          # bench.py: every key carries the call's integer arguments (shapes)

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--size", type=int, default=480)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--variant", default="egm")
+    ap.add_argument("--call-log", default=None, help="write the C-ABI call keys of the profiled step here, in issue order")
     ap.add_argument("--eval", action="store_true", help="inference forward instead of a train step (cfg5 uses --batch 32 --size 1024)")
     a = ap.parse_args()
     import egm_unet_b200 as E
@@ -45,10 +46,17 @@ def main():
         for _ in range(a.warmup):
             step()
         torch.cuda.synchronize()
+        from egm_unet_b200 import abi
+        if a.call_log:
+            abi._CALL_LOG = []
         torch.cuda.profiler.start()
         step()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
+        if a.call_log:
+            with open(a.call_log, "w") as f:
+                f.write("\n".join(abi._CALL_LOG) + "\n")
+            abi._CALL_LOG = None
     print("one step done")
 
 
