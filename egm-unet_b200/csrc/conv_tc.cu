@@ -785,6 +785,9 @@ static int launch_conv_halo(const NhwcView& xv, const void* wpk, const float* bi
   p.stages = (int)((198 * 1024 - wres) / p.haloStride); if (p.stages > stage_cap) p.stages = stage_cap; if (p.stages < 2) p.stages = 2;
   p.accCols = (Cout + 31) / 32 * 32;
   p.nacc = 512 / p.accCols; if (p.nacc > 8) p.nacc = 8; if (p.nacc < 2) p.nacc = 2;
+  // few tiles per CTA (the 60^2 / 30^2 maps): deep accumulator rings buy nothing, but a CTA that owns all 512 TMEM columns keeps the
+  // CTA of a concurrently running branch kernel (engine.Parallel) off its SM -- stay within half of TMEM there
+  if (p.numTiles <= 4 * egm_num_sms() && p.nacc * p.accCols > 256 && p.accCols <= 128) p.nacc = 256 / p.accCols;
   p.exp = 0;
 #ifdef EGM_DIAG
   { const char* ev = getenv("EGM_EXP"); p.exp = ev ? atoi(ev) : 0; }

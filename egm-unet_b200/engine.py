@@ -17,6 +17,76 @@ import torch.nn as nn
 from . import abi
 from .abi import call
 
+_SIDE_STREAMS: Dict[int, List["torch.cuda.Stream"]] = {}
+
+
+def _side_streams(device) -> List["torch.cuda.Stream"]:
+    """Three side streams per device, shared by every Ctx (so the caching allocator keeps ONE pool per branch slot)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SIDE_STREAMS:
+        _SIDE_STREAMS[idx] = [torch.cuda.Stream(device=device) for _ in range(3)]
+    return _SIDE_STREAMS[idx]
+
+
+_WGRAD_STREAMS: Dict[int, List["torch.cuda.Stream"]] = {}
+
+
+def _wgrad_streams(device) -> List["torch.cuda.Stream"]:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _WGRAD_STREAMS:
+        _WGRAD_STREAMS[idx] = [torch.cuda.Stream(device=device, priority=0) for _ in range(2)]   # lowest priority: never ahead of the dgrad chain
+    return _WGRAD_STREAMS[idx]
+
+
+class Parallel:
+    """Fork / join of independent branches of the graph onto side streams (the three branches of an EdgeEnhancedGRFB at the small
+    resolutions, whose kernels are 3-20 us long and fill a fraction of the 148 SMs).  Forward: `with par.branch(k): ...` runs its body
+    on side stream k after the fork point; `par.join()` makes the main stream wait for every branch.  Tape entries pushed inside a
+    branch carry (region, k) and `Ctx.backward` replays them the same way, so the branches overlap in both directions -- inside
+    the captured CUDA graph they become parallel paths.
+
+    Memory safety under torch's stream-keyed caching allocator: (a) the main stream does nothing between fork and join; (b) a branch
+    only touches tensors of its own stream or tensors allocated on the main stream BEFORE the fork, and never writes a tensor another
+    branch reads or writes (the callers keep every op that accumulates into a shared gradient outside the region); (c) every later
+    use of a side stream starts with a wait on a newer main-stream event, which orders it after whatever the main stream did with
+    memory that has meanwhile been returned to that side stream's pool."""
+
+    def __init__(self, ctx: "Ctx", on: bool):
+        self.ctx, self.on = ctx, bool(on)
+        if self.on:
+            ctx._region += 1
+            self.rid = ctx._region
+            self.main = torch.cuda.current_stream(ctx.device)
+            self.fork = torch.cuda.Event()
+            self.fork.record(self.main)
+            self.used: List["torch.cuda.Stream"] = []
+
+    def branch(self, k: int):
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            if not self.on:
+                yield
+                return
+            s = _side_streams(self.ctx.device)[k]
+            s.wait_event(self.fork)
+            prev, self.ctx._cur = self.ctx._cur, (self.rid, k)
+            try:
+                with torch.cuda.stream(s):
+                    yield
+            finally:
+                self.ctx._cur = prev
+            self.used.append(s)
+        return cm()
+
+    def join(self):
+        if self.on:
+            for s in self.used:
+                self.main.wait_stream(s)
+            self.used = []
+
+
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 MODE_PLAIN, MODE_EDGE_GATE, MODE_RESIDUAL = 0, 1, 2
 
@@ -101,7 +171,18 @@ class Ctx:
         # epilogue statistics wherever the kernels support them (measured: 23.54 ms/step against 24.04 with the per-layer
         # "profitable" rule, profiles/step_variants_r2.txt); EGM_BN_STATS_PROFITABLE=1 restores the rule
         self.stats_all = os.environ.get("EGM_BN_STATS_PROFITABLE", "0") != "1"
-        self._arena, self._arena_off = None, 0
+        # branches of a GRFB run on side streams where the maps have at most this many pixels (N*H*W); 0 = never
+        self.par_maxpix = int(os.environ.get("EGM_BRANCH_PAR_MAXPIX", "230400"))
+        # weight-gradient lane: the tcgen05 wgrad kernels of planned convs (nothing reads their packed output before the end of
+        # backward) run on one low-priority side stream instead of inside the dgrad -> BN-backward -> dgrad dependency chain
+        # (measured 23.13 -> 22.10 ms/step, profiles/step_variants_r2.txt; EGM_WGRAD_STREAM=0 puts them back in line)
+        self.wgrad_lane = os.environ.get("EGM_WGRAD_STREAM", "1") != "0"
+        self.wgrad_lanes = max(1, min(2, int(os.environ.get("EGM_WGRAD_LANES", "1"))))
+        self._w_rr = 0
+        self._w_hold: list = []           # operands of wgrad kernels still in flight on the lane (kept alive until the join)
+        self._cur = None                  # None = main stream, else (parallel region id, branch) -- the tag of tape entries
+        self._region = 0
+        self._arenas: Dict[object, list] = {}    # stream slot -> [arena, offset]: a branch zeroes and uses its own arena
 
     ARENA_DOUBLES = 1 << 16
 
@@ -111,12 +192,13 @@ class Ctx:
             t = self.f64(n)
             call("memset_zero", t, n * 8)
             return t
-        if self._arena is None or self._arena_off + n > self.ARENA_DOUBLES:
-            self._arena = self.f64(self.ARENA_DOUBLES)
-            call("memset_zero", self._arena, self.ARENA_DOUBLES * 8)
-            self._arena_off = 0
-        t = self._arena[self._arena_off:self._arena_off + n]
-        self._arena_off += (n + 1) // 2 * 2
+        slot = None if self._cur is None else self._cur[1]
+        a = self._arenas.get(slot)
+        if a is None or a[1] + n > self.ARENA_DOUBLES:
+            a = self._arenas[slot] = [self.f64(self.ARENA_DOUBLES), 0]
+            call("memset_zero", a[0], self.ARENA_DOUBLES * 8)
+        t = a[0][a[1]:a[1] + n]
+        a[1] += (n + 1) // 2 * 2
         return t
 
     # ---- allocation helpers
@@ -137,13 +219,71 @@ class Ctx:
 
     def push(self, fn: Callable):
         if self.record:
-            self.tape.append(fn)
+            self.tape.append((self._cur, fn))
+
+    def wgrad_async(self, fn: Callable, hold):
+        """run fn() (one wgrad launch) on the weight-gradient lane, ordered after everything enqueued on the current stream so far"""
+        cur = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        w = _wgrad_streams(self.device)[self._w_rr % self.wgrad_lanes]
+        self._w_rr += 1
+        w.wait_event(ev)
+        with torch.cuda.stream(w):
+            fn()
+        self._w_hold.append(hold)
+
+    def join_wgrad(self):
+        """make the current stream wait for the weight-gradient lane(s) (before anything reads the packed / bias gradients)"""
+        if self._w_hold:
+            cur = torch.cuda.current_stream(self.device)
+            for w in _wgrad_streams(self.device)[:self.wgrad_lanes]:
+                cur.wait_stream(w)
+            self._w_hold = []
+
+    def parallel(self, pixels: int) -> Parallel:
+        return Parallel(self, 0 < pixels <= self.par_maxpix)
 
     def backward(self, after_each: Optional[Callable] = None):
+        """Replay the tape in reverse.  Entries recorded inside a Parallel region run on their branch's side stream (forked from the
+        main stream when the region is entered, joined when it is left); `after_each` (the data-parallel bucket reducer) only runs
+        at main-stream points, i.e. when every kernel enqueued so far is ordered before what the main stream does next."""
+        main = torch.cuda.current_stream(self.device) if self.device.type == "cuda" else None
+        region, fork, used = None, None, {}
+
+        def join():
+            for st in used.values():
+                main.wait_stream(st)
+            used.clear()
         while self.tape:
-            self.tape.pop()()
-            if after_each is not None:
-                after_each()
+            tag, fn = self.tape.pop()
+            if tag is None:
+                if region is not None:
+                    join()
+                    region = None
+                fn()
+                if after_each is not None:
+                    after_each()
+                continue
+            rid, k = tag
+            if rid != region:
+                if region is not None:
+                    join()
+                region = rid
+                fork = torch.cuda.Event()
+                fork.record(main)
+            if k not in used:
+                used[k] = _side_streams(self.device)[k]
+                used[k].wait_event(fork)
+            prev, self._cur = self._cur, tag
+            try:
+                with torch.cuda.stream(used[k]):
+                    fn()
+            finally:
+                self._cur = prev
+        if region is not None:
+            join()
+        self.join_wgrad()
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
@@ -445,7 +585,8 @@ def _tc_read_view(ctx, t, n, h, w, ctot, coff, c, cp):
     return tp, cp, 0, cp
 
 
-def _conv_tc_fwd_bwd(ctx, x, x_coff, cin, cinp, co, cop, kh, kw, dilation, wf, wd, bp, bias_present, bparam, bgrad_sink, wgrad_to, epi=None):
+def _conv_tc_fwd_bwd(ctx, x, x_coff, cin, cinp, co, cop, kh, kw, dilation, wf, wd, bp, bias_present, bparam, bgrad_sink, wgrad_to, epi=None,
+                     lane=False):
     """Forward + tape entry of one tcgen05 conv on channel-strided views.  wgrad_to(dwp) receives / names the packed fp32
     gradient buffer: it returns the tensor egm_conv2d_wgrad_tc_view writes and is called again (post=True) afterwards."""
     n, h, w, ctot = x.shape
@@ -471,11 +612,19 @@ def _conv_tc_fwd_bwd(ctx, x, x_coff, cin, cinp, co, cop, kh, kw, dilation, wf, w
                 return
             dyt, dcs, dco, dv = _tc_read_view(ctx, dy, n, h, w, co, 0, co, cop)
             dwp = wgrad_to(False)
-            call("conv2d_wgrad_tc_view", xt, xcs, xco, xv, dyt, dcs, dco, dv, dwp, n, h, w, cinp, cop, kh, kw, dilation)
+            if lane and ctx.wgrad_lane:       # packed gradient is only read by egm_wgrad_unpack_batch: off the critical path
+                ctx.wgrad_async(lambda: call("conv2d_wgrad_tc_view", xt, xcs, xco, xv, dyt, dcs, dco, dv, dwp, n, h, w, cinp, cop, kh, kw, dilation),
+                                (xt, dyt, dy))
+            else:
+                call("conv2d_wgrad_tc_view", xt, xcs, xco, xv, dyt, dcs, dco, dv, dwp, n, h, w, cinp, cop, kh, kw, dilation)
             wgrad_to(True)
             if bias_present:
                 gb = torch.empty(co, **ctx.f32) if bgrad_sink is not None else ctx.grad_slot(bparam)
-                call("channel_sum", dy, ctx.code, M, co, co, 0, ctx.f64(2 * co), gb)
+                scratch = ctx.f64(2 * co)
+                if lane and ctx.wgrad_lane and bgrad_sink is None:      # the bias gradient goes straight into the flat gradient buffer: same lane
+                    ctx.wgrad_async(lambda: call("channel_sum", dy, ctx.code, M, co, co, 0, scratch, gb), (dy, scratch))
+                else:
+                    call("channel_sum", dy, ctx.code, M, co, co, 0, scratch, gb)
                 if bgrad_sink is not None:
                     bgrad_sink(gb)
             if x.needs_grad:
@@ -536,7 +685,7 @@ def _conv2d_planned(ctx, x, job: WeightJob, bias, bparam, dilation, x_coff, cin,
                 ctx.grad_slot(p)
         return job.dwp
     return _conv_tc_fwd_bwd(ctx, x, x_coff, cin, job.cinp, co, job.coutp, kh, kw, dilation, job.wf, job.wd, bp,
-                            bparam is not None or bgrad_sink is not None, bparam, bgrad_sink, wgrad_to, epi)
+                            bparam is not None or bgrad_sink is not None, bparam, bgrad_sink, wgrad_to, epi, lane=True)
 
 
 def conv_module(ctx: Ctx, x: Var, m: nn.Conv2d, **kw) -> Var:

@@ -122,18 +122,26 @@ def grfb(ctx: Ctx, x: Var, m) -> Var:
     cat = Var(ctx.empty(n, h, w, c + 6 * ip))
     release_grad(ctx, cat)            # pushed first => runs after every slice consumer in backward
     copy_into(ctx, x, cat, 0)
+    # The three branches are independent after their first conv.  Those first convs all back-propagate into xe's gradient, so they
+    # stay on the main stream (their backward runs after the join); the rest of each branch runs on its own side stream where the
+    # maps are small (engine.Parallel) -- every branch writes its own channel slice of `cat` and only reads cat's gradient.
     d = basic_conv(ctx, xe, m.branch_dir[0])
-    d = basic_conv(ctx, d, m.branch_dir[1])
-    basic_conv(ctx, d, m.branch_dir[2], out=cat, out_coff=c)
     e = basic_conv(ctx, xe, m.branch_edge[0])
-    e = edge_enhancer(ctx, e, m.branch_edge[1])
-    e = basic_conv(ctx, e, m.branch_edge[2])
-    e = basic_conv(ctx, e, m.branch_edge[3])
-    basic_conv(ctx, e, m.branch_edge[4], out=cat, out_coff=c + 2 * ip)
     q = basic_conv(ctx, xe, m.branch_ctx[0])
-    q = basic_conv(ctx, q, m.branch_ctx[1])
-    q = basic_conv(ctx, q, m.branch_ctx[2])
-    basic_conv(ctx, q, m.branch_ctx[3], out=cat, out_coff=c + 4 * ip)
+    par = ctx.parallel(M)
+    with par.branch(0):
+        d = basic_conv(ctx, d, m.branch_dir[1])
+        basic_conv(ctx, d, m.branch_dir[2], out=cat, out_coff=c)
+    with par.branch(1):
+        e = edge_enhancer(ctx, e, m.branch_edge[1])
+        e = basic_conv(ctx, e, m.branch_edge[2])
+        e = basic_conv(ctx, e, m.branch_edge[3])
+        basic_conv(ctx, e, m.branch_edge[4], out=cat, out_coff=c + 2 * ip)
+    with par.branch(2):
+        q = basic_conv(ctx, q, m.branch_ctx[1])
+        q = basic_conv(ctx, q, m.branch_ctx[2])
+        basic_conv(ctx, q, m.branch_ctx[3], out=cat, out_coff=c + 4 * ip)
+    par.join()
     fo = fusion_conv(ctx, cat, m.fusion_conv)
     o = conv_bn_act(ctx, x, m.shortcut.conv, m.shortcut.bn, ACT_NONE, MODE_RESIDUAL, aux=fo, alpha=float(m.scale))
     tz = conv_module(ctx, o, m.target_enhancer[0])          # [N,H,W,3]

@@ -153,7 +153,10 @@ class Trainer:
         if self.reducer is not None:          # overlap: buckets are all-reduced on the comm stream as backward completes them
             red = self.reducer
             st.on_grad = red.mark
-            red.before_launch = plan.unpack_bucket if (plan is not None and plan.ready) else None
+            if plan is not None and plan.ready:      # the packed gradients of a bucket must be complete (weight-gradient lane) before they are scattered
+                red.before_launch = lambda b: (ctx.join_wgrad(), plan.unpack_bucket(b))
+            else:
+                red.before_launch = None
             try:
                 ctx.backward(after_each=red.flush_ready)
                 red.finish()
@@ -186,6 +189,15 @@ class Trainer:
         call("sgd_step", st.params, st.grads, self.mom_buf, st.total, self.hp)
         return loss
 
+    def _capture_kw(self):
+        """With the weight-gradient lane (EGM_WGRAD_STREAM=1) the step is captured on a HIGH-priority stream: the lane's kernels
+        (lowest priority) then only take SM slots the dependency chain leaves free.  Kernel nodes inherit their stream's priority."""
+        if os.environ.get("EGM_WGRAD_STREAM", "1") == "0":
+            return {}
+        if getattr(self, "_cap_stream", None) is None:
+            self._cap_stream = torch.cuda.Stream(device=self.dev, priority=-1)
+        return {"stream": self._cap_stream}
+
     # ------------------------------------------------------------------ CUDA-graph replay of the whole step
     def _graph_step(self, image: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """The ~800 kernel launches of a step are captured once per input shape (all kernels take plain pointers and never sync
@@ -208,7 +220,7 @@ class Trainer:
                 try:
                     torch.cuda.synchronize(self.dev)
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with torch.cuda.graph(g, **self._capture_kw()):
                         loss = self.forward_backward(s_img, s_tgt)
                         call("sgd_step", self.store.params, self.store.grads, self.mom_buf, self.store.total, self.hp)
                     comm_inside = True
@@ -222,7 +234,7 @@ class Trainer:
                 reducer, self.reducer = self.reducer, None          # no side-stream traffic inside the capture
                 try:
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with torch.cuda.graph(g, **self._capture_kw()):
                         loss = self.forward_backward(s_img, s_tgt)
                         if self.world == 1:
                             call("sgd_step", self.store.params, self.store.grads, self.mom_buf, self.store.total, self.hp)
