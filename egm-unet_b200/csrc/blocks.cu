@@ -285,12 +285,14 @@ __global__ void __launch_bounds__(256) k_sa_conv_bwd_dw(const float* __restrict_
   for (int s = 0; s < 7; ++s) { float v = block_sum(acc[s], red); if (threadIdx.x == 0) atomicAdd(dw + ch * 49 + r * 7 + s, v); }
 }
 extern "C" int egm_sa_conv_bwd(const float* dsa, const float* sa, const float* mm, const float* w, float* dmm, float* dw, int N, int H, int W, void* stream) {
+  // dmm == NULL or dw == NULL skips that half: the input gradient is on the backward dependency chain, the 98-element weight gradient
+  // is not (the engine launches it on the weight-gradient lane)
   cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(dw, 0, sizeof(float) * 98, st);
+  if (dw) cudaMemsetAsync(dw, 0, sizeof(float) * 98, st);
   long long M = (long long)N * H * W; if (M == 0) return EGM_OK;
-  egm_launch(k_sa_conv_bwd_dmm, egm_grid_for(M, 128), 128, 0, st, dsa, sa, w, dmm, N, H, W);
+  if (dmm) egm_launch(k_sa_conv_bwd_dmm, egm_grid_for(M, 128), 128, 0, st, dsa, sa, w, dmm, N, H, W);
   int bx = egm_grid_for(M, 256, 2) / 14 + 1;
-  egm_launch(k_sa_conv_bwd_dw, dim3(bx, 14), 256, 0, st, dsa, sa, mm, dw, N, H, W);
+  if (dw) egm_launch(k_sa_conv_bwd_dw, dim3(bx, 14), 256, 0, st, dsa, sa, mm, dw, N, H, W);
   EGM_LAUNCH_CHECK("sa_conv_bwd"); return EGM_OK;
 }
 

@@ -11,6 +11,36 @@ struct BnArgs {
   int act, mode; float alpha;
 };
 
+// Finalize fused into the APPLY kernels (statistics from a conv epilogue): sums != nullptr makes every thread derive the scale / shift of
+// its own channel vector from the batch sums (the same fp64 formulas as k_bn_finalize; a few hundred cycles, hidden behind the first
+// loads) instead of reading vectors a separate ~7 us single-warp launch would have produced; the first C/V threads of block 0 publish
+// scale / shift / mean / rstd for the backward pass and update the running statistics.
+struct BnFin {
+  const double* sums; double M;
+  const float* gamma; const float* beta; float* rmean; float* rvar; long long* nbt; float momentum, eps;
+  float* scale; float* shift; float* mean; float* rstd;
+};
+template <int V>
+__device__ __forceinline__ void bn_fin_vec(const BnFin& f, const BnArgs& a, int c, int C, bool publish, FVec<V>& sc, FVec<V>& sh) {
+  if (!f.sums) { sc = ldv<V>(a.scale + c); sh = ldv<V>(a.shift + c); return; }
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const double mean = f.sums[c + j] / f.M; double var = f.sums[C + c + j] / f.M - mean * mean; if (var < 0) var = 0;
+    const double rstd = 1.0 / sqrt(var + (double)f.eps);
+    const float g = f.gamma[c + j];
+    sc.v[j] = (float)(g * rstd); sh.v[j] = (float)(f.beta[c + j] - mean * g * rstd);
+    if (publish) {
+      if (f.rmean) {
+        const double unb = f.M > 1 ? var * f.M / (f.M - 1) : var;
+        f.rmean[c + j] = (float)((1.0 - f.momentum) * f.rmean[c + j] + f.momentum * mean);
+        f.rvar[c + j] = (float)((1.0 - f.momentum) * f.rvar[c + j] + f.momentum * unb);
+      }
+      f.scale[c + j] = sc.v[j]; f.shift[c + j] = sh.v[j]; f.mean[c + j] = (float)mean; f.rstd[c + j] = (float)rstd;
+    }
+  }
+  if (publish && c == 0 && f.nbt) *f.nbt += 1;
+}
+
 // Finalize fused into the reduction kernels: the LAST block to add its partial sums (ticket counter behind the sums) turns them
 // into scale/shift/mean/rstd + running statistics (forward) or the backward coefficients + dgamma/dbeta (backward).  Saves one
 // dependent ~3 us launch per BN layer and pass (148 per train step).
@@ -112,8 +142,9 @@ __global__ void k_bn_stats(StatsF<T, V> f, long long M, int C, double* out, BnTa
   bn_tail_run(tl, out, C, threadIdx.x, blockDim.x, false);
 }
 static bool bn_stats_stream_launch(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, const BnTail& tl, cudaStream_t st);
-static bool bn_fwd_stream_launch(const void* z, long long zcs, long long zco, const BnArgs& a, const void* aux, void* y, long long ycs, long long yco, int dtype,
-                                 long long M, int C, cudaStream_t st);
+struct BnFin;
+static bool bn_fwd_stream_launch(const void* z, long long zcs, long long zco, const BnArgs& a, const BnFin& fin, const void* aux, void* y, long long ycs,
+                                 long long yco, int dtype, long long M, int C, cudaStream_t st);
 static int bn_stats_impl(const void* x, int dtype, long long M, int C, long long cstride, long long coff, double* sums, BnTail tl, cudaStream_t st) {
   EGM_REQUIRE(C >= 1 && C <= 2048, EGM_E_SHAPE, "bn_stats: C=%d unsupported", C);
   cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C + (tl.counter ? 1 : 0)), st);
@@ -173,10 +204,11 @@ extern "C" int egm_bn_finalize(const double* sums, long long M, const float* gam
 // ---------------------------------------------------------------- apply (+activation / gate / residual)
 template <typename T, int V>
 __global__ void k_bn_act_fwd(const T* __restrict__ z, long long zcs, long long zco, BnArgs a, const T* __restrict__ aux, T* __restrict__ y,
-                             long long ycs, long long yco, long long M, int CV) { egm_pdl_enter();
-  // blockDim.x = CV * rpb: every thread keeps ONE channel vector, so scale/shift are loaded once
+                             long long ycs, long long yco, long long M, int CV, BnFin fin) { egm_pdl_enter();
+  // blockDim.x = CV * rpb: every thread keeps ONE channel vector, so scale/shift are loaded (or derived from the batch sums) once
   const int rpb = blockDim.x / CV, cv = threadIdx.x % CV, r = threadIdx.x / CV, c = cv * V;
-  const FVec<V> sc = ldv<V>(a.scale + c), sh = ldv<V>(a.shift + c);
+  FVec<V> sc, sh;
+  bn_fin_vec<V>(fin, a, c, CV * V, blockIdx.x == 0 && r == 0, sc, sh);
 #pragma unroll 2
   for (long long m = (long long)blockIdx.x * rpb + r; m < M; m += (long long)gridDim.x * rpb) {
     FVec<V> zv = ldv<V>(z + m * zcs + zco + c), xv, o;
@@ -197,17 +229,32 @@ static inline int ew_blocks(long long M, int threads, int C, int V) {
   long long cap = (long long)egm_num_sms() * 8;
   if (b > cap) b = cap; if (b < 1) b = 1; return (int)b;
 }
+static int bn_act_fwd_impl(const void* z, long long z_cstride, long long z_coff, const BnArgs& a, const BnFin& fin, const void* aux, void* y,
+                           long long y_cstride, long long y_coff, int dtype, long long M, int C, cudaStream_t st) {
+  if (M * C == 0) return EGM_OK;
+  EGM_REQUIRE(a.mode == 0 || aux, EGM_E_BADARG, "bn_act_fwd: mode %d needs aux", a.mode);
+  int v = egm_pick_vec(C, z_cstride, z_coff), v2 = egm_pick_vec(C, y_cstride, y_coff); if (v2 < v) v = v2;
+  if (bn_fwd_stream_launch(z, z_cstride, z_coff, a, fin, aux, y, y_cstride, y_coff, dtype, M, C, st)) { EGM_LAUNCH_CHECK("bn_act_fwd(stream)"); return EGM_OK; }
+  const int threads = reduce_threads(C, v);
+  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_bn_act_fwd<T, V>, ew_blocks(M, threads, C, V), threads, 0, st,
+      (const T*)z, z_cstride, z_coff, a, (const T*)aux, (T*)y, y_cstride, y_coff, M, C / V, fin))));
+  EGM_LAUNCH_CHECK("bn_act_fwd"); return EGM_OK;
+}
 extern "C" int egm_bn_act_fwd(const void* z, long long z_cstride, long long z_coff, const float* scale, const float* shift, int act, int mode,
                               const void* aux, float alpha, void* y, long long y_cstride, long long y_coff, int dtype, long long M, int C, void* stream) {
-  if (M * C == 0) return EGM_OK;
-  EGM_REQUIRE(mode == 0 || aux, EGM_E_BADARG, "bn_act_fwd: mode %d needs aux", mode);
-  int v = egm_pick_vec(C, z_cstride, z_coff), v2 = egm_pick_vec(C, y_cstride, y_coff); if (v2 < v) v = v2;
   BnArgs a{scale, shift, nullptr, nullptr, nullptr, act, mode, alpha};
-  if (bn_fwd_stream_launch(z, z_cstride, z_coff, a, aux, y, y_cstride, y_coff, dtype, M, C, (cudaStream_t)stream)) { EGM_LAUNCH_CHECK("bn_act_fwd(stream)"); return EGM_OK; }
-  const int threads = reduce_threads(C, v);
-  EGM_DISPATCH_DTYPE(dtype, EGM_DISPATCH_VEC(v, (egm_launch(k_bn_act_fwd<T, V>, ew_blocks(M, threads, C, V), threads, 0, (cudaStream_t)stream, 
-      (const T*)z, z_cstride, z_coff, a, (const T*)aux, (T*)y, y_cstride, y_coff, M, C / V))));
-  EGM_LAUNCH_CHECK("bn_act_fwd"); return EGM_OK;
+  return bn_act_fwd_impl(z, z_cstride, z_coff, a, BnFin{}, aux, y, y_cstride, y_coff, dtype, M, C, (cudaStream_t)stream);
+}
+// egm_bn_finalize (training) + egm_bn_act_fwd in ONE launch: `sums` are the batch sums a conv epilogue produced (egm_conv2d_tc_ex);
+// scale / shift / mean / rstd are still written (the backward pass reads them) and the running statistics are updated.
+extern "C" int egm_bn_finalize_act_fwd(const double* sums, long long Mstat, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                       long long* num_batches_tracked, float momentum, float eps, float* scale, float* shift, float* mean, float* rstd,
+                                       const void* z, long long z_cstride, long long z_coff, int act, int mode, const void* aux, float alpha, void* y,
+                                       long long y_cstride, long long y_coff, int dtype, long long M, int C, void* stream) {
+  EGM_REQUIRE(sums && Mstat > 0 && M > 0, EGM_E_BADARG, "bn_finalize_act_fwd: needs batch sums over a non-empty batch");
+  BnArgs a{scale, shift, nullptr, nullptr, nullptr, act, mode, alpha};
+  BnFin fin{sums, (double)Mstat, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, scale, shift, mean, rstd};
+  return bn_act_fwd_impl(z, z_cstride, z_coff, a, fin, aux, y, y_cstride, y_coff, dtype, M, C, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------- backward
@@ -406,19 +453,19 @@ static bool bn_stats_stream_launch(const void* x, int dtype, long long M, int C,
   }
   return true;
 }
-static bool bn_fwd_stream_launch(const void* z, long long zcs, long long zco, const BnArgs& a, const void* aux, void* y, long long ycs, long long yco, int dtype,
-                                 long long M, int C, cudaStream_t st) {
+static bool bn_fwd_stream_launch(const void* z, long long zcs, long long zco, const BnArgs& a, const BnFin& fin, const void* aux, void* y, long long ycs,
+                                 long long yco, int dtype, long long M, int C, cudaStream_t st) {
   if (!bn_stream_eligible(a.mode, M, C, zcs, zco) || ycs != C || yco != 0 || (dtype != EGM_F32 && dtype != EGM_BF16)) return false;
   if (a.mode == 1) return false;        // sigmoid gate: ALU-bound in the consumer warps, the grid-stride kernel is faster (measured)
   EGM_DISPATCH_DTYPE(dtype, {
     if (a.mode == 0) {
       const size_t smb = bs::ring_bytes<1>(0);
       static bool attr[64] = {}; egm_ensure_smem(k_bn_act_fwd_stream<T, false>, (int)smb, attr);
-      egm_launch(k_bn_act_fwd_stream<T, false>, bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st, (const T*)z, nullptr, a, (T*)y, M * C, C);
+      egm_launch(k_bn_act_fwd_stream<T, false>, bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st, (const T*)z, nullptr, a, (T*)y, M * C, C, fin);
     } else {
       const size_t smb = bs::ring_bytes<2>(0);
       static bool attr[64] = {}; egm_ensure_smem(k_bn_act_fwd_stream<T, true>, (int)smb, attr);
-      egm_launch(k_bn_act_fwd_stream<T, true>, bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st, (const T*)z, (const T*)aux, a, (T*)y, M * C, C);
+      egm_launch(k_bn_act_fwd_stream<T, true>, bn_stream_grid(M * C, sizeof(T)), bs::THREADS, smb, st, (const T*)z, (const T*)aux, a, (T*)y, M * C, C, fin);
     }
   });
   return true;

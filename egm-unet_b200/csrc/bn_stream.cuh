@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(bs::THREADS, 1) k_bn_stats_stream(const T* __r
 // ------------------------------------------------------------------ y = act(z*scale + shift) | gate | residual   (dense in and out)
 template <typename T, bool AUX>
 __global__ void __launch_bounds__(bs::THREADS, 1) k_bn_act_fwd_stream(const T* __restrict__ z, const T* __restrict__ aux, BnArgs a, T* __restrict__ y,
-                                                                     long long total, int C) { egm_pdl_enter();
+                                                                     long long total, int C, BnFin fin) { egm_pdl_enter();
   using namespace bs;
   constexpr int NT = AUX ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(bs::THREADS, 1) k_bn_act_fwd_stream(const T* _
     return;
   }
   const int t = threadIdx.x, c = (t * V) % C;
-  const FVec<V> sc = ldv<V>(a.scale + c), sh = ldv<V>(a.shift + c);
+  FVec<V> sc, sh;
+  bn_fin_vec<V>(fin, a, c, C, blockIdx.x == 0 && t * V < C, sc, sh);      // the first C/V consumers of block 0 cover every channel once
   int s = 0; uint32_t ph = 0;
   for (long long ch = blockIdx.x; ch < nChunks; ch += gridDim.x) {
     const long long e0 = ch * EPC; const int n = (int)(total - e0 < EPC ? total - e0 : EPC);

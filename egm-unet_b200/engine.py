@@ -162,6 +162,9 @@ class Ctx:
         self.use_tc = use_tc and dtype == torch.bfloat16
         self.f32 = dict(dtype=torch.float32, device=device)
         self.wplan: Optional["WeightPlan"] = None   # batched weight preparation (Trainer); None = per-conv pack kernels
+        # BN finalize inside the apply kernel (egm_bn_finalize_act_fwd).  Opt-in: measured 21.84 vs 21.69 ms/step -- every block redoing
+        # the fp64 finalize of its channels costs the small maps more than the 59 saved ~7 us launches give back
+        self.fuse_bn_finalize = os.environ.get("EGM_BN_FIN_FUSE", "0") == "1"
         self.fuse_bn = os.environ.get("EGM_NO_BN_FUSE", "0") != "1"   # BN statistics / inference BN+ReLU in the conv epilogue
         # skip connections produced inside the Up concat buffers (SkipView).  Opt-in: measured 23.69 ms/step against 23.56 with the
         # materialised concat (profiles/step_variants_r2.txt) -- what the Up kernel and the gradient slice copy save (0.25 ms) is lost
@@ -705,7 +708,10 @@ def bn_act(ctx: Ctx, z: Var, bn: nn.BatchNorm2d, act: int, mode: int = MODE_PLAI
     scale, shift, mean, rstd = (torch.empty(c, **ctx.f32) for _ in range(4))
     training = ctx.training or bn.running_mean is None
     mom = 0.1 if bn.momentum is None else bn.momentum
-    if training and M > 0 and sums is not None:      # statistics came out of the producing conv's epilogue (fp32 accumulators)
+    fused_fin = training and M > 0 and sums is not None and ctx.fuse_bn_finalize
+    if fused_fin:                 # statistics came out of the producing conv's epilogue: finalize inside the apply kernel below
+        pass
+    elif training and M > 0 and sums is not None:
         call("bn_finalize", sums, M, gamma, beta, bn.running_mean, bn.running_var, bn.num_batches_tracked, float(mom), float(bn.eps), 1, c,
              scale, shift, mean, rstd)
     elif training and M > 0:      # statistics + finalize (scale/shift/mean/rstd, running stats) in one launch
@@ -722,7 +728,11 @@ def bn_act(ctx: Ctx, z: Var, bn: nn.BatchNorm2d, act: int, mode: int = MODE_PLAI
         ycs, yco = c, 0
     else:
         y, ycs, yco = out, out.C, out_coff
-    call("bn_act_fwd", z.t, c, 0, scale, shift, act, mode, aux.t if aux is not None else None, float(alpha), y.t, ycs, yco, ctx.code, M, c)
+    if fused_fin:
+        call("bn_finalize_act_fwd", sums, M, gamma, beta, bn.running_mean, bn.running_var, bn.num_batches_tracked, float(mom), float(bn.eps),
+             scale, shift, mean, rstd, z.t, c, 0, act, mode, aux.t if aux is not None else None, float(alpha), y.t, ycs, yco, ctx.code, M, c)
+    else:
+        call("bn_act_fwd", z.t, c, 0, scale, shift, act, mode, aux.t if aux is not None else None, float(alpha), y.t, ycs, yco, ctx.code, M, c)
     if ctx.record:
         def bwd():
             dy = y.grad

@@ -90,7 +90,12 @@ def fusion_conv(ctx: Ctx, cat: Var, m) -> Var:
             dsa = torch.empty(M, **ctx.f32)
             call("pixel_dot", dt, s.t, ca, dsa, ctx.code, n, HW, dim)
             dmm = torch.empty(M * 2, **ctx.f32)
-            call("sa_conv_bwd", dsa, sa, mm, wsa, dmm, ctx.grad_slot(m.spatial_attention.conv1.weight), n, h, w)
+            gw = ctx.grad_slot(m.spatial_attention.conv1.weight)
+            if ctx.wgrad_lane and planned:      # the 7x7 weight gradient is read by nobody before the optimizer: off the dependency chain
+                call("sa_conv_bwd", dsa, sa, mm, wsa, dmm, None, n, h, w)
+                ctx.wgrad_async(lambda: call("sa_conv_bwd", dsa, sa, mm, wsa, None, gw, n, h, w), (dsa, sa, mm))
+            else:
+                call("sa_conv_bwd", dsa, sa, mm, wsa, dmm, gw, n, h, w)
             ds = ctx.empty(n, h, w, dim)
             call("fuse_mix_bwd_s", dt, sa, ca, dmm, amax, ds, ctx.code, n, HW, dim)
             s.accum(ds)

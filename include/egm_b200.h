@@ -122,6 +122,13 @@ int egm_bn_finalize(const double* sums, long long M, const float* gamma, const f
                     float* scale, float* shift, float* mean, float* rstd, void* stream);
 int egm_bn_act_fwd(const void* z, long long z_cstride, long long z_coff, const float* scale, const float* shift, int act, int mode,
                    const void* aux, float alpha, void* y, long long y_cstride, long long y_coff, int dtype, long long M, int C, void* stream);
+/* egm_bn_finalize (training) + egm_bn_act_fwd in one launch, for batch sums taken in a conv epilogue (egm_conv2d_tc_ex): every thread
+ * derives the scale / shift of its channels from `sums` ([2][C] doubles over Mstat pixels); scale / shift / mean / rstd are still
+ * written for the backward pass and the running statistics updated (nn.BatchNorm2d training semantics, src/EGM-UNet.py:50,53,966). */
+int egm_bn_finalize_act_fwd(const double* sums, long long Mstat, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                            long long* num_batches_tracked, float momentum, float eps, float* scale, float* shift, float* mean, float* rstd,
+                            const void* z, long long z_cstride, long long z_coff, int act, int mode, const void* aux, float alpha, void* y,
+                            long long y_cstride, long long y_coff, int dtype, long long M, int C, void* stream);
 int egm_bn_act_bwd_reduce(const void* dy, long long dy_cstride, long long dy_coff, const void* z, const float* scale, const float* shift,
                           const float* mean, const float* rstd, int act, int mode, const void* aux, float alpha, int dtype, long long M, int C,
                           double* sums, void* stream);
@@ -190,7 +197,7 @@ int egm_unary(const void* a, const void* b, const float* scalar_dev, void* y, in
 int egm_dot_all(const void* a, const void* b, float* out, int dtype, long long n, void* stream);
 int egm_chan_meanmax(const void* s, float* mm, unsigned char* amax, int dtype, long long M, int C, void* stream);
 int egm_sa_conv_fwd(const float* mm, const float* w, float* sa, int N, int H, int W, void* stream);
-int egm_sa_conv_bwd(const float* dsa, const float* sa, const float* mm, const float* w, float* dmm, float* dw, int N, int H, int W, void* stream);
+int egm_sa_conv_bwd(const float* dsa, const float* sa, const float* mm, const float* w, float* dmm, float* dw, int N, int H, int W, void* stream);   /* dmm or dw may be NULL: only the other half is computed */
 int egm_gap_gmp(const void* f, float* avg, float* mx, int* arg, void* scratch, int dtype, int N, long long HW, int C, void* stream);
 int egm_ca_mlp_fwd(const float* avg, const float* mx, const float* w0, const float* w2, float* ca, float* hid, int N, int C, int Cr, void* stream);
 int egm_ca_mlp_bwd(const float* dca, const float* ca, const float* avg, const float* mx, const float* hid, const float* w0, const float* w2,

@@ -438,9 +438,10 @@ def test_conv_bn_act_train_stats_in_epilogue(case):
     x = _q(_rand(N, cin, H, W), torch.bfloat16)
     g = _q(_rand(N, cout, H, W, seed=3), torch.bfloat16)
     res = {}
-    for fuse in (True, False):
+    for fuse in (True, False, "fin"):     # "fin": additionally the finalize step inside the apply kernel (egm_bn_finalize_act_fwd)
         hs = Harness(torch.bfloat16, use_tc=True)
-        hs.ctx.fuse_bn = fuse
+        hs.ctx.fuse_bn = bool(fuse)
+        hs.ctx.fuse_bn_finalize = fuse == "fin"
         hs.ctx.stats_all = True           # every shape the epilogue supports, not only the ones the profitability rule selects
         cc, bb = nn.Conv2d(cin, cout, k, padding=dil * (k - 1) // 2, dilation=dil, groups=groups, bias=bias), nn.BatchNorm2d(cout, momentum=0.01)
         cc.load_state_dict(conv.state_dict()); bb.load_state_dict(bn.state_dict())
@@ -457,6 +458,9 @@ def test_conv_bn_act_train_stats_in_epilogue(case):
     yr.backward(g)
     ref = (yr.detach(), xr.grad, conv.weight.grad, bn.weight.grad, bn.bias.grad, bn.running_mean, bn.running_var, 1)
     names = ("y", "dx", "dw", "dgamma", "dbeta", "running_mean", "running_var")
+    for nme, a, b in zip(names, res["fin"], res[True]):      # same arithmetic, one launch fewer: identical up to the wgrad atomics' order
+        assert float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)) < 1e-3, nme
+    assert res["fin"][7] == res[True][7] == 1
     for fuse in (True, False):
         for nme, a, b in zip(names, res[fuse], ref):
             # gradients pass through bf16-stored dy / dz; running statistics: fp32-accumulator statistics (fused) vs statistics of the

@@ -26,7 +26,9 @@ def main():
     ii, ki, mi, ui, vi = hdr.index("ID"), hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Unit"), hdr.index("Metric Value")
     launches = collections.OrderedDict()
     for r in rd:
-        d = launches.setdefault(int(r[ii]), {"name": r[ki].split("(")[0]})
+        nm = r[ki].split("(")[0]
+        nm = nm[5:] if nm.startswith("void ") else nm
+        d = launches.setdefault(int(r[ii]), {"name": nm.split("<")[0], "full": nm})
         v = float(r[vi].replace(",", ""))
         u = r[ui].lower()
         if "time_duration" in r[mi]:
@@ -56,6 +58,14 @@ def main():
         p["launches"] += 1; p["ms"] += d.get("ms", 0.0); p["dram_bytes"] += d.get("dram", 0.0)
     out["per_kernel"] = dict(sorted(per.items(), key=lambda kv: -kv[1]["ms"]))
     json.dump(out, open(sys.argv[3], "w"), indent=1)
+    if len(sys.argv) > 4:      # human-readable per-kernel table of the step
+        tot = out["step_ms_serialised"]
+        with open(sys.argv[4], "w") as f:
+            f.write(f"# one train step (tools/one_step.py under ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none):\n")
+            f.write(f"# {out['launches_in_step']} kernel launches, {tot:.2f} ms serialised (cold-cache per-launch times), {out['step_dram_bytes'] / 1e9:.2f} GB of DRAM traffic\n")
+            f.write(f"{'kernel':40s} {'ms':>8s} {'launches':>8s} {'share':>7s} {'DRAM GB':>9s} {'GB/s':>8s}\n")
+            for k, v in out["per_kernel"].items():
+                f.write(f"{k[:40]:40s} {v['ms']:8.3f} {v['launches']:8d} {100 * v['ms'] / tot:6.1f}% {v['dram_bytes'] / 1e9:9.3f} {v['dram_bytes'] / max(v['ms'], 1e-9) / 1e6:8.0f}\n")
     print(json.dumps({k: out[k] for k in ("launches_in_step", "step_ms_serialised", "step_dram_bytes", "conv", "doubleconv")}, indent=1))
 
 
