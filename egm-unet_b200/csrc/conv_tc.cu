@@ -35,6 +35,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// first use of a tensor map fetches its 128-byte descriptor from global memory (~1 us): start that at kernel entry, under the barrier /
+// TMEM set-up, instead of in front of the first TMA load
+__device__ __forceinline__ void tmap_prefetch(const CUtensorMap* tm) { asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tm) : "memory"); }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
                "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -309,6 +312,7 @@ __device__ __forceinline__ void issue_group(uint32_t d, uint64_t ad, uint64_t bd
 template <int EPI, int NG>      // NG epilogue groups, see k_conv_tc_halo
 __global__ void __launch_bounds__(64 + 128 * NG, 1) k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                                                           __nv_bfloat16* __restrict__ y, const float* __restrict__ bias, ConvTcParams p) { egm_pdl_enter();
+  if (threadIdx.x == 0) { tmap_prefetch(&tmX); tmap_prefetch(&tmW); }
   constexpr bool RELU = EPI == EPI_RELU;
   constexpr int NSTAT = EPI >= 16 ? EPI : 1;
   extern __shared__ uint8_t smem_raw[];
@@ -538,6 +542,7 @@ constexpr int HT_H = 16, HT_W = 8;
 template <int EPI, int NG>
 __global__ void __launch_bounds__(64 + 128 * NG, 1) k_conv_tc_halo(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                                                                __nv_bfloat16* __restrict__ y, const float* __restrict__ bias, ConvHaloParams p) { egm_pdl_enter();
+  if (threadIdx.x == 0) { tmap_prefetch(&tmX); tmap_prefetch(&tmW); }
   constexpr bool RELU = EPI == EPI_RELU;
   constexpr int NSTAT = EPI >= 16 ? EPI : 1;
   extern __shared__ uint8_t smem_raw[];
@@ -941,6 +946,7 @@ constexpr int WG_TAPS = 3;
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                                                            float* __restrict__ dwp, WgradParams p) { egm_pdl_enter();
+  if (threadIdx.x == 0) { tmap_prefetch(&tmDY); tmap_prefetch(&tmX); }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + (size_t)p.stages * p.stageBytes);
@@ -1075,6 +1081,7 @@ struct WgradHaloParams {
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc_halo(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                                                                 float* __restrict__ dwp, WgradHaloParams p) { egm_pdl_enter();
+  if (threadIdx.x == 0) { tmap_prefetch(&tmDY); tmap_prefetch(&tmX); }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + (size_t)p.stages * p.stageBytes);

@@ -170,6 +170,7 @@ class Ctx:
         # materialised concat (profiles/step_variants_r2.txt) -- what the Up kernel and the gradient slice copy save (0.25 ms) is lost
         # again because BatchNorm on a channel-strided tensor falls off the cp.async.bulk streaming kernels (+0.31 ms at 480^2)
         self.virtual_skip = os.environ.get("EGM_VIRTUAL_SKIP", "0") == "1"
+        self.split_upcat = os.environ.get("EGM_NO_SPLIT_UPCAT", "0") != "1"
         self.fuse_edge = os.environ.get("EGM_NO_EDGE_FUSE", "0") != "1"   # edge enhancer: high-pass + 1x1 conv as one composed 3x3 tcgen05 conv
         # epilogue statistics wherever the kernels support them (measured: 23.54 ms/step against 24.04 with the per-layer
         # "profitable" rule, profiles/step_variants_r2.txt); EGM_BN_STATS_PROFITABLE=1 restores the rule
@@ -832,7 +833,13 @@ def upsample_concat(ctx: Ctx, low: Var, skip) -> Var:
             ctx.push(bwd_v)
         return out
     out = Var(ctx.empty(n, h, w, cs + cu))
-    call("upsample_concat_fwd", skip.t, low.t, out.t, ctx.code, n, hl, wl, h, w, cs, cu)
+    if ctx.split_upcat and cs % 8 == 0 and cu % 8 == 0:
+        # two warp-uniform launches instead of one kernel whose warps mix pure-copy lanes (skip half) with interpolating lanes:
+        # the slice copy runs at 4.2 TB/s, the combined kernel at 2.3 TB/s (ncu, profiles/launches_r2_summary.txt)
+        call("copy_slice", skip.t, out.t, ctx.code, n * h * w, cs, cs, 0, cs + cu, 0, 0)
+        call("upsample_concat_fwd", None, low.t, out.t, ctx.code, n, hl, wl, h, w, cs, cu)
+    else:
+        call("upsample_concat_fwd", skip.t, low.t, out.t, ctx.code, n, hl, wl, h, w, cs, cu)
     if ctx.record:
         def bwd():
             d, out.grad = out.grad, None

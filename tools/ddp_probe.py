@@ -45,6 +45,10 @@ def main():
     dist.all_reduce(lo, op=dist.ReduceOp.MIN)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     log("replicas identical:", bool(torch.equal(lo, hi)))
+    # fingerprint of the trained parameters: equal (up to the split-K atomics' summation order) between runs that differ only in the
+    # step's stream concurrency (EGM_WGRAD_STREAM / EGM_BRANCH_PAR_MAXPIX) -- a race in the overlap would show up here
+    log("param fingerprint: L2 %.9e  L1 %.9e  dot(arange) %.9e" % (float(p.double().norm()), float(p.double().abs().sum()),
+        float((p.double() * torch.arange(p.numel(), device=p.device, dtype=torch.float64).remainder(97.0)).sum())))
     tr.close()
     dist.barrier()
     dist.destroy_process_group()
