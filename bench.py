@@ -338,6 +338,10 @@ def main():
     # ---- per-kernel breakdown of ONE eager step (outside the timed region).  Primary: kernel durations from CUPTI activity records
     # (hardware timestamps per kernel, keyed by the C-ABI call that launched it); fallback: windowed, queue-primed CUDA events.
     tr.use_graph = False                    # the per-kernel breakdown needs real launches
+    # ... and every kernel ALONE on the GPU: the production step overlaps the GRFB branches and the weight-gradient lane on side streams
+    # (engine.Parallel / Ctx.wgrad_async), which stretches the event delta of each overlapped kernel; the roofline inputs are
+    # per-kernel durations, so the instrumented step runs with that concurrency off (the timed region above had it on)
+    os.environ["EGM_WGRAD_STREAM"], os.environ["EGM_BRANCH_PAR_MAXPIX"] = "0", "0"
     ev_prof = primed_profile(step_resident, dev)
     launches = max(launches, sum(v["calls"] for v in ev_prof.values()))   # kernels inside one replayed graph == C-ABI launches of one eager step
     prof = abi.profile_step_cupti(step_resident)
@@ -347,7 +351,8 @@ def main():
                   "cross-check: windowed queue-primed CUDA events, which add ~5 us of event/launch overhead per call")
     else:
         prof, prof2 = ev_prof, primed_profile(step_resident, dev)
-        timing = "CUDA events per launch on the launch stream, queue primed by a spin kernel per window of 160 calls (CUPTI unavailable)"
+        timing = ("CUDA events per launch on the launch stream, queue primed by a spin kernel per window of 160 calls (CUPTI unavailable); "
+                  "instrumented eager step with the side-stream concurrency of the production step switched off, i.e. each kernel alone")
 
     def dc_ms(p):
         return sum(v["ms"] for k, v in p.items() if is_doubleconv(k, args.batch))
