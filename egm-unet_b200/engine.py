@@ -24,7 +24,9 @@ def _side_streams(device) -> List["torch.cuda.Stream"]:
     """Three side streams per device, shared by every Ctx (so the caching allocator keeps ONE pool per branch slot)."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
     if idx not in _SIDE_STREAMS:
-        _SIDE_STREAMS[idx] = [torch.cuda.Stream(device=device) for _ in range(3)]
+        # high priority like the capture stream: branch kernels ARE the dependency chain while a region is open (the weight-gradient
+        # lane, lowest priority, must not get SM slots ahead of them)
+        _SIDE_STREAMS[idx] = [torch.cuda.Stream(device=device, priority=-1) for _ in range(3)]
     return _SIDE_STREAMS[idx]
 
 
@@ -93,12 +95,18 @@ MODE_PLAIN, MODE_EDGE_GATE, MODE_RESIDUAL = 0, 1, 2
 
 class Var:
     """A dense NHWC activation [N,H,W,C] and (during backward) its gradient."""
-    __slots__ = ("t", "grad", "needs_grad")
+    __slots__ = ("t", "grad", "needs_grad", "gready")
 
     def __init__(self, t: torch.Tensor, needs_grad: bool = True):
         self.t = t
         self.grad: Optional[torch.Tensor] = None
         self.needs_grad = needs_grad
+        self.gready = None            # CUDA event: a side-stream kernel is still writing .grad (Ctx.wgrad_async); waited for on next touch
+
+    def _sync_grad(self):
+        if self.gready is not None:
+            torch.cuda.current_stream(self.t.device).wait_event(self.gready)
+            self.gready = None
 
     @property
     def shape(self):
@@ -116,6 +124,7 @@ class Var:
     def grad_target(self, partial: bool = False):
         """(tensor, accumulate_flag) to write this Var's gradient into.  partial=True: the writer
         only touches a channel slice, so a fresh buffer is zero-filled."""
+        self._sync_grad()
         if self.grad is None:
             self.grad = torch.empty_like(self.t)
             if partial:
@@ -125,6 +134,7 @@ class Var:
         return self.grad, 1
 
     def accum(self, g: torch.Tensor):
+        self._sync_grad()
         if self.grad is None:
             self.grad = g
         else:
@@ -181,6 +191,7 @@ class Ctx:
         # backward) run on one low-priority side stream instead of inside the dgrad -> BN-backward -> dgrad dependency chain
         # (measured 23.13 -> 22.10 ms/step, profiles/step_variants_r2.txt; EGM_WGRAD_STREAM=0 puts them back in line)
         self.wgrad_lane = os.environ.get("EGM_WGRAD_STREAM", "1") != "0"
+        self.skip_lane = os.environ.get("EGM_NO_SKIP_LANE", "0") != "1"     # skip-connection gradient slice copies on the lane too
         self.wgrad_lanes = max(1, min(2, int(os.environ.get("EGM_WGRAD_LANES", "1"))))
         self._w_rr = 0
         self._w_hold: list = []           # operands of wgrad kernels still in flight on the lane (kept alive until the join)
@@ -225,7 +236,7 @@ class Ctx:
         if self.record:
             self.tape.append((self._cur, fn))
 
-    def wgrad_async(self, fn: Callable, hold):
+    def wgrad_async(self, fn: Callable, hold, want_event: bool = False):
         """run fn() (one wgrad launch) on the weight-gradient lane, ordered after everything enqueued on the current stream so far"""
         cur = torch.cuda.current_stream(self.device)
         ev = torch.cuda.Event()
@@ -233,9 +244,14 @@ class Ctx:
         w = _wgrad_streams(self.device)[self._w_rr % self.wgrad_lanes]
         self._w_rr += 1
         w.wait_event(ev)
+        done = None
         with torch.cuda.stream(w):
             fn()
+            if want_event:
+                done = torch.cuda.Event()
+                done.record(w)
         self._w_hold.append(hold)
+        return done
 
     def join_wgrad(self):
         """make the current stream wait for the weight-gradient lane(s) (before anything reads the packed / bias gradients)"""
@@ -736,6 +752,7 @@ def bn_act(ctx: Ctx, z: Var, bn: nn.BatchNorm2d, act: int, mode: int = MODE_PLAI
         call("bn_act_fwd", z.t, c, 0, scale, shift, act, mode, aux.t if aux is not None else None, float(alpha), y.t, ycs, yco, ctx.code, M, c)
     if ctx.record:
         def bwd():
+            y._sync_grad()
             dy = y.grad
             if dy is None:
                 return
@@ -846,7 +863,12 @@ def upsample_concat(ctx: Ctx, low: Var, skip) -> Var:
             if d is None:
                 return
             gs, acc = skip.grad_target()
-            call("copy_slice", d, gs, ctx.code, n * h * w, cs, cs + cu, 0, cs, 0, acc)
+            if ctx.wgrad_lane and ctx.skip_lane and ctx.wplan is not None and ctx.wplan.ready and ctx._cur is None:
+                # the skip gradient is next touched a whole decoder + encoder level later (MaxPool backward of the level below, then
+                # the skip's producer): the slice copy leaves the dependency chain for the side lane; Var.gready orders the next touch
+                skip.gready = ctx.wgrad_async(lambda: call("copy_slice", d, gs, ctx.code, n * h * w, cs, cs + cu, 0, cs, 0, acc), (d, gs), want_event=True)
+            else:
+                call("copy_slice", d, gs, ctx.code, n * h * w, cs, cs + cu, 0, cs, 0, acc)
             gl = ctx.empty(n, hl, wl, cu)
             call("upsample_concat_bwd_low", d, gl, ctx.code, n, hl, wl, h, w, cs, cu)
             low.accum(gl)

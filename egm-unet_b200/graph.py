@@ -154,6 +154,7 @@ def grfb(ctx: Ctx, x: Var, m) -> Var:
     call("mul_pixel_gate", o.t, tz.t, y.t, ctx.code, M, o.C, 3, 1)
     if ctx.record:
         def bwd():
+            y._sync_grad()
             dy, y.grad = y.grad, None
             if dy is None:
                 return
