@@ -49,7 +49,8 @@ class Parallel:
 
     Memory safety under torch's stream-keyed caching allocator: (a) the main stream does nothing between fork and join; (b) a branch
     only touches tensors of its own stream or tensors allocated on the main stream BEFORE the fork, and never writes a tensor another
-    branch reads or writes (the callers keep every op that accumulates into a shared gradient outside the region); (c) every later
+    branch reads or writes (a gradient shared by several branches is accumulated through per-branch proxy Vars and summed after the
+    join, graph.grfb); (c) every later
     use of a side stream starts with a wait on a newer main-stream event, which orders it after whatever the main stream did with
     memory that has meanwhile been returned to that side stream's pool."""
 
@@ -195,6 +196,7 @@ class Ctx:
         self.wgrad_lanes = max(1, min(2, int(os.environ.get("EGM_WGRAD_LANES", "1"))))
         self._w_rr = 0
         self._w_hold: list = []           # operands of wgrad kernels still in flight on the lane (kept alive until the join)
+        self.grfb_first_in_region = os.environ.get("EGM_GRFB_FIRST_OUTSIDE", "0") != "1"   # first conv of each GRFB branch inside the parallel region
         self._cur = None                  # None = main stream, else (parallel region id, branch) -- the tag of tape entries
         self._region = 0
         self._arenas: Dict[object, list] = {}    # stream slot -> [arena, offset]: a branch zeroes and uses its own arena

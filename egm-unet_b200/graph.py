@@ -127,22 +127,37 @@ def grfb(ctx: Ctx, x: Var, m) -> Var:
     cat = Var(ctx.empty(n, h, w, c + 6 * ip))
     release_grad(ctx, cat)            # pushed first => runs after every slice consumer in backward
     copy_into(ctx, x, cat, 0)
-    # The three branches are independent after their first conv.  Those first convs all back-propagate into xe's gradient, so they
-    # stay on the main stream (their backward runs after the join); the rest of each branch runs on its own side stream where the
-    # maps are small (engine.Parallel) -- every branch writes its own channel slice of `cat` and only reads cat's gradient.
-    d = basic_conv(ctx, xe, m.branch_dir[0])
-    e = basic_conv(ctx, xe, m.branch_edge[0])
-    q = basic_conv(ctx, xe, m.branch_ctx[0])
+    # The three branches are independent except that their first convs all back-propagate into xe's gradient.  Where the maps are small
+    # (engine.Parallel) each branch runs on its own side stream, forward and backward; its first conv reads xe through a proxy Var
+    # with a private gradient, and the three private gradients are summed into xe's after the join.  Every branch writes its own
+    # channel slice of `cat` and only reads cat's gradient.
     par = ctx.parallel(M)
+    first_in = par.on and ctx.grfb_first_in_region
+    if first_in:
+        xb = [Var(xe.t), Var(xe.t), Var(xe.t)]
+        if ctx.record:
+            def bwd_sum():            # pushed before the region => runs after it (main stream, behind the join)
+                for v in xb:
+                    g, v.grad = v.grad, None
+                    if g is not None:
+                        xe.accum(g)
+            ctx.push(bwd_sum)
+    else:
+        xb = [xe, xe, xe]
+    if not first_in:                  # first convs on the main stream, one after the other (they accumulate into the same gradient)
+        d0, e0, q0 = basic_conv(ctx, xe, m.branch_dir[0]), basic_conv(ctx, xe, m.branch_edge[0]), basic_conv(ctx, xe, m.branch_ctx[0])
     with par.branch(0):
+        d = basic_conv(ctx, xb[0], m.branch_dir[0]) if first_in else d0
         d = basic_conv(ctx, d, m.branch_dir[1])
         basic_conv(ctx, d, m.branch_dir[2], out=cat, out_coff=c)
     with par.branch(1):
+        e = basic_conv(ctx, xb[1], m.branch_edge[0]) if first_in else e0
         e = edge_enhancer(ctx, e, m.branch_edge[1])
         e = basic_conv(ctx, e, m.branch_edge[2])
         e = basic_conv(ctx, e, m.branch_edge[3])
         basic_conv(ctx, e, m.branch_edge[4], out=cat, out_coff=c + 2 * ip)
     with par.branch(2):
+        q = basic_conv(ctx, xb[2], m.branch_ctx[0]) if first_in else q0
         q = basic_conv(ctx, q, m.branch_ctx[1])
         q = basic_conv(ctx, q, m.branch_ctx[2])
         basic_conv(ctx, q, m.branch_ctx[3], out=cat, out_coff=c + 4 * ip)
