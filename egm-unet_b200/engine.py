@@ -186,8 +186,8 @@ class Ctx:
         # epilogue statistics wherever the kernels support them (measured: 23.54 ms/step against 24.04 with the per-layer
         # "profitable" rule, profiles/step_variants_r2.txt); EGM_BN_STATS_PROFITABLE=1 restores the rule
         self.stats_all = os.environ.get("EGM_BN_STATS_PROFITABLE", "0") != "1"
-        # branches of a GRFB run on side streams where the maps have at most this many pixels (N*H*W); 0 = never
-        self.par_maxpix = int(os.environ.get("EGM_BRANCH_PAR_MAXPIX", "230400"))
+        # branches of a GRFB run on side streams where the maps have at most this many pixels (N*H*W; default: every GRFB level of cfg2); 0 = never
+        self.par_maxpix = int(os.environ.get("EGM_BRANCH_PAR_MAXPIX", "921600"))
         # weight-gradient lane: the tcgen05 wgrad kernels of planned convs (nothing reads their packed output before the end of
         # backward) run on one low-priority side stream instead of inside the dgrad -> BN-backward -> dgrad dependency chain
         # (measured 23.13 -> 22.10 ms/step, profiles/step_variants_r2.txt; EGM_WGRAD_STREAM=0 puts them back in line)
@@ -777,6 +777,24 @@ def bn_act(ctx: Ctx, z: Var, bn: nn.BatchNorm2d, act: int, mode: int = MODE_PLAI
                  ctx.code, M, c)
         ctx.push(bwd)
     return y
+
+
+def conv_for_bn(ctx: Ctx, x: Var, conv: nn.Conv2d, bn: nn.BatchNorm2d):
+    """The conv half of conv -> BatchNorm: (z, sums).  `sums` are the batch statistics from the conv epilogue (training, where the kernels
+    support it) for `bn_act(..., sums=sums)`, else None.  Lets a caller run the conv early / on another stream than the BN that needs
+    more inputs (the GRFB shortcut: relu(scale * fusion + BN(conv(x))))."""
+    d = conv.dilation[0]
+    assert conv.stride == (1, 1) and conv.padding[0] == d * (conv.kernel_size[0] - 1) // 2, "only stride-1 'same' convolutions"
+    co, cig, kh, kw = conv.weight.shape
+    cin = cig * conv.groups
+    training = ctx.training or bn.running_mean is None
+    route, cinp, cop = tc_route(ctx, cin, co, kh, kw, d, conv.groups, x.C != cin)
+    if (ctx.fuse_bn and route is not None and kh == kw and training and x.M > 0
+            and abi.query("conv2d_tc_stats_supported" if ctx.stats_all else "conv2d_tc_stats_profitable", cinp, cop, kh, kw, d)):
+        epi = Epi(stats=True)
+        z = conv2d(ctx, x, conv.weight, conv.bias, groups=conv.groups, dilation=d, epi=epi)
+        return z, epi.sums
+    return conv2d(ctx, x, conv.weight, conv.bias, groups=conv.groups, dilation=d), None
 
 
 def conv_bn_act(ctx: Ctx, x: Var, conv: nn.Conv2d, bn: nn.BatchNorm2d, act: int, mode: int = MODE_PLAIN, aux: Optional[Var] = None,

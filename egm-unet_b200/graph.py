@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import abi
 from .abi import call
-from .engine import (ACT_NONE, ACT_RELU, ACT_SIGMOID, MODE_PLAIN, MODE_RESIDUAL, Ctx, SkipView, Var, WSpec, _p, bn_act, conv2d, conv_bn_act, conv_module,
+from .engine import (ACT_NONE, ACT_RELU, ACT_SIGMOID, MODE_PLAIN, MODE_RESIDUAL, Ctx, SkipView, Var, WSpec, _p, bn_act, conv2d, conv_bn_act, conv_for_bn, conv_module,
                      copy_into, deconv_concat, edge_enhancer, from_nchw, maxpool2, mca_layer, out_conv, release_grad, slice_channels, to_nchw,
                      upsample_concat)
 
@@ -63,50 +63,63 @@ def fusion_conv(ctx: Ctx, cat: Var, m) -> Var:
             call("kernel_embed", dw, ctx.grad_slot(m.conv_3x3.weight), dim * dim, 7, 3, 1, 0)
         s = conv2d(ctx, f, w7, b7, wgrad_sink=sink_w7, bgrad_sink=sink_b7, wspec=spec_w7)
 
-    # spatial attention on s (SpatialAttentionModule :1189-1200)
+    # spatial attention on s (SpatialAttentionModule :1189-1200) and channel attention on f (ChannelAttentionModule :1171-1187) are
+    # independent chains of small kernels, forward and backward: two branches of a parallel region (engine.Parallel)
     mm = torch.empty(M * 2, **ctx.f32)
     amax = torch.empty(M, dtype=torch.uint8, device=ctx.device)
-    call("chan_meanmax", s.t, mm, amax, ctx.code, M, dim)
     sa = torch.empty(M, **ctx.f32)
     wsa = _p(m.spatial_attention.conv1.weight)
-    call("sa_conv_fwd", mm, wsa, sa, n, h, w)
-    # channel attention on f (ChannelAttentionModule :1171-1187)
     ca_m = m.channel_attention
     cr = ca_m.fc[0].weight.shape[0]
     avg, mx, ca = (torch.empty(n * dim, **ctx.f32) for _ in range(3))
     arg = torch.empty(n * dim, dtype=torch.int32, device=ctx.device)
-    call("gap_gmp", f.t, avg, mx, arg, torch.empty(n * dim * 12 + 16, dtype=torch.uint8, device=ctx.device), ctx.code, n, HW, dim)
     hid = torch.empty(2 * n * cr, **ctx.f32)
     w0, w2 = _p(ca_m.fc[0].weight), _p(ca_m.fc[2].weight)
-    call("ca_mlp_fwd", avg, mx, w0, w2, ca, hid, n, dim, cr)
     t = Var(ctx.empty(n, h, w, dim))
+    hold = {}                          # dt: handed from the main-stream closure to the two branch closures in backward
+    par = ctx.parallel(M)
+    with par.branch(0):
+        call("chan_meanmax", s.t, mm, amax, ctx.code, M, dim)
+        call("sa_conv_fwd", mm, wsa, sa, n, h, w)
+        if ctx.record:
+            def bwd_sa():             # dsa -> dmm -> ds
+                dt = hold.get("dt")
+                if dt is None:
+                    return
+                dsa = torch.empty(M, **ctx.f32)
+                call("pixel_dot", dt, s.t, ca, dsa, ctx.code, n, HW, dim)
+                dmm = torch.empty(M * 2, **ctx.f32)
+                gw = ctx.grad_slot(m.spatial_attention.conv1.weight)
+                if ctx.wgrad_lane and planned:      # the 7x7 weight gradient is read by nobody before the optimizer: off the dependency chain
+                    call("sa_conv_bwd", dsa, sa, mm, wsa, dmm, None, n, h, w)
+                    ctx.wgrad_async(lambda: call("sa_conv_bwd", dsa, sa, mm, wsa, None, gw, n, h, w), (dsa, sa, mm))
+                else:
+                    call("sa_conv_bwd", dsa, sa, mm, wsa, dmm, gw, n, h, w)
+                ds = ctx.empty(n, h, w, dim)
+                call("fuse_mix_bwd_s", dt, sa, ca, dmm, amax, ds, ctx.code, n, HW, dim)
+                s.accum(ds)
+            ctx.push(bwd_sa)
+    with par.branch(1):
+        call("gap_gmp", f.t, avg, mx, arg, torch.empty(n * dim * 12 + 16, dtype=torch.uint8, device=ctx.device), ctx.code, n, HW, dim)
+        call("ca_mlp_fwd", avg, mx, w0, w2, ca, hid, n, dim, cr)
+        if ctx.record:
+            def bwd_ca():             # channel-attention path + residual: df (+)= dt + davg/HW + [p == argmax] dmx
+                dt = hold.get("dt")
+                if dt is None:
+                    return
+                dca = torch.empty(n * dim, **ctx.f32)
+                call("sample_chan_dot", dt, s.t, sa, dca, ctx.code, n, HW, dim)
+                davg, dmx = torch.empty(n * dim, **ctx.f32), torch.empty(n * dim, **ctx.f32)
+                call("ca_mlp_bwd", dca, ca, avg, mx, hid, w0, w2, ctx.grad_slot(ca_m.fc[0].weight), ctx.grad_slot(ca_m.fc[2].weight),
+                     davg, dmx, n, dim, cr)
+                gf, acc = f.grad_target()
+                call("fuse_df_finish", gf, dt, davg, dmx, arg, acc, ctx.code, n, HW, dim)
+            ctx.push(bwd_ca)
+    par.join()
     call("fuse_mix_fwd", f.t, s.t, sa, ca, t.t, ctx.code, n, HW, dim)
     if ctx.record:
-        def bwd_mix():
-            dt, t.grad = t.grad, None
-            if dt is None:
-                return
-            # spatial-attention path: dsa -> dmm -> ds
-            dsa = torch.empty(M, **ctx.f32)
-            call("pixel_dot", dt, s.t, ca, dsa, ctx.code, n, HW, dim)
-            dmm = torch.empty(M * 2, **ctx.f32)
-            gw = ctx.grad_slot(m.spatial_attention.conv1.weight)
-            if ctx.wgrad_lane and planned:      # the 7x7 weight gradient is read by nobody before the optimizer: off the dependency chain
-                call("sa_conv_bwd", dsa, sa, mm, wsa, dmm, None, n, h, w)
-                ctx.wgrad_async(lambda: call("sa_conv_bwd", dsa, sa, mm, wsa, None, gw, n, h, w), (dsa, sa, mm))
-            else:
-                call("sa_conv_bwd", dsa, sa, mm, wsa, dmm, gw, n, h, w)
-            ds = ctx.empty(n, h, w, dim)
-            call("fuse_mix_bwd_s", dt, sa, ca, dmm, amax, ds, ctx.code, n, HW, dim)
-            s.accum(ds)
-            # channel-attention path + residual: df (+)= dt + davg/HW + [p == argmax] dmx
-            dca = torch.empty(n * dim, **ctx.f32)
-            call("sample_chan_dot", dt, s.t, sa, dca, ctx.code, n, HW, dim)
-            davg, dmx = torch.empty(n * dim, **ctx.f32), torch.empty(n * dim, **ctx.f32)
-            call("ca_mlp_bwd", dca, ca, avg, mx, hid, w0, w2, ctx.grad_slot(ca_m.fc[0].weight), ctx.grad_slot(ca_m.fc[2].weight),
-                 davg, dmx, n, dim, cr)
-            gf, acc = f.grad_target()
-            call("fuse_df_finish", gf, dt, davg, dmx, arg, acc, ctx.code, n, HW, dim)
+        def bwd_mix():                # runs first in backward (main stream): publish dt, then the two branch closures follow
+            hold["dt"], t.grad = t.grad, None
         ctx.push(bwd_mix)
     return conv_module(ctx, t, m.up)
 
@@ -144,6 +157,17 @@ def grfb(ctx: Ctx, x: Var, m) -> Var:
             ctx.push(bwd_sum)
     else:
         xb = [xe, xe, xe]
+    zs = None
+    if first_in:                      # the shortcut's 1x1 conv only needs x: it joins branch 0; its BN (needs the fusion output) stays behind
+        xs = Var(x.t)
+        if ctx.record:
+            def bwd_sum_x():
+                g, xs.grad = xs.grad, None
+                if g is not None:
+                    x.accum(g)
+            ctx.push(bwd_sum_x)
+        with par.branch(0):
+            zs, zs_sums = conv_for_bn(ctx, xs, m.shortcut.conv, m.shortcut.bn)
     if not first_in:                  # first convs on the main stream, one after the other (they accumulate into the same gradient)
         d0, e0, q0 = basic_conv(ctx, xe, m.branch_dir[0]), basic_conv(ctx, xe, m.branch_edge[0]), basic_conv(ctx, xe, m.branch_ctx[0])
     with par.branch(0):
@@ -163,7 +187,10 @@ def grfb(ctx: Ctx, x: Var, m) -> Var:
         basic_conv(ctx, q, m.branch_ctx[3], out=cat, out_coff=c + 4 * ip)
     par.join()
     fo = fusion_conv(ctx, cat, m.fusion_conv)
-    o = conv_bn_act(ctx, x, m.shortcut.conv, m.shortcut.bn, ACT_NONE, MODE_RESIDUAL, aux=fo, alpha=float(m.scale))
+    if zs is not None:
+        o = bn_act(ctx, zs, m.shortcut.bn, ACT_NONE, MODE_RESIDUAL, aux=fo, alpha=float(m.scale), sums=zs_sums)
+    else:
+        o = conv_bn_act(ctx, x, m.shortcut.conv, m.shortcut.bn, ACT_NONE, MODE_RESIDUAL, aux=fo, alpha=float(m.scale))
     tz = conv_module(ctx, o, m.target_enhancer[0])          # [N,H,W,3]
     y = Var(ctx.empty(n, h, w, o.C))
     call("mul_pixel_gate", o.t, tz.t, y.t, ctx.code, M, o.C, 3, 1)
