@@ -36,7 +36,8 @@ _WGRAD_STREAMS: Dict[int, List["torch.cuda.Stream"]] = {}
 def _wgrad_streams(device) -> List["torch.cuda.Stream"]:
     idx = device.index if device.index is not None else torch.cuda.current_device()
     if idx not in _WGRAD_STREAMS:
-        _WGRAD_STREAMS[idx] = [torch.cuda.Stream(device=device, priority=0) for _ in range(2)]   # lowest priority: never ahead of the dgrad chain
+        prio = int(os.environ.get("EGM_WGRAD_PRIO", "0"))          # 0 = lowest priority: never ahead of the dgrad chain (A/B knob: -1)
+        _WGRAD_STREAMS[idx] = [torch.cuda.Stream(device=device, priority=prio) for _ in range(2)]
     return _WGRAD_STREAMS[idx]
 
 
