@@ -83,3 +83,58 @@ def test_init_distributed_mode_without_rendezvous_env(capsys, monkeypatch):
     args = argparse.Namespace(dist_url="env://")
     train_utils.init_distributed_mode(args)
     assert args.distributed is False and "Not using distributed mode" in capsys.readouterr().out
+
+
+def test_integration_doc_maps_every_header_symbol():
+    """INTEGRATION.md is the reference-side binding guide: every entry point include/egm_b200.h declares must be named there
+    (`egm_x_fwd/bwd` shorthand counts for both directions)."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "egm_b200.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    syms = list(dict.fromkeys(re.findall(r"\b(egm_\w+)\s*\(", hdr)))
+    assert len(syms) >= 90
+    missing = [s for s in syms if s not in doc and not (s.endswith(("_fwd", "_bwd")) and s[:-4] in doc)]
+    assert not missing, missing
+
+
+def test_bench_family_bookkeeping_knows_the_view_entry_points():
+    """bench.py's HBM-family table keys on C-ABI call names: the strided MaxPool forms and the fused Up path must land in their families."""
+    b = _bench()
+    assert b.hbm_family_bytes("maxpool2x2_fwd_view:64,0,1,16,480,480,32") == ("pool", 16 * 480 * 480 * 32 * 2 * 1.25)
+    assert b.hbm_family_bytes("maxpool2x2_bwd_view:32,0,32,0,1,1,16,480,480,32")[0] == "pool"
+    fam, nbytes = b.hbm_family_bytes("upsample_concat_fwd:1,16,240,240,480,480,32,32")
+    assert fam == "upsample_concat" and nbytes == (16 * 240 * 240 * 32 + 16 * 480 * 480 * 32 + 16 * 480 * 480 * 64) * 2
+    assert b.is_doubleconv("conv2d_tc_ex:32,0,32,32,0,32,0,16,480,480,32,32,3,3,1,0") and b.is_doubleconv("conv2d_wgrad_tc_view:64,0,64,32,0,32,16,480,480,64,32,3,3,1")
+    assert not b.is_doubleconv("conv2d_tc_view:16,0,16,16,0,16,0,16,240,240,16,16,1,1,1")
+
+
+def test_ncu_conv_traffic_matches_launches_to_calls(tmp_path):
+    """tools/ncu_conv_traffic.py: the i-th conv kernel of an ncu launch list is the i-th conv call of the step's call log; DRAM bytes of
+    the DoubleConv launches are summed per step (bench.py's roofline.traffic)."""
+    import json
+    import subprocess
+    hdr = '"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"'
+    rows = [hdr]
+
+    def add(i, name, ns, rd, wr):
+        base = f'"{i}","1","python","h","{name}","1","7","(192, 1, 1)","(148, 1, 1)","0","10.0","Command line profiler metrics"'
+        rows.append(base + f',"dram__bytes_read.sum","Mbyte","{rd}"')
+        rows.append(base + f',"dram__bytes_write.sum","Kbyte","{wr}"')
+        rows.append(base + f',"gpu__time_duration.sum","us","{ns}"')
+    add(0, "void k_nchw_to_nhwc<__nv_bfloat16>(const float *, T1 *, long long, int, long long)", 20.0, 44.0, 1.0)
+    add(1, "void k_conv_tc_halo<32, 1>(CUtensorMap_st, CUtensorMap_st, __nv_bfloat16 *, const float *, ConvHaloParams)", 150.0, 236.0, 186000.0)
+    add(2, "void k_conv_tc_halo<0, 1>(CUtensorMap_st, CUtensorMap_st, __nv_bfloat16 *, const float *, ConvHaloParams)", 25.0, 30.0, 100.0)
+    add(3, "k_wgrad_tc_halo(CUtensorMap_st, CUtensorMap_st, float *, WgradHaloParams)", 120.0, 480.0, 4000.0)
+    csvp, callp, outp = tmp_path / "l.csv", tmp_path / "c.txt", tmp_path / "o.json"
+    csvp.write_text("==PROF== noise\n" + "\n".join(rows) + "\n")
+    callp.write_text("nchw_to_nhwc:0,16,3,480,480\n"
+                     "conv2d_tc_ex:32,0,32,32,0,32,0,16,480,480,32,32,3,3,1,0\n"
+                     "conv2d_tc_view:16,0,16,16,0,16,0,16,240,240,16,16,1,1,1\n"
+                     "bn_act_fwd:32,0,1,0,32,0,1,3686400,32\n"
+                     "conv2d_wgrad_tc_view:32,0,32,32,0,32,16,480,480,32,32,3,3,1\n")
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "ncu_conv_traffic.py"), str(csvp), str(callp), str(outp)], stdout=subprocess.DEVNULL)
+    o = json.load(open(outp))
+    assert o["launches_in_step"] == 4 and o["conv"]["launches"] == 3
+    assert o["doubleconv"]["launches"] == 2                                    # the 16->16 1x1 is not a DoubleConv layer
+    assert abs(o["doubleconv_dram_bytes_per_step"] - (236e6 + 186e6 + 480e6 + 4e6)) < 1.0
+    assert abs(o["doubleconv"]["ms"] - 0.27) < 1e-9
