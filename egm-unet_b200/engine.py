@@ -265,7 +265,8 @@ class Ctx:
             self._w_hold = []
 
     def parallel(self, pixels: int) -> Parallel:
-        return Parallel(self, 0 < pixels <= self.par_maxpix)
+        # regions do not nest: the tape replays them as a flat fork / join sequence on the main stream
+        return Parallel(self, 0 < pixels <= self.par_maxpix and self._cur is None)
 
     def backward(self, after_each: Optional[Callable] = None):
         """Replay the tape in reverse.  Entries recorded inside a Parallel region run on their branch's side stream (forked from the
